@@ -1,0 +1,559 @@
+// (c) GVP denoiser on flat tensors + dst-sorted CSR.
+//
+// Replaces LigRecDynamicsGVP.forward (models/dynamics_gvp.py:149-199), LigRecGVP.forward and
+// NoisePredictionBlock (:38-101), GVPMultiEdgeConv.forward/message (models/gvp.py:459-550),
+// GVP.forward (:89-116), GVPLayerNorm (:152-166), _rbf (:26-41), _norm_no_nan (:12-19).
+//
+// One device routine, gvp_tile(), applies a GVP to a tile of 64 rows held in shared memory
+// (scalars [64 x (fin+h)], vectors [64 x v x 3]); it is the body of
+//   gvp_edge_kernel  -- gather (s_src, v_src, unit x_diff, rbf(d)) per edge, chain the message
+//                       GVPs in shared memory, deterministic segmented reduction by destination
+//                       (no per-edge message ever reaches HBM);
+//   gvp_node_kernel  -- recombine messages, /norm, residual, GVPLayerNorm, update GVPs,
+//                       residual, GVPLayerNorm (gvp.py:501-536);
+//   gvp_head_kernel  -- NoisePredictionBlock: noise GVPs + Linear(64 -> atom_nf).
+// The scalar contraction [64 x (fin+h)] @ WfT is the shared tile GEMM of common.cuh.
+//
+// Offsets array (float offsets into the packed blob), in this order:
+//   globals [8]:  lig_enc.WT, b, ln.w, ln.b, kp_enc.WT, b, ln.w, ln.b
+//   per conv l:   for et in etypes(l):  n_message_gvps x (Wh, Wu, WfT, bf, WgT, bg)
+//                 for nt in dst(l):     n_update_gvps  x (Wh, Wu, WfT, bf, WgT, bg),
+//                                       msg_ln.w, msg_ln.b, upd_ln.w, upd_ln.b
+//   head:         n_noise_gvps x (Wh, Wu, WfT, bf, WgT, bg), WoT, bo
+//   etypes(l) = (ll, kl, lk, kk) if update_kp and l != n_convs-1 else (ll, kl)
+#include "common.cuh"
+#include <string.h>
+#include <vector>
+
+namespace kpd {
+
+constexpr int VMAX = 17;   // vector channels held per row (vector_size + 1 for x_diff)
+constexpr int MAXG = 4;    // GVPs chained per kernel
+
+struct GvpW {
+    const float* Wh;    // [vin][hd]
+    const float* Wu;    // [hd][vout]
+    const float* WfT;   // [fin+hd][ldf]
+    const float* bf;    // [ldf]
+    const float* WgT;   // [fout][vout]
+    const float* bg;    // [vout]
+    int vin, vout, hd, fin, fout, ldf, sigmoid_gate;
+};
+
+// GVP.forward (models/gvp.py:89-116) on a shared-memory tile of TE rows.
+//   S: [TE][lds], input scalars in cols [0,fin); V: [TE][VMAX][3] input vectors (vin used).
+//   On return S cols [0,fout) hold feats_out and V rows [0,vout) hold the gated vectors.
+__device__ void gvp_tile(const GvpW& g, float* S, int lds, float* V, float* Vh, float* Bs) {
+    const int tid = threadIdx.x;
+    // Vh = einsum('b v c, v h -> b h c'); sh = sqrt(clamp(sum_c Vh^2, 1e-8))  (:96, :99)
+    for (int idx = tid; idx < TE * g.hd; idx += NT) {
+        const int r = idx / g.hd, hh = idx - r * g.hd;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        const float* v = V + r * (VMAX * 3);
+        for (int k = 0; k < g.vin; ++k) {
+            const float w = g.Wh[k * g.hd + hh];
+            a0 = fmaf(v[3 * k], w, a0); a1 = fmaf(v[3 * k + 1], w, a1); a2 = fmaf(v[3 * k + 2], w, a2);
+        }
+        float* o = Vh + r * (VMAX * 3) + 3 * hh;
+        o[0] = a0; o[1] = a1; o[2] = a2;
+        S[r * lds + g.fin + hh] = sqrtf(fmaxf(a0 * a0 + a1 * a1 + a2 * a2, 1e-8f));
+    }
+    __syncthreads();
+    // Vu = einsum('b h c, h u -> b u c')  (:97) -> V (the input vectors are dead now)
+    for (int idx = tid; idx < TE * g.vout; idx += NT) {
+        const int r = idx / g.vout, u = idx - r * g.vout;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        const float* vh = Vh + r * (VMAX * 3);
+        for (int k = 0; k < g.hd; ++k) {
+            const float w = g.Wu[k * g.vout + u];
+            a0 = fmaf(vh[3 * k], w, a0); a1 = fmaf(vh[3 * k + 1], w, a1); a2 = fmaf(vh[3 * k + 2], w, a2);
+        }
+        float* o = V + r * (VMAX * 3) + 3 * u;
+        o[0] = a0; o[1] = a1; o[2] = a2;
+    }
+    // feats_out = SiLU(Linear(cat(feats, sh)))  (:101-103)
+    float acc[TE / 16][16];
+#pragma unroll
+    for (int i = 0; i < TE / 16; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+    const int nmain = (g.fout + 3) & ~3;
+    tile_gemm<TE / 16>(S, lds, g.WfT, g.ldf, g.fin + g.hd, nmain, Bs, acc);
+    {
+        const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+        for (int i = 0; i < TE / 16; ++i) {
+            const int r = ty * (TE / 16) + i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = 4 * tx + 64 * j;
+                if (col < nmain) {
+                    float4 o;
+                    o.x = silu_f(acc[i][4 * j + 0] + g.bf[col + 0]);
+                    o.y = silu_f(acc[i][4 * j + 1] + g.bf[col + 1]);
+                    o.z = silu_f(acc[i][4 * j + 2] + g.bf[col + 2]);
+                    o.w = silu_f(acc[i][4 * j + 3] + g.bf[col + 3]);
+                    *reinterpret_cast<float4*>(S + r * lds + col) = o;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // gating = Linear(feats_out); vectors_out = act(gating) * Vu  (:105-111)
+    for (int idx = tid; idx < TE * g.vout; idx += NT) {
+        const int r = idx / g.vout, u = idx - r * g.vout;
+        float a = g.bg[u];
+        const float* s = S + r * lds;
+        for (int k = 0; k < g.fout; ++k) a = fmaf(s[k], g.WgT[k * g.vout + u], a);
+        if (g.sigmoid_gate) a = sigmoid_f(a);
+        float* o = V + r * (VMAX * 3) + 3 * u;
+        o[0] *= a; o[1] *= a; o[2] *= a;
+    }
+    __syncthreads();
+}
+
+// scalar LayerNorm over S cols [0,Sdim) (one warp per row) + GVP vector norm (gvp.py:159-166)
+__device__ void gvp_layernorm_tile(float* S, int lds, int Sdim, float* V, int nv, const float* w, const float* b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = 0; rr < TE / 8; ++rr) {
+        const int r = warp * (TE / 8) + rr;
+        float* x = S + r * lds;
+        float s = 0.f;
+        for (int c = lane; c < Sdim; c += 32) s += x[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)Sdim;
+        float v = 0.f;
+        for (int c = lane; c < Sdim; c += 32) { const float d = x[c] - mean; v += d * d; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = 1.0f / sqrtf(v / (float)Sdim + 1e-5f);
+        for (int c = lane; c < Sdim; c += 32) x[c] = (x[c] - mean) * rstd * w[c] + b[c];
+        // vn = sqrt(mean_v clamp(|v|^2, 1e-8) + eps) + eps
+        float* vv = V + r * (VMAX * 3);
+        float q = 0.f;
+        for (int k = lane; k < nv; k += 32)
+            q += fmaxf(vv[3 * k] * vv[3 * k] + vv[3 * k + 1] * vv[3 * k + 1] + vv[3 * k + 2] * vv[3 * k + 2], 1e-8f);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float vn = sqrtf(q / (float)nv + 1e-5f) + 1e-5f;
+        for (int k = lane; k < 3 * nv; k += 32) vv[k] = vv[k] / vn;
+    }
+    __syncthreads();
+}
+
+struct GvpSmem {
+    float *S, *Bs, *V, *Vh;
+    int* src_s; int* dst_s;
+};
+
+__device__ __forceinline__ GvpSmem gvp_carve_smem(float* smem, int lds) {
+    GvpSmem m;
+    m.S = smem;
+    m.Bs = m.S + TE * lds;
+    m.V = m.Bs + BS_FLOATS;
+    m.Vh = m.V + TE * VMAX * 3;
+    m.src_s = reinterpret_cast<int*>(m.Vh + TE * VMAX * 3);
+    m.dst_s = m.src_s + TE;
+    return m;
+}
+
+static size_t gvp_smem_bytes(int lds) {
+    return sizeof(float) * ((size_t)TE * lds + BS_FLOATS + 2 * TE * VMAX * 3) + sizeof(int) * 2 * TE;
+}
+
+struct GvpEtypeArgs {
+    const int* rowptr; const int* src; const int* dst; int n_dst;
+    const float* s_src; const float* v_src; const float* xs; const float* xd;
+    GvpW msg[MAXG];
+    float* sm; float* vm; float* part;
+};
+
+struct GvpEdgeLaunch {
+    GvpEtypeArgs e[4];
+    int Sdim, Vdim, n_msg, lds, pw, rbf_dim;
+    float rbf_step, rbf_sigma;
+};
+
+__global__ void __launch_bounds__(NT, 1) gvp_edge_kernel(const GvpEdgeLaunch L) {
+    const GvpEtypeArgs& a = L.e[blockIdx.y];
+    const int E = a.rowptr[a.n_dst];
+    const int tile_begin = blockIdx.x * TE;
+    if (tile_begin >= E) return;
+    const int n = min(TE, E - tile_begin);
+    extern __shared__ __align__(16) float smem[];
+    GvpSmem m = gvp_carve_smem(smem, L.lds);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Sd = L.Sdim, Vd = L.Vdim, lds = L.lds;
+
+    zero_stage(m.Bs);
+    if (tid < TE) {
+        const int e = tile_begin + min(tid, n - 1);
+        const int s = a.src[e], d = a.dst[e];
+        m.src_s[tid] = s;
+        m.dst_s[tid] = d;
+        // gvp.py:474-480: x_diff, dij = sqrt(clamp(|x_diff|^2,1e-8)) + 1e-8, unit vector, rbf(dij)
+        const float dx = a.xs[3 * s] - a.xd[3 * d], dy = a.xs[3 * s + 1] - a.xd[3 * d + 1],
+                    dz = a.xs[3 * s + 2] - a.xd[3 * d + 2];
+        const float dij = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-8f)) + 1e-8f;
+        float* v0 = m.V + tid * (VMAX * 3);
+        v0[0] = dx / dij; v0[1] = dy / dij; v0[2] = dz / dij;
+        float* srow = m.S + tid * lds + Sd;
+        for (int k = 0; k < L.rbf_dim; ++k) {
+            const float z = (dij - (float)k * L.rbf_step) / L.rbf_sigma;
+            srow[k] = expf(-(z * z));
+        }
+    }
+    __syncthreads();
+    // gather s_src (float4 rows) and v_src
+    for (int rr = 0; rr < TE / 8; ++rr) {
+        const int r = warp * (TE / 8) + rr;
+        const float* sp = a.s_src + (size_t)m.src_s[r] * Sd;
+        for (int f = lane; f < (Sd >> 2); f += 32)
+            *reinterpret_cast<float4*>(m.S + r * lds + 4 * f) = *reinterpret_cast<const float4*>(sp + 4 * f);
+        const float* vp = a.v_src + (size_t)m.src_s[r] * (Vd * 3);
+        for (int k = lane; k < Vd * 3; k += 32) m.V[r * (VMAX * 3) + 3 + k] = vp[k];
+    }
+    __syncthreads();
+    for (int i = 0; i < L.n_msg; ++i) gvp_tile(a.msg[i], m.S, lds, m.V, m.Vh, m.Bs);
+
+    SegOut o;
+    o.part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
+    o.part1 = a.part + ((size_t)blockIdx.x * 2 + 1) * L.pw;
+    o.out = a.sm; o.ld_out = Sd;
+    for (int col = tid; col < Sd; col += NT)
+        seg_reduce_column(m.S, lds, col, n, m.dst_s, a.rowptr, tile_begin, o, col);
+    if (tid < Vd * 3) {
+        SegOut ov = o;
+        ov.out = a.vm; ov.ld_out = Vd * 3;
+        ov.part0 += Sd; ov.part1 += Sd;
+        seg_reduce_column(m.V, VMAX * 3, tid, n, m.dst_s, a.rowptr, tile_begin, ov, tid);
+    }
+}
+
+struct GvpNodeArgs {
+    int n, Sdim, Vdim, lds, pw, n_upd, n_et;
+    float* s; float* v;                        // node features, updated in place
+    const int* rowptr[2]; const float* sm[2]; const float* vm[2]; const float* part[2];
+    int norm_mode; float norm_const;           // 0 const, 1 per-etype mean, 2 mean in-degree + 1
+    const int* node_batch; const int* ptr;
+    GvpW upd[MAXG];
+    const float *mln_w, *mln_b, *uln_w, *uln_b;
+};
+
+__global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    GvpSmem m = gvp_carve_smem(smem, a.lds);
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * TE;
+    const int n = min(TE, a.n - n0);
+    const int Sd = a.Sdim, Vd = a.Vdim, lds = a.lds, W = Sd + 3 * Vd;
+    zero_stage(m.Bs);
+    // features + aggregated messages / norm  (gvp.py:501-520)
+    for (int idx = tid; idx < TE * W; idx += NT) {
+        const int r = idx / W, c = idx - r * W;
+        const int nd = n0 + min(r, n - 1);
+        float msg = 0.f;
+        for (int e = 0; e < a.n_et; ++e) {
+            const int r0 = a.rowptr[e][nd], r1 = a.rowptr[e][nd + 1];
+            float g = c < Sd ? seg_gather(a.sm[e], Sd, a.part[e], a.pw, r0, r1, nd, c)
+                             : seg_gather(a.vm[e], 3 * Vd, a.part[e] + Sd, a.pw, r0, r1, nd, c - Sd);
+            if (a.norm_mode == 1) g = g / (float)max(r1 - r0, 1);      // fn.mean per edge type
+            msg += g;
+        }
+        float nv = a.norm_const;
+        if (a.norm_mode == 1) nv = 1.0f;
+        else if (a.norm_mode == 2) {
+            const int b = a.node_batch[nd];
+            const int p0 = a.ptr[b], p1 = a.ptr[b + 1];
+            int tot = 0;
+            for (int e = 0; e < a.n_et; ++e) tot += a.rowptr[e][p1] - a.rowptr[e][p0];
+            nv = (float)tot / (float)(p1 - p0) + 1.0f;
+        }
+        msg = msg / nv;
+        if (c < Sd) m.S[r * lds + c] = a.s[(size_t)nd * Sd + c] + msg;
+        else m.V[r * (VMAX * 3) + (c - Sd)] = a.v[(size_t)nd * (3 * Vd) + (c - Sd)] + msg;
+    }
+    __syncthreads();
+    gvp_layernorm_tile(m.S, lds, Sd, m.V, Vd, a.mln_w, a.mln_b);
+    // stash the normalised features as the residual (rows of this CTA only)
+    for (int idx = tid; idx < n * W; idx += NT) {
+        const int r = idx / W, c = idx - r * W;
+        if (c < Sd) a.s[(size_t)(n0 + r) * Sd + c] = m.S[r * lds + c];
+        else a.v[(size_t)(n0 + r) * (3 * Vd) + (c - Sd)] = m.V[r * (VMAX * 3) + (c - Sd)];
+    }
+    __syncthreads();
+    for (int i = 0; i < a.n_upd; ++i) gvp_tile(a.upd[i], m.S, lds, m.V, m.Vh, m.Bs);
+    for (int idx = tid; idx < TE * W; idx += NT) {
+        const int r = idx / W, c = idx - r * W;
+        const int nd = n0 + min(r, n - 1);
+        if (c < Sd) m.S[r * lds + c] += a.s[(size_t)nd * Sd + c];
+        else m.V[r * (VMAX * 3) + (c - Sd)] += a.v[(size_t)nd * (3 * Vd) + (c - Sd)];
+    }
+    __syncthreads();
+    gvp_layernorm_tile(m.S, lds, Sd, m.V, Vd, a.uln_w, a.uln_b);
+    for (int idx = tid; idx < n * W; idx += NT) {
+        const int r = idx / W, c = idx - r * W;
+        if (c < Sd) a.s[(size_t)(n0 + r) * Sd + c] = m.S[r * lds + c];
+        else a.v[(size_t)(n0 + r) * (3 * Vd) + (c - Sd)] = m.V[r * (VMAX * 3) + (c - Sd)];
+    }
+}
+
+struct GvpHeadArgs {
+    int n, Sdim, Vdim, lds, n_gvps, F, Fp, hid_out;
+    const float* s; const float* v;
+    GvpW g[MAXG];
+    const float* WoT; const float* bo;
+    float* eps_h; float* eps_x;
+};
+
+__global__ void __launch_bounds__(NT, 1) gvp_head_kernel(const GvpHeadArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    GvpSmem m = gvp_carve_smem(smem, a.lds);
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * TE;
+    const int n = min(TE, a.n - n0);
+    const int Sd = a.Sdim, Vd = a.Vdim, lds = a.lds, W = Sd + 3 * Vd;
+    zero_stage(m.Bs);
+    for (int idx = tid; idx < TE * W; idx += NT) {
+        const int r = idx / W, c = idx - r * W;
+        const int nd = n0 + min(r, n - 1);
+        if (c < Sd) m.S[r * lds + c] = a.s[(size_t)nd * Sd + c];
+        else m.V[r * (VMAX * 3) + (c - Sd)] = a.v[(size_t)nd * (3 * Vd) + (c - Sd)];
+    }
+    __syncthreads();
+    for (int i = 0; i < a.n_gvps; ++i) gvp_tile(a.g[i], m.S, lds, m.V, m.Vh, m.Bs);
+    // to_scalar_output + vectors.squeeze(1)  (dynamics_gvp.py:42-43)
+    for (int idx = tid; idx < n * (a.F + 3); idx += NT) {
+        const int r = idx / (a.F + 3), c = idx - r * (a.F + 3);
+        if (c < a.F) {
+            float s = a.bo[c];
+            for (int k = 0; k < a.hid_out; ++k) s = fmaf(m.S[r * lds + k], a.WoT[k * a.Fp + c], s);
+            a.eps_h[(size_t)(n0 + r) * a.F + c] = s;
+        } else {
+            a.eps_x[(size_t)(n0 + r) * 3 + (c - a.F)] = m.V[r * (VMAX * 3) + (c - a.F)];
+        }
+    }
+}
+
+}  // namespace kpd
+
+using namespace kpd;
+
+struct GvpLayerW {
+    int n_et, n_dst;
+    GvpW msg[4][MAXG];
+    GvpW upd[2][MAXG];
+    const float *mln_w[2], *mln_b[2], *uln_w[2], *uln_b[2];
+};
+
+struct kpd_gvp_model {
+    kpd_gvp_config cfg;
+    int S, Sp, V, F, Fp, C, lds, pw;
+    const float* lig_enc[4]; const float* kp_enc[4];
+    std::vector<GvpLayerW> layers;
+    GvpW head[MAXG];
+    const float* WoT; const float* bo;
+    size_t smem;
+};
+
+struct GvpWs {
+    float *s[2], *v[2], *sm[4], *vm[4], *part[4], *tin, *tenc;
+};
+
+static int gvp_ntiles(int cap) { return cdiv(cap > 0 ? cap : 1, TE) + 1; }
+
+static GvpWs gvp_carve(const kpd_gvp_model* m, const kpd_batch* b, const int caps[4], void* ws, int64_t* bytes) {
+    GvpWs w;
+    Carver c(ws);
+    const int N[2] = {b->n_lig, b->n_kp};
+    const int maxN = N[0] > N[1] ? N[0] : N[1];
+    for (int nt = 0; nt < 2; ++nt) {
+        w.s[nt] = c.take<float>((int64_t)N[nt] * m->S);
+        w.v[nt] = c.take<float>((int64_t)N[nt] * m->V * 3);
+    }
+    const int dstN[4] = {N[0], N[0], N[1], N[1]};
+    for (int e = 0; e < 4; ++e) {
+        w.sm[e] = c.take<float>((int64_t)dstN[e] * m->S);
+        w.vm[e] = c.take<float>((int64_t)dstN[e] * m->V * 3);
+        w.part[e] = c.take<float>((int64_t)gvp_ntiles(caps[e]) * 2 * m->pw);
+    }
+    const int win = (m->F > m->C ? m->F : m->C) + 1;
+    w.tin = c.take<float>((int64_t)maxN * win);
+    w.tenc = c.take<float>((int64_t)maxN * m->S);
+    if (bytes) *bytes = c.bytes();
+    return w;
+}
+
+extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, const int64_t* off, int32_t n_off,
+                              kpd_gvp_model** out) {
+    KPD_REQUIRE(cfg && blob && off && out, "kpd_gvp_create: null argument");
+    KPD_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0, "kpd_gvp_create: blob must be 16-byte aligned");
+    KPD_REQUIRE(cfg->vector_size >= 1 && cfg->vector_size + 1 <= VMAX, "kpd_gvp_create: vector_size %d unsupported (max %d)", cfg->vector_size, VMAX - 1);
+    KPD_REQUIRE(cfg->n_hidden_scalars % 4 == 0 && cfg->n_hidden_scalars <= 256, "kpd_gvp_create: n_hidden_scalars must be a multiple of 4 and <= 256 (got %d)", cfg->n_hidden_scalars);
+    KPD_REQUIRE(cfg->n_message_gvps >= 1 && cfg->n_message_gvps <= MAXG && cfg->n_update_gvps >= 1 && cfg->n_update_gvps <= MAXG &&
+                cfg->n_noise_gvps >= 1 && cfg->n_noise_gvps <= MAXG, "kpd_gvp_create: at most %d GVPs per block", MAXG);
+    KPD_REQUIRE(cfg->rbf_dim >= 2 && cfg->rbf_dim <= 32, "kpd_gvp_create: rbf_dim %d unsupported", cfg->rbf_dim);
+    auto* m = new kpd_gvp_model();
+    m->cfg = *cfg;
+    m->S = cfg->n_hidden_scalars; m->Sp = m->S; m->V = cfg->vector_size;
+    m->F = cfg->n_lig_scalars; m->Fp = (m->F + 3) & ~3; m->C = cfg->n_kp_scalars;
+    {   // widest row any GVP of this model reads or writes: message GVP 0 reads S+rbf+V+1 columns,
+        // the last noise GVP writes 64 (dynamics_gvp.py:12) even when S < 64
+        int wmax = m->S + cfg->rbf_dim + m->V + 1;
+        if (wmax < 64 + m->V) wmax = 64 + m->V;
+        m->lds = tile_ld(wmax);
+    }
+    m->pw = ((m->S + 3 * m->V) + 3) & ~3;
+    int i = 0;
+    auto P = [&](void) -> const float* { int64_t o = off[i++]; return o < 0 ? nullptr : blob + o; };
+    auto G = [&](int vin, int vout, int fin, int fout, int sig) {
+        GvpW g;
+        g.vin = vin; g.vout = vout; g.hd = vin > vout ? vin : vout; g.fin = fin; g.fout = fout;
+        g.ldf = (fout + 3) & ~3; g.sigmoid_gate = sig;
+        g.Wh = P(); g.Wu = P(); g.WfT = P(); g.bf = P(); g.WgT = P(); g.bg = P();
+        return g;
+    };
+    int expect = 8 + cfg->n_noise_gvps * 6 + 2;
+    for (int l = 0; l < cfg->n_convs; ++l) {
+        const bool full = cfg->update_kp && l != cfg->n_convs - 1;
+        expect += (full ? 4 : 2) * cfg->n_message_gvps * 6 + (full ? 2 : 1) * (cfg->n_update_gvps * 6 + 4);
+    }
+    if (n_off != expect) { delete m; KPD_REQUIRE(false, "kpd_gvp_create: expected %d offsets, got %d", expect, n_off); }
+    for (int k = 0; k < 4; ++k) m->lig_enc[k] = P();
+    for (int k = 0; k < 4; ++k) m->kp_enc[k] = P();
+    m->layers.resize(cfg->n_convs);
+    for (int l = 0; l < cfg->n_convs; ++l) {
+        GvpLayerW& L = m->layers[l];
+        const bool full = cfg->update_kp && l != cfg->n_convs - 1;
+        L.n_et = full ? 4 : 2;
+        L.n_dst = full ? 2 : 1;
+        for (int e = 0; e < L.n_et; ++e)
+            for (int k = 0; k < cfg->n_message_gvps; ++k)
+                L.msg[e][k] = k == 0 ? G(m->V + 1, m->V, m->S + cfg->rbf_dim, m->S, 1) : G(m->V, m->V, m->S, m->S, 1);
+        for (int nt = 0; nt < L.n_dst; ++nt) {
+            for (int k = 0; k < cfg->n_update_gvps; ++k) L.upd[nt][k] = G(m->V, m->V, m->S, m->S, 1);
+            L.mln_w[nt] = P(); L.mln_b[nt] = P(); L.uln_w[nt] = P(); L.uln_b[nt] = P();
+        }
+    }
+    for (int k = 0; k < cfg->n_noise_gvps; ++k) {
+        const bool last = k == cfg->n_noise_gvps - 1;
+        m->head[k] = last ? G(m->V, 1, m->S, 64, 0) : G(m->V, m->V, m->S, m->S, 1);   // dynamics_gvp.py:18-25
+    }
+    m->WoT = P(); m->bo = P();
+    m->smem = gvp_smem_bytes(m->lds);
+    cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
+    cudaError_t e2 = cudaFuncSetAttribute(gvp_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
+    cudaError_t e3 = cudaFuncSetAttribute(gvp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        delete m;
+        KPD_REQUIRE(false, "kpd_gvp_create: cannot set the dynamic shared memory size of the GVP kernels");
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void kpd_gvp_destroy(kpd_gvp_model* m) { delete m; }
+
+extern "C" int kpd_gvp_dims(const kpd_gvp_model* m, int* n_kp_scalars, int* vector_size) {
+    KPD_REQUIRE(m, "kpd_gvp_dims: null model");
+    *n_kp_scalars = m->C; *vector_size = m->V;
+    return 0;
+}
+
+extern "C" int64_t kpd_gvp_workspace_bytes(const kpd_gvp_model* m, const kpd_batch* batch, int32_t cap_ll,
+                                           int32_t cap_kl, int32_t cap_kk) {
+    const int caps[4] = {cap_ll, cap_kl, cap_kl, cap_kk};
+    int64_t bytes = 0;
+    gvp_carve(m, batch, caps, nullptr, &bytes);
+    return bytes;
+}
+
+extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const float* h_lig, const float* x_lig,
+                               const float* h_kp, const float* x_kp, const float* v_kp, const float* t_ptr,
+                               int32_t t_per_complex, const kpd_csr* ll, const kpd_csr* kl, const kpd_csr* lk,
+                               const kpd_csr* kk, float* eps_h, float* eps_x, void* workspace, void* stream) {
+    KPD_REQUIRE(m && b && h_lig && x_lig && h_kp && x_kp && v_kp && t_ptr && ll && kl && eps_h && eps_x && workspace,
+                "kpd_gvp_forward: null argument");
+    const bool ukp = m->cfg.update_kp != 0;
+    KPD_REQUIRE(!ukp || (lk && kk), "kpd_gvp_forward: update_kp needs lk and kk graphs");
+    KPD_REQUIRE(ukp || m->cfg.n_convs == 1, "kpd_gvp_forward: update_kp=False only works with one conv in the reference (SURVEY N6)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const kpd_csr* G[4] = {ll, kl, lk, kk};
+    const int caps[4] = {ll->cap, kl->cap, ukp ? lk->cap : 0, ukp ? kk->cap : 0};
+    GvpWs w = gvp_carve(m, b, caps, workspace, nullptr);
+    const int N[2] = {b->n_lig, b->n_kp};
+    const int S = m->S, V = m->V;
+
+    // ---- encoders: time concatenated first, Linear + SiLU + LayerNorm (dynamics_gvp.py:161-169)
+    KPD_TRY(launch_concat_time(h_lig, m->F, w.tin, m->F + 1, N[0], t_ptr, b->lig_batch, t_per_complex, st));
+    KPD_TRY(launch_linear(w.tin, m->F + 1, m->lig_enc[0], m->Sp, m->lig_enc[1], nullptr, 0, w.tenc, S, N[0], m->F + 1, S, 1, st));
+    KPD_TRY(launch_layernorm(w.tenc, S, w.s[0], S, N[0], S, m->lig_enc[2], m->lig_enc[3], st));
+    KPD_TRY(launch_concat_time(h_kp, m->C, w.tin, m->C + 1, N[1], t_ptr, b->kp_batch, t_per_complex, st));
+    KPD_TRY(launch_linear(w.tin, m->C + 1, m->kp_enc[0], m->Sp, m->kp_enc[1], nullptr, 0, w.tenc, S, N[1], m->C + 1, S, 1, st));
+    KPD_TRY(launch_layernorm(w.tenc, S, w.s[1], S, N[1], S, m->kp_enc[2], m->kp_enc[3], st));
+    // ligand vectors start at zero (:179-184); keypoint vectors come from the receptor encoder
+    cudaError_t ce = cudaMemsetAsync(w.v[0], 0, sizeof(float) * (size_t)N[0] * V * 3, st);
+    KPD_REQUIRE(ce == cudaSuccess, "kpd_gvp_forward: memset failed: %s", cudaGetErrorString(ce));
+    KPD_TRY(launch_copy_rows(v_kp, V * 3, w.v[1], V * 3, N[1], V * 3, st));
+
+    const int src_nt[4] = {0, 1, 0, 1}, dst_nt[4] = {0, 0, 1, 1};
+    const float* X[2] = {x_lig, x_kp};
+    const int norm_mode = m->cfg.norm_mode;
+
+    for (int l = 0; l < m->cfg.n_convs; ++l) {
+        const GvpLayerW& W = m->layers[l];
+        GvpEdgeLaunch L;
+        memset(&L, 0, sizeof(L));
+        L.Sdim = S; L.Vdim = V; L.n_msg = m->cfg.n_message_gvps; L.lds = m->lds; L.pw = m->pw;
+        L.rbf_dim = m->cfg.rbf_dim;
+        L.rbf_step = m->cfg.rbf_dmax / (float)(m->cfg.rbf_dim - 1);   // linspace(0, D_max, D_count)
+        L.rbf_sigma = m->cfg.rbf_dmax / (float)m->cfg.rbf_dim;
+        int max_tiles = 1;
+        for (int e = 0; e < W.n_et; ++e) {
+            GvpEtypeArgs& a = L.e[e];
+            a.rowptr = G[e]->rowptr; a.src = G[e]->src; a.dst = G[e]->dst; a.n_dst = G[e]->n_dst;
+            a.s_src = w.s[src_nt[e]]; a.v_src = w.v[src_nt[e]];
+            a.xs = X[src_nt[e]]; a.xd = X[dst_nt[e]];
+            for (int k = 0; k < L.n_msg; ++k) a.msg[k] = W.msg[e][k];
+            a.sm = w.sm[e]; a.vm = w.vm[e]; a.part = w.part[e];
+            const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TE);
+            if (t > max_tiles) max_tiles = t;
+        }
+        gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
+        KPD_TRY(check_launch("gvp_edge_kernel"));
+        for (int nt = 0; nt < W.n_dst; ++nt) {
+            if (N[nt] <= 0) continue;
+            GvpNodeArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
+            a.n_upd = m->cfg.n_update_gvps; a.n_et = 2;
+            a.s = w.s[nt]; a.v = w.v[nt];
+            for (int k = 0; k < 2; ++k) {
+                const int e = nt * 2 + k;
+                a.rowptr[k] = G[e]->rowptr; a.sm[k] = w.sm[e]; a.vm[k] = w.vm[e]; a.part[k] = w.part[e];
+            }
+            a.norm_mode = norm_mode; a.norm_const = m->cfg.message_norm;
+            a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
+            a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
+            for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
+            a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
+            gvp_node_kernel<<<cdiv(a.n, TE), NT, m->smem, st>>>(a);
+            KPD_TRY(check_launch("gvp_node_kernel"));
+        }
+    }
+    {
+        GvpHeadArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = N[0]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.n_gvps = m->cfg.n_noise_gvps;
+        a.F = m->F; a.Fp = m->Fp; a.hid_out = 64;
+        a.s = w.s[0]; a.v = w.v[0];
+        for (int k = 0; k < a.n_gvps; ++k) a.g[k] = m->head[k];
+        a.WoT = m->WoT; a.bo = m->bo; a.eps_h = eps_h; a.eps_x = eps_x;
+        if (a.n > 0) {
+            gvp_head_kernel<<<cdiv(a.n, TE), NT, m->smem, st>>>(a);
+            KPD_TRY(check_launch("gvp_head_kernel"));
+        }
+    }
+    return 0;
+}

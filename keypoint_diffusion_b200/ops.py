@@ -1,0 +1,333 @@
+"""Thin Python wrappers over the C ABI (include/kpdiff_b200.h): batch layout, graph build,
+denoiser forward, posterior step and the captured sampling loop.
+
+torch is used for device memory and streams only; every computation below is a call into
+libkpdiff_b200.so.  All tensors must live on one CUDA device (no CPU fallback).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (KpdBatch, KpdCsr, KpdEgnnConfig, KpdGraphParams, KpdGvpConfig, KpdSamplerConfig, check, lib, ptr)
+from . import pack
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("keypoint_diffusion_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    return t.contiguous().to(torch.float32)
+
+
+class DeviceBatch:
+    """Node layout of a batch of complexes (replaces the DGL batch bookkeeping read by the hot
+    path: g.batch_size, g.batch_num_nodes, utils.get_batch_idxs -- reference utils.py:81-170)."""
+
+    def __init__(self, lig_n: Sequence[int], kp_n: Sequence[int], device):
+        lig_n = [int(v) for v in lig_n]
+        kp_n = [int(v) for v in kp_n]
+        if len(lig_n) != len(kp_n) or not lig_n:
+            raise ValueError("lig_n and kp_n must be non-empty and of equal length")
+        if min(lig_n) < 1 or min(kp_n) < 1:
+            raise ValueError("every complex needs at least one ligand atom and one keypoint")
+        self.device = torch.device(device)
+        self.lig_n, self.kp_n = lig_n, kp_n
+        self.B = len(lig_n)
+        ln = torch.tensor(lig_n, dtype=torch.int64)
+        kn = torch.tensor(kp_n, dtype=torch.int64)
+        self.n_lig, self.n_kp = int(ln.sum()), int(kn.sum())
+        lp = torch.zeros(self.B + 1, dtype=torch.int32); lp[1:] = torch.cumsum(ln, 0)
+        kp = torch.zeros(self.B + 1, dtype=torch.int32); kp[1:] = torch.cumsum(kn, 0)
+        ar = torch.arange(self.B, dtype=torch.int32)
+        self.lig_ptr = lp.to(self.device)
+        self.kp_ptr = kp.to(self.device)
+        self.lig_batch = ar.repeat_interleave(ln).to(self.device)
+        self.kp_batch = ar.repeat_interleave(kn).to(self.device)
+        self.c = KpdBatch(self.B, self.n_lig, self.n_kp, max(lig_n), max(kp_n), self.lig_ptr.data_ptr(),
+                          self.kp_ptr.data_ptr(), self.lig_batch.data_ptr(), self.kp_batch.data_ptr())
+
+    def edge_capacity(self, gp: "GraphParams") -> Tuple[int, int]:
+        """(cap_ll, cap_kl): the most edges any configuration of this batch can produce."""
+        ll_lim = gp.ll_k if gp.ll_k > 0 else gp.ll_cap
+        kl_lim = gp.kl_k if gp.kl_k > 0 else gp.kl_cap
+        cap_ll = sum(n * min(n - 1, ll_lim) for n in self.lig_n)
+        cap_kl = sum(k * min(n, kl_lim) for n, k in zip(self.lig_n, self.kp_n))
+        return max(cap_ll, 1), max(cap_kl, 1)
+
+
+@dataclass
+class GraphParams:
+    """How add_lig_edges draws ligand edges (reference models/dynamics.py:393-404)."""
+    ll_k: int = 0
+    ll_r: float = 5.0
+    ll_cap: int = 200
+    kl_k: int = 5
+    kl_r: float = 8.0
+    kl_cap: int = 100
+
+    @property
+    def c(self):
+        return KpdGraphParams(self.ll_k, self.ll_cap, self.kl_k, self.kl_cap, float(self.ll_r), float(self.kl_r))
+
+    @staticmethod
+    def from_module(ll_k, kl_k, graph_cutoffs):
+        return GraphParams(ll_k=int(ll_k), ll_r=float(graph_cutoffs.get("ll", 0.0) or 0.0), kl_k=int(kl_k),
+                           kl_r=float(graph_cutoffs.get("kl", 0.0) or 0.0))
+
+
+class Csr:
+    """dst-sorted CSR + COO of one edge type on the device."""
+
+    def __init__(self, n_dst: int, cap: int, device):
+        self.n_dst, self.cap = int(n_dst), int(cap)
+        self.rowptr = torch.zeros(self.n_dst + 1, dtype=torch.int32, device=device)
+        self.src = torch.zeros(self.cap + 1, dtype=torch.int32, device=device)
+        self.dst = torch.zeros(self.cap + 1, dtype=torch.int32, device=device)
+        self.c = KpdCsr(self.n_dst, self.cap, self.rowptr.data_ptr(), self.src.data_ptr(), self.dst.data_ptr())
+
+    @staticmethod
+    def from_edges(src: torch.Tensor, dst: torch.Tensor, n_dst: int, device) -> "Csr":
+        """Static graph (kk) given as global (src, dst) index lists: stable sort by destination."""
+        src = src.to("cpu", torch.int64)
+        dst = dst.to("cpu", torch.int64)
+        order = torch.sort(dst, stable=True).indices
+        out = Csr(n_dst, max(int(src.numel()), 1), device)
+        if src.numel():
+            out.src[: src.numel()] = src[order].to(torch.int32).to(device)
+            out.dst[: src.numel()] = dst[order].to(torch.int32).to(device)
+        rp = torch.zeros(n_dst + 1, dtype=torch.int64)
+        rp[1:] = torch.cumsum(torch.bincount(dst, minlength=n_dst), 0)
+        out.rowptr.copy_(rp.to(torch.int32))
+        return out
+
+    def edges(self) -> torch.Tensor:
+        """[2, E] int64 (src; dst) on the CPU -- synchronises; for tests and debugging only."""
+        e = int(self.rowptr[-1].item())
+        return torch.stack([self.src[:e].long().cpu(), self.dst[:e].long().cpu()])
+
+
+class LigandGraphs:
+    """ll / kl / lk graphs of one denoiser call + the scratch kpd_build_graph needs."""
+
+    def __init__(self, batch: DeviceBatch, gp: GraphParams, with_lk: bool):
+        self.batch, self.gp, self.with_lk = batch, gp, with_lk
+        cap_ll, cap_kl = batch.edge_capacity(gp)
+        dev = batch.device
+        self.ll = Csr(batch.n_lig, cap_ll, dev)
+        self.kl = Csr(batch.n_lig, cap_kl, dev)
+        self.lk = Csr(batch.n_kp, cap_kl, dev) if with_lk else None
+        self.counts_ll = torch.zeros(batch.B, dtype=torch.int32, device=dev)
+        self.counts_kl = torch.zeros(batch.B, dtype=torch.int32, device=dev)
+        self.ws = torch.empty(int(lib.kpd_graph_workspace_bytes(C.byref(batch.c))), dtype=torch.uint8, device=dev)
+
+    def build(self, x_lig: torch.Tensor, x_kp: torch.Tensor):
+        _require_cuda(x_lig, x_kp)
+        assert x_lig.dtype == torch.float32 and x_kp.dtype == torch.float32
+        assert x_lig.is_contiguous() and x_kp.is_contiguous()
+        gpc = self.gp.c
+        check(lib.kpd_build_graph(C.byref(self.batch.c), ptr(x_lig), ptr(x_kp), C.byref(gpc), C.byref(self.ll.c),
+                                  C.byref(self.kl.c), C.byref(self.lk.c) if self.lk else None,
+                                  ptr(self.counts_ll), ptr(self.counts_kl), ptr(self.ws), _stream()),
+              "kpd_build_graph")
+        return self
+
+
+def linear(x, wt, bias=None, residual=None, act=0, n_out=None):
+    """Y = act(X @ WT + b) (+R) through kpd_linear (WT K-major, columns padded to x4)."""
+    _require_cuda(x, wt)
+    M, K = x.shape
+    N = n_out if n_out is not None else wt.shape[1]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    check(lib.kpd_linear(ptr(x), x.stride(0), ptr(wt), wt.stride(0), ptr(bias), ptr(residual),
+                         residual.stride(0) if residual is not None else 0, ptr(y), y.stride(0), M, K, N, act,
+                         _stream()), "kpd_linear")
+    return y
+
+
+class _Model:
+    arch = -1
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+
+    def _workspace(self, batch: DeviceBatch, caps: Tuple[int, int, int]) -> torch.Tensor:
+        key = (id(batch), caps)
+        ws = self._ws.get(key)
+        if ws is None:
+            fn = lib.kpd_egnn_workspace_bytes if self.arch == 0 else lib.kpd_gvp_workspace_bytes
+            n = int(fn(self.handle, C.byref(batch.c), *caps))
+            ws = torch.empty(n, dtype=torch.uint8, device=batch.device)
+            self._ws = {key: ws}          # keep only the latest layout
+        return ws
+
+
+class EgnnModel(_Model):
+    """Packed EGNN denoiser weights on the device (kpd_egnn_model)."""
+    arch = 0
+
+    def __init__(self, sd: Dict[str, torch.Tensor], *, atom_nf, rec_nf, hidden_nf, n_layers, use_tanh,
+                 update_kp_feat, norm, message_norm, device, coords_range=10.0, z_effective=False):
+        super().__init__()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("EgnnModel needs a CUDA device (no CPU fallback)")
+        self.update_kp_feat = bool(update_kp_feat)
+        self.atom_nf, self.rec_nf, self.hidden_nf = atom_nf, rec_nf, hidden_nf
+        has_rec = "rec_encoder.0.weight" in sd
+        self.blob, offs = pack.pack_egnn(sd, atom_nf=atom_nf, rec_nf=rec_nf, hidden_nf=hidden_nf, n_layers=n_layers,
+                                         update_kp_feat=update_kp_feat, norm=norm, device=self.device)
+        cfg = KpdEgnnConfig(atom_nf, rec_nf, hidden_nf, n_layers, int(bool(use_tanh)), int(bool(update_kp_feat)),
+                            int(bool(norm)), int(has_rec), float(coords_range), float(message_norm),
+                            int(bool(z_effective)))
+        arr = (C.c_int64 * len(offs))(*offs)
+        check(lib.kpd_egnn_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_egnn_create")
+
+    def __del__(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            lib.kpd_egnn_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def forward(self, batch: DeviceBatch, graphs: LigandGraphs, kk: Optional[Csr], h_lig, x_lig, h_kp, x_kp, t,
+                kp_feat_enc=None):
+        """(eps_h, eps_x) for one denoiser call; t: float tensor [1] (shared) or [B] on the device."""
+        _require_cuda(h_lig, x_lig, h_kp, x_kp, t)
+        eps_h = torch.empty(batch.n_lig, self.atom_nf, dtype=torch.float32, device=self.device)
+        eps_x = torch.empty(batch.n_lig, 3, dtype=torch.float32, device=self.device)
+        caps = (graphs.ll.cap, graphs.kl.cap, kk.cap if kk is not None else 1)
+        ws = self._workspace(batch, caps)
+        per_complex = int(t.numel() == batch.B and batch.B > 1)
+        check(lib.kpd_egnn_forward(self.handle, C.byref(batch.c), ptr(_f32(h_lig)), ptr(_f32(x_lig)), ptr(_f32(h_kp)),
+                                   ptr(_f32(x_kp)), ptr(kp_feat_enc), ptr(_f32(t)), per_complex,
+                                   C.byref(graphs.ll.c), C.byref(graphs.kl.c),
+                                   C.byref(graphs.lk.c) if graphs.lk is not None else None,
+                                   C.byref(kk.c) if kk is not None else None, ptr(eps_h), ptr(eps_x), ptr(ws),
+                                   _stream()), "kpd_egnn_forward")
+        return eps_h, eps_x
+
+
+class GvpModel(_Model):
+    """Packed GVP denoiser weights on the device (kpd_gvp_model)."""
+    arch = 1
+
+    def __init__(self, sd: Dict[str, torch.Tensor], *, n_lig_scalars, n_kp_scalars, vector_size, n_convs,
+                 n_hidden_scalars, update_kp, n_message_gvps, n_update_gvps, n_noise_gvps, message_norm, device,
+                 rbf_dmax=15.0, rbf_dim=16):
+        super().__init__()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GvpModel needs a CUDA device (no CPU fallback)")
+        self.update_kp = bool(update_kp)
+        self.atom_nf, self.vector_size = n_lig_scalars, vector_size
+        self.blob, offs = pack.pack_gvp(sd, n_lig_scalars=n_lig_scalars, n_kp_scalars=n_kp_scalars,
+                                        vector_size=vector_size, n_convs=n_convs, n_hidden_scalars=n_hidden_scalars,
+                                        update_kp=update_kp, n_message_gvps=n_message_gvps,
+                                        n_update_gvps=n_update_gvps, n_noise_gvps=n_noise_gvps, device=self.device)
+        if message_norm == "mean":
+            mode, mn = 1, 1.0
+        elif float(message_norm) == 0.0:
+            mode, mn = 2, 0.0
+        else:
+            mode, mn = 0, float(message_norm)
+        cfg = KpdGvpConfig(n_lig_scalars, n_kp_scalars, vector_size, n_convs, n_hidden_scalars, n_message_gvps,
+                           n_update_gvps, n_noise_gvps, int(bool(update_kp)), mode, mn, float(rbf_dmax), int(rbf_dim))
+        arr = (C.c_int64 * len(offs))(*offs)
+        check(lib.kpd_gvp_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_gvp_create")
+
+    def __del__(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            lib.kpd_gvp_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def forward(self, batch: DeviceBatch, graphs: LigandGraphs, kk: Optional[Csr], h_lig, x_lig, h_kp, x_kp, v_kp, t):
+        _require_cuda(h_lig, x_lig, h_kp, x_kp, v_kp, t)
+        eps_h = torch.empty(batch.n_lig, self.atom_nf, dtype=torch.float32, device=self.device)
+        eps_x = torch.empty(batch.n_lig, 3, dtype=torch.float32, device=self.device)
+        caps = (graphs.ll.cap, graphs.kl.cap, kk.cap if kk is not None else 1)
+        ws = self._workspace(batch, caps)
+        per_complex = int(t.numel() == batch.B and batch.B > 1)
+        check(lib.kpd_gvp_forward(self.handle, C.byref(batch.c), ptr(_f32(h_lig)), ptr(_f32(x_lig)), ptr(_f32(h_kp)),
+                                  ptr(_f32(x_kp)), ptr(_f32(v_kp)), ptr(_f32(t)), per_complex, C.byref(graphs.ll.c),
+                                  C.byref(graphs.kl.c), C.byref(graphs.lk.c) if graphs.lk is not None else None,
+                                  C.byref(kk.c) if kk is not None else None, ptr(eps_h), ptr(eps_x), ptr(ws),
+                                  _stream()), "kpd_gvp_forward")
+        return eps_h, eps_x
+
+
+def ddpm_step(batch: DeviceBatch, x_lig, h_lig, x_kp, eps_x, eps_h, coef, step: torch.Tensor, noise_x=None,
+              noise_h=None, seed=0):
+    """In-place reverse step s <- s+1 (reference ligand_diffuser.py:515-536); step: int32 [1] on device."""
+    _require_cuda(x_lig, h_lig, x_kp, eps_x, eps_h, coef, step)
+    check(lib.kpd_ddpm_step(C.byref(batch.c), ptr(x_lig), ptr(h_lig), ptr(x_kp), ptr(eps_x), ptr(eps_h),
+                            h_lig.shape[1], ptr(coef), ptr(step), ptr(noise_x), ptr(noise_h), int(seed), _stream()),
+          "kpd_ddpm_step")
+
+
+def remove_com(batch: DeviceBatch, x_lig, x_kp, which: str):
+    """In-place remove_com (reference ligand_diffuser.py:185-203); returns the [B,3] means."""
+    _require_cuda(x_lig, x_kp)
+    com = torch.empty(batch.B, 3, dtype=torch.float32, device=batch.device)
+    check(lib.kpd_remove_com(C.byref(batch.c), ptr(x_lig), ptr(x_kp), {"ligand": 0, "receptor": 1}[which], ptr(com),
+                             _stream()), "kpd_remove_com")
+    return com
+
+
+class Sampler:
+    """The captured reverse-diffusion loop for one (model, batch) pair (kpd_sampler)."""
+
+    def __init__(self, model: _Model, batch: DeviceBatch, gp: GraphParams, kk: Optional[Csr], coef: torch.Tensor,
+                 T: int, atom_nf: int, steps_per_graph: int = 50, use_cuda_graph: bool = True,
+                 lig_feat_norm_constant: float = 1.0):
+        self.model, self.batch, self.gp, self.kk, self.coef = model, batch, gp, kk, coef
+        _require_cuda(coef)
+        self.T, self.atom_nf = int(T), int(atom_nf)
+        self.has_lk = bool(model.update_kp_feat if model.arch == 0 else model.update_kp)
+        steps_per_graph = max(1, min(int(steps_per_graph), self.T))
+        self.cfg = KpdSamplerConfig(model.arch, self.T, self.atom_nf, steps_per_graph, int(bool(use_cuda_graph)),
+                                    float(lig_feat_norm_constant))
+        cap_ll, cap_kl = batch.edge_capacity(gp)
+        cap_kk = kk.cap if kk is not None else 1
+        n = int(lib.kpd_sampler_workspace_bytes(C.byref(self.cfg), model.handle, C.byref(batch.c), cap_ll, cap_kl, cap_kk))
+        if n < 0:
+            check(-1, "kpd_sampler_workspace_bytes")
+        self.ws = torch.empty(n, dtype=torch.uint8, device=batch.device)
+        self.handle = C.c_void_p()
+        self._gpc = gp.c
+        check(lib.kpd_sampler_create(C.byref(self.cfg), model.handle, C.byref(batch.c), C.byref(self._gpc),
+                                     C.byref(kk.c) if kk is not None else None, int(self.has_lk), ptr(coef), cap_ll,
+                                     cap_kl, ptr(self.ws), n, C.byref(self.handle)), "kpd_sampler_create")
+
+    def __del__(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            lib.kpd_sampler_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def run(self, x_kp, h_kp, v_kp, init_lig_pos, noise=None, seed=0, n_steps=None):
+        """Returns (x_lig [n_lig,3], h_lig [n_lig,F], x_kp) on the device, in the input frame."""
+        _require_cuda(x_kp, h_kp, init_lig_pos)
+        b = self.batch
+        x_kp = _f32(x_kp).clone()
+        x_lig = torch.empty(b.n_lig, 3, dtype=torch.float32, device=b.device)
+        h_lig = torch.empty(b.n_lig, self.atom_nf, dtype=torch.float32, device=b.device)
+        n_steps = self.T if n_steps is None else int(n_steps)
+        if noise is not None:
+            _require_cuda(noise)
+            assert noise.shape == (self.T + 1, b.n_lig * (3 + self.atom_nf)) and noise.dtype == torch.float32
+        check(lib.kpd_sampler_run(self.handle, ptr(x_kp), ptr(_f32(h_kp)), ptr(_f32(v_kp)) if v_kp is not None else None,
+                                  ptr(_f32(init_lig_pos)), ptr(x_lig), ptr(h_lig), ptr(noise), int(seed), n_steps,
+                                  _stream()), "kpd_sampler_run")
+        return x_lig, h_lig, x_kp
+
+    @property
+    def launches_per_step(self):
+        return int(lib.kpd_sampler_launches_per_step(self.handle))

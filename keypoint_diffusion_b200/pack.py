@@ -1,0 +1,178 @@
+"""Weight packer: reference ``state_dict`` -> one fp32 device blob + offsets for the CUDA library.
+
+Setup-time host code (runs once per model).  Layouts are the ones documented at the top of
+csrc/egnn.cu and csrc/gvp.cu: every Linear is stored K-major (transposed) with its output width
+padded to a multiple of 4 floats, every entry starts on a 16-byte boundary.
+
+EGNN specifics (reference models/dynamics.py):
+  * the first Linear of edge_mlp / coord_mlp (:41, :73) acts on cat(h_src, h_dst, dij); it is
+    split into W1a (h_src), W1b (h_dst) and w1c (dij) and the two h blocks of every edge type
+    that a node type takes part in are concatenated into one per-node GEMM weight (WpreT), with
+    the bias folded into the destination role;
+  * H = hidden_nf + 1 (:337-339).
+"""
+from typing import Dict, List, Tuple
+
+import torch
+
+
+def _r4(n):
+    return (n + 3) // 4 * 4
+
+
+class _Blob:
+    def __init__(self):
+        self.parts: List[torch.Tensor] = []
+        self.n = 0
+
+    def add(self, t: torch.Tensor) -> int:
+        t = t.detach().to(torch.float32).contiguous().reshape(-1).cpu()
+        off = self.n
+        pad = _r4(t.numel()) - t.numel()
+        self.parts.append(t)
+        if pad or t.numel() == 0:
+            z = torch.zeros(pad if t.numel() else 4)
+            self.parts.append(z)
+            self.n += z.numel()
+        self.n += t.numel()
+        return off
+
+    def finish(self, device) -> torch.Tensor:
+        return torch.cat(self.parts).to(device)
+
+
+def _padcols(w: torch.Tensor, ncols: int) -> torch.Tensor:
+    out = torch.zeros(w.shape[0], ncols, dtype=torch.float32)
+    out[:, : w.shape[1]] = w
+    return out
+
+
+def _padvec(v: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.zeros(n, dtype=torch.float32)
+    out[: v.numel()] = v.reshape(-1)
+    return out
+
+
+def _linT(sd, name, ncols=None):
+    """K-major (transposed) weight + bias of nn.Linear ``name``, output width padded."""
+    w = sd[name + ".weight"].detach().float().cpu()
+    n = _r4(w.shape[0]) if ncols is None else ncols
+    wt = _padcols(w.t().contiguous(), n)
+    b = sd.get(name + ".bias")
+    bv = _padvec(b.detach().float().cpu(), n) if b is not None else torch.zeros(n)
+    return wt, bv
+
+
+EGNN_ROLES = {
+    # node type -> ordered (edge type, 's'|'d') roles; slot = 2*role + branch
+    True: {"lig": [("ll", "s"), ("ll", "d"), ("lk", "s"), ("kl", "d")],
+           "kp": [("kl", "s"), ("kk", "s"), ("kk", "d"), ("lk", "d")]},
+    False: {"lig": [("ll", "s"), ("ll", "d"), ("kl", "d")], "kp": [("kl", "s")]},
+}
+
+
+def pack_egnn(sd: Dict[str, torch.Tensor], *, atom_nf, rec_nf, hidden_nf, n_layers, update_kp_feat, norm,
+              device) -> Tuple[torch.Tensor, List[int]]:
+    H = hidden_nf + 1
+    Hp = _r4(H)
+    hidp = _r4(hidden_nf)
+    nmain = min(H, 256) // 4 * 4
+    nlo = H - nmain
+    blob, offs = _Blob(), []
+
+    def put(t):
+        offs.append(blob.add(t))
+
+    w, b = _linT(sd, "lig_encoder.0", 64); put(w); put(b)
+    w, b = _linT(sd, "lig_encoder.2", hidp); put(w); put(b)
+    if "rec_encoder.0.weight" in sd:
+        w, b = _linT(sd, "rec_encoder.0", _r4(2 * rec_nf)); put(w); put(b)
+        w, b = _linT(sd, "rec_encoder.2", hidp); put(w); put(b)
+    else:
+        offs.extend([-1, -1, -1, -1])
+    w, b = _linT(sd, "lig_decoder.0", _r4(2 * atom_nf)); put(w); put(b)
+    w, b = _linT(sd, "lig_decoder.2", _r4(atom_nf)); put(w); put(b)
+
+    etypes = ["ll", "kl", "lk", "kk"] if update_kp_feat else ["ll", "kl"]
+    upd = ["lig", "kp"] if update_kp_feat else ["lig"]
+    roles = EGNN_ROLES[bool(update_kp_feat)]
+    for l in range(n_layers):
+        q = f"egnn.conv_layers.{l}."
+        for nt in ("lig", "kp"):
+            cols, bias = [], []
+            for et, sdir in roles[nt]:
+                for mlp in ("edge_mlp", "coord_mlp"):
+                    W1 = sd[f"{q}{mlp}.{et}.0.weight"].detach().float().cpu()     # [H, 2H+1]
+                    blk = W1[:, :H] if sdir == "s" else W1[:, H:2 * H]
+                    cols.append(_padcols(blk.t().contiguous(), Hp))              # [H(in), Hp(out)]
+                    bias.append(_padvec(sd[f"{q}{mlp}.{et}.0.bias"].detach().float().cpu(), Hp)
+                                if sdir == "d" else torch.zeros(Hp))
+            put(torch.cat(cols, dim=1))
+            put(torch.cat(bias))
+        for et in etypes:
+            for mlp in ("edge_mlp", "coord_mlp"):
+                W1 = sd[f"{q}{mlp}.{et}.0.weight"].detach().float().cpu()
+                put(_padvec(W1[:, 2 * H], Hp))                                     # w1c (dij column)
+                W2 = sd[f"{q}{mlp}.{et}.2.weight"].detach().float().cpu()         # [H, H]
+                put(_padcols(W2.t().contiguous(), Hp))                             # W2T
+                put(_padvec(sd[f"{q}{mlp}.{et}.2.bias"].detach().float().cpu(), Hp))
+                lo = torch.zeros(3, Hp)
+                if nlo:
+                    lo[:nlo, :H] = W2[nmain:H, :]
+                put(lo)                                                            # W2lo
+            put(_padvec(sd[f"{q}soft_attention.{et}.0.weight"].detach().float().cpu(), Hp))
+            put(_padvec(sd[f"{q}soft_attention.{et}.0.bias"].detach().float().cpu(), 4))
+            put(_padvec(sd[f"{q}coord_mlp.{et}.4.weight"].detach().float().cpu(), Hp))
+        for nt in upd:
+            w, b = _linT(sd, f"{q}node_mlp.{nt}.0", Hp); put(w); put(b)            # [2H][Hp]
+            w, b = _linT(sd, f"{q}node_mlp.{nt}.2", Hp); put(w); put(b)            # [H][Hp]
+            if norm:
+                put(_padvec(sd[f"{q}layer_norm.{nt}.weight"].detach().float().cpu(), Hp))
+                put(_padvec(sd[f"{q}layer_norm.{nt}.bias"].detach().float().cpu(), Hp))
+            else:
+                offs.extend([-1, -1])
+    return blob.finish(device), offs
+
+
+def gvp_layer_etypes(l, n_convs, update_kp):
+    """reference models/dynamics_gvp.py:65-74: the last conv of an update_kp model is lig-only."""
+    base = [("lig", "ll", "lig"), ("kp", "kl", "lig")]
+    if (not update_kp) or l == n_convs - 1:
+        return base
+    return base + [("lig", "lk", "kp"), ("kp", "kk", "kp")]
+
+
+def pack_gvp(sd: Dict[str, torch.Tensor], *, n_lig_scalars, n_kp_scalars, vector_size, n_convs,
+             n_hidden_scalars, update_kp, n_message_gvps, n_update_gvps, n_noise_gvps,
+             device) -> Tuple[torch.Tensor, List[int]]:
+    blob, offs = _Blob(), []
+
+    def put(t):
+        offs.append(blob.add(t))
+
+    def put_gvp(name):
+        put(sd[name + ".Wh"])
+        put(sd[name + ".Wu"])
+        w, b = _linT(sd, name + ".to_feats_out.0"); put(w); put(b)
+        put(sd[name + ".scalar_to_vector_gates.weight"].detach().float().cpu().t().contiguous())   # [fout][vout]
+        put(sd[name + ".scalar_to_vector_gates.bias"])
+
+    for enc in ("lig_encoder", "kp_encoder"):
+        w, b = _linT(sd, enc + ".0", n_hidden_scalars); put(w); put(b)
+        put(sd[enc + ".2.weight"]); put(sd[enc + ".2.bias"])
+    for l in range(n_convs):
+        q = f"noise_predictor.conv_layers.{l}."
+        etypes = gvp_layer_etypes(l, n_convs, update_kp)
+        for et in etypes:
+            for i in range(n_message_gvps):
+                put_gvp(f"{q}edge_message_fns.{'_'.join(et)}.{i}")
+        for nt in (["lig", "kp"] if len(etypes) == 4 else ["lig"]):
+            for i in range(n_update_gvps):
+                put_gvp(f"{q}node_update_fns.{nt}.{i}")
+            put(sd[f"{q}message_layer_norms.{nt}.feat_norm.weight"]); put(sd[f"{q}message_layer_norms.{nt}.feat_norm.bias"])
+            put(sd[f"{q}update_layer_norms.{nt}.feat_norm.weight"]); put(sd[f"{q}update_layer_norms.{nt}.feat_norm.bias"])
+    q = "noise_predictor.noise_predictor."
+    for i in range(n_noise_gvps):
+        put_gvp(f"{q}gvps.{i}")
+    w, b = _linT(sd, q + "to_scalar_output"); put(w); put(b)
+    return blob.finish(device), offs
