@@ -31,6 +31,14 @@ extern "C" {
 
 const char* kpd_last_error(void);
 int kpd_version(void);
+/* kernels this library has launched in this process (captured launches count once) */
+int64_t kpd_launch_count(void);
+/* Optional CUDA-event timing of one kernel family for bench.py's roofline leg.  kernel_id:
+ * 1 egnn_edge, 2 gvp_edge, 3 graph build, 4 ddpm_step, 5 gvp_node, 6 gvp_head, 7 egnn node
+ * stage, 8 egnn per-node pre-GEMM; 0 disables.  Inactive during stream capture.
+ * kpd_profile_collect synchronises on the recorded events and resets the record list. */
+int kpd_profile_enable(int32_t kernel_id, int32_t max_records);
+int kpd_profile_collect(double* total_ms, int32_t* count);
 
 /* ------------------------------------------------------------------------------------------
  * Batch layout.  Replaces the DGL batched heterograph bookkeeping the path reads:
@@ -239,6 +247,8 @@ void kpd_sampler_destroy(kpd_sampler* s);
 int kpd_sampler_run(kpd_sampler* s, float* x_kp, const float* h_kp, const float* v_kp,
                     const float* init_lig_pos, float* x_lig, float* h_lig, const float* noise,
                     uint64_t seed, int32_t n_steps, void* stream);
+/* mean edges per reverse step of the last run: out[4] = {E_ll, E_kl (= E_lk), E_kk, steps}; syncs */
+int kpd_sampler_edge_stats(kpd_sampler* s, double* out);
 /* kernels launched per reverse step by the captured sequence (for bench.py's gpu_launches) */
 int32_t kpd_sampler_launches_per_step(const kpd_sampler* s);
 

@@ -60,6 +60,10 @@ def _load():
     sig = {
         "kpd_last_error": (C.c_char_p, []),
         "kpd_version": (I, []),
+        "kpd_launch_count": (L, []),
+        "kpd_profile_enable": (I, [I, I]),
+        "kpd_profile_collect": (I, [C.POINTER(C.c_double), C.POINTER(I)]),
+        "kpd_sampler_edge_stats": (I, [P, C.POINTER(C.c_double)]),
         "kpd_graph_workspace_bytes": (L, [C.POINTER(KpdBatch)]),
         "kpd_build_graph": (I, [C.POINTER(KpdBatch), P, P, C.POINTER(KpdGraphParams), C.POINTER(KpdCsr),
                                 C.POINTER(KpdCsr), C.POINTER(KpdCsr), P, P, P, P]),

@@ -241,4 +241,15 @@ int launch_scale(float* x, int n, float s, cudaStream_t st);
 int launch_step_prologue(int* counter, int* step, float* t_cur, const float* coef, cudaStream_t st);
 long long launch_count();   // kernels launched through check_launch() so far (this process)
 
+// optional per-kernel CUDA-event timing (bench.py's roofline leg); no-ops unless enabled and
+// never active while a stream is being captured
+enum ProfId { PROF_EGNN_EDGE = 1, PROF_GVP_EDGE = 2, PROF_GRAPH = 3, PROF_STEP = 4, PROF_GVP_NODE = 5,
+              PROF_GVP_HEAD = 6, PROF_EGNN_NODE = 7, PROF_EGNN_PRE = 8, PROF_ENCDEC = 9 };
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+
+int build_graph_impl(const kpd_batch* batch, const float* x_lig, const float* x_kp, const kpd_graph_params* p,
+                     kpd_csr* ll, kpd_csr* kl, kpd_csr* lk, int32_t* counts_ll, int32_t* counts_kl, void* workspace,
+                     long long* edge_accum, cudaStream_t st);
+
 }  // namespace kpd

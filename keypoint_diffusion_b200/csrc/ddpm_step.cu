@@ -90,9 +90,12 @@ ddpm_step_kernel(kpd_batch b, float* __restrict__ x_lig, float* __restrict__ h_l
 int launch_ddpm_step(const kpd_batch* b, float* x_lig, float* h_lig, float* x_kp, const float* eps_x,
                      const float* eps_h, int F, const float* coef, const int* step_ptr, const float* noise_x,
                      const float* noise_h, uint64_t seed, const RunParams* rp, cudaStream_t st) {
+    prof_begin(PROF_STEP, st);
     ddpm_step_kernel<<<b->B, 128, 0, st>>>(*b, x_lig, h_lig, x_kp, eps_x, eps_h, F, coef, step_ptr, noise_x,
                                            noise_h, seed, rp);
-    return check_launch("ddpm_step_kernel");
+    const int rc = check_launch("ddpm_step_kernel");
+    prof_end(PROF_STEP, st);
+    return rc;
 }
 
 // which: 0 = ligand COM, 1 = keypoint COM.  shift != 0: subtract it from both node types.

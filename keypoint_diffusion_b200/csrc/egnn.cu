@@ -408,10 +408,12 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
 
     for (int l = 0; l < m->cfg.n_layers; ++l) {
         const EgnnLayerW& W = m->layers[l];
+        prof_begin(PROF_EGNN_PRE, st);
         for (int nt = 0; nt < 2; ++nt) {
             const int ncol = m->nslot[nt] * Hp;
             KPD_TRY(launch_linear(w.h[nt], Hp, W.WpreT[nt], ncol, W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, st));
         }
+        prof_end(PROF_EGNN_PRE, st);
         EgnnEdgeLaunch L;
         memset(&L, 0, sizeof(L));
         L.H = H; L.Hp = Hp; L.nmain = m->nmain; L.nlo = m->nlo; L.lda = m->lda; L.pw = m->pw;
@@ -426,8 +428,11 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             a.watt = W.watt[e]; a.batt = W.batt[e]; a.w3c = W.w3c[e];
             a.hn = w.hn[e]; a.xn = w.xn[e]; a.part = w.part[e];
         }
+        prof_begin(PROF_EGNN_EDGE, st);
         egnn_edge_kernel<<<dim3(max_tiles, m->n_et), NT, m->edge_smem, st>>>(L);
         KPD_TRY(check_launch("egnn_edge_kernel"));
+        prof_end(PROF_EGNN_EDGE, st);
+        prof_begin(PROF_EGNN_NODE, st);
 
         for (int nt = 0; nt < m->n_upd; ++nt) {
             EgnnNodePrep a;
@@ -454,6 +459,7 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             if (m->cfg.norm) KPD_TRY(launch_layernorm(w.y, Hp, w.h[nt], Hp, N[nt], H, W.lnw[nt], W.lnb[nt], st));
             else KPD_TRY(launch_copy_rows(w.y, Hp, w.h[nt], Hp, N[nt], H, st));
         }
+        prof_end(PROF_EGNN_NODE, st);
     }
     // ---- decoder on h[:, :-1] and eps_x (models/dynamics.py:376-381)
     KPD_TRY(launch_linear(w.h[0], Hp, m->dec[0], m->F2p, m->dec[1], nullptr, 0, w.t2, m->F2p, N[0], hid, 2 * m->F, 1, st));

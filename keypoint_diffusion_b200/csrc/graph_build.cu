@@ -172,7 +172,7 @@ graph_mark_kernel(kpd_batch b, const float* __restrict__ x_lig, const float* __r
 // exclusive scan of the per-complex totals; also publishes the edge totals into rowptr[n_dst]
 __global__ void __launch_bounds__(1024)
 graph_scan_kernel(int B, GraphWs g, int* rowptr_ll, int n_lig, int* rowptr_kl, int* rowptr_lk, int n_kp,
-                  int* counts_ll, int* counts_kl) {
+                  int* counts_ll, int* counts_kl, long long* edge_accum) {
     __shared__ int s_a[1024], s_b[1024];
     __shared__ int carry_a, carry_b;
     if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; }
@@ -205,6 +205,7 @@ graph_scan_kernel(int B, GraphWs g, int* rowptr_ll, int n_lig, int* rowptr_kl, i
         rowptr_ll[n_lig] = carry_a;
         rowptr_kl[n_lig] = carry_b;
         if (rowptr_lk) rowptr_lk[n_kp] = carry_b;
+        if (edge_accum) { edge_accum[0] += carry_a; edge_accum[1] += carry_b; edge_accum[2] += 1; }
     }
 }
 
@@ -300,13 +301,20 @@ extern "C" int64_t kpd_graph_workspace_bytes(const kpd_batch* batch) {
 extern "C" int kpd_build_graph(const kpd_batch* batch, const float* x_lig, const float* x_kp,
                                const kpd_graph_params* p, kpd_csr* ll, kpd_csr* kl, kpd_csr* lk,
                                int32_t* counts_ll, int32_t* counts_kl, void* workspace, void* stream) {
+    return build_graph_impl(batch, x_lig, x_kp, p, ll, kl, lk, counts_ll, counts_kl, workspace, nullptr,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int kpd::build_graph_impl(const kpd_batch* batch, const float* x_lig, const float* x_kp, const kpd_graph_params* p,
+                          kpd_csr* ll, kpd_csr* kl, kpd_csr* lk, int32_t* counts_ll, int32_t* counts_kl,
+                          void* workspace, long long* edge_accum, cudaStream_t st) {
     KPD_REQUIRE(batch && p && ll && kl, "kpd_build_graph: null argument");
     KPD_REQUIRE(batch->B > 0, "kpd_build_graph: empty batch");
     KPD_REQUIRE(p->ll_k <= KPD_MAX_KNN - 1 && p->kl_k <= KPD_MAX_KNN, "kpd_build_graph: k > %d unsupported", KPD_MAX_KNN);
     KPD_REQUIRE(ll->n_dst == batch->n_lig && kl->n_dst == batch->n_lig, "kpd_build_graph: n_dst mismatch");
     KPD_REQUIRE(!lk || lk->n_dst == batch->n_kp, "kpd_build_graph: lk n_dst mismatch");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     GraphWs g = carve_graph_ws(batch, workspace, nullptr);
+    prof_begin(PROF_GRAPH, st);
     const size_t smem1 = (size_t)3 * batch->max_lig * sizeof(float) + (size_t)batch->max_lig * g.wk * sizeof(uint32_t);
     KPD_REQUIRE(smem1 <= 200 * 1024, "kpd_build_graph: complex too large for shared memory (%zu B)", smem1);
     if (smem1 > 48 * 1024)
@@ -314,11 +322,12 @@ extern "C" int kpd_build_graph(const kpd_batch* batch, const float* x_lig, const
     graph_mark_kernel<<<batch->B, 128, smem1, st>>>(*batch, x_lig, x_kp, *p, g);
     KPD_TRY(check_launch("graph_mark_kernel"));
     graph_scan_kernel<<<1, 1024, 0, st>>>(batch->B, g, ll->rowptr, batch->n_lig, kl->rowptr,
-                                          lk ? lk->rowptr : nullptr, batch->n_kp, counts_ll, counts_kl);
+                                          lk ? lk->rowptr : nullptr, batch->n_kp, counts_ll, counts_kl, edge_accum);
     KPD_TRY(check_launch("graph_scan_kernel"));
     const size_t smem3 = ((size_t)max(batch->max_lig, batch->max_kp) + 128) * sizeof(int);
     kpd_csr lk_v = lk ? *lk : kpd_csr{0, 0, nullptr, nullptr, nullptr};
     graph_fill_kernel<<<batch->B, 128, smem3, st>>>(*batch, g, *ll, *kl, lk_v, lk ? 1 : 0);
     KPD_TRY(check_launch("graph_fill_kernel"));
+    prof_end(PROF_GRAPH, st);
     return 0;
 }

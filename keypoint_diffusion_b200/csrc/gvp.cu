@@ -520,8 +520,10 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TE);
             if (t > max_tiles) max_tiles = t;
         }
+        prof_begin(PROF_GVP_EDGE, st);
         gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
         KPD_TRY(check_launch("gvp_edge_kernel"));
+        prof_end(PROF_GVP_EDGE, st);
         for (int nt = 0; nt < W.n_dst; ++nt) {
             if (N[nt] <= 0) continue;
             GvpNodeArgs a;
@@ -538,8 +540,10 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
             for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
             a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
+            prof_begin(PROF_GVP_NODE, st);
             gvp_node_kernel<<<cdiv(a.n, TE), NT, m->smem, st>>>(a);
             KPD_TRY(check_launch("gvp_node_kernel"));
+            prof_end(PROF_GVP_NODE, st);
         }
     }
     {
@@ -551,8 +555,10 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         for (int k = 0; k < a.n_gvps; ++k) a.g[k] = m->head[k];
         a.WoT = m->WoT; a.bo = m->bo; a.eps_h = eps_h; a.eps_x = eps_x;
         if (a.n > 0) {
+            prof_begin(PROF_GVP_HEAD, st);
             gvp_head_kernel<<<cdiv(a.n, TE), NT, m->smem, st>>>(a);
             KPD_TRY(check_launch("gvp_head_kernel"));
+            prof_end(PROF_GVP_HEAD, st);
         }
     }
     return 0;

@@ -7,6 +7,7 @@
 // the per-edge contractions live in the fused tile kernels (egnn.cu / gvp.cu).
 #include "common.cuh"
 #include <stdarg.h>
+#include <vector>
 
 namespace kpd {
 
@@ -30,6 +31,32 @@ int check_launch(const char* what) {
         return -2;
     }
     return 0;
+}
+
+struct ProfRec { cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static int g_prof_id = 0;
+static size_t g_prof_used = 0;
+static bool g_prof_open = false;
+
+static bool prof_active(int id, cudaStream_t st) {
+    if (g_prof_id != id || g_prof_used >= g_prof.size()) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+    return true;
+}
+
+void prof_begin(int id, cudaStream_t st) {
+    if (!prof_active(id, st)) return;
+    cudaEventRecord(g_prof[g_prof_used].a, st);
+    g_prof_open = true;
+}
+
+void prof_end(int id, cudaStream_t st) {
+    if (!g_prof_open || g_prof_id != id) return;
+    cudaEventRecord(g_prof[g_prof_used].b, st);
+    ++g_prof_used;
+    g_prof_open = false;
 }
 
 constexpr int LBM = 64, LBN = 64, LBK = 16;
@@ -190,6 +217,39 @@ int launch_sub(const float* a, const float* b, float* out, int n, cudaStream_t s
 }  // namespace kpd
 
 extern "C" const char* kpd_last_error(void) { return kpd::g_err; }
+extern "C" int64_t kpd_launch_count(void) { return kpd::launch_count(); }
+
+extern "C" int kpd_profile_enable(int32_t kernel_id, int32_t max_records) {
+    using namespace kpd;
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_used = 0;
+    g_prof_open = false;
+    g_prof_id = kernel_id;
+    if (kernel_id <= 0) return 0;
+    g_prof.resize(max_records > 0 ? max_records : 0);
+    for (auto& r : g_prof) {
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+            set_error("kpd_profile_enable: cudaEventCreate failed");
+            return -1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int kpd_profile_collect(double* total_ms, int32_t* count) {
+    using namespace kpd;
+    double tot = 0.0;
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        cudaEventSynchronize(g_prof[i].b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b) == cudaSuccess) tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = (int32_t)g_prof_used;
+    g_prof_used = 0;
+    return 0;
+}
 extern "C" int kpd_version(void) { return 100; }
 
 extern "C" int kpd_linear(const float* X, int32_t ldx, const float* WT, int32_t ldw, const float* bias,

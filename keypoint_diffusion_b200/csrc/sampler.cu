@@ -24,6 +24,7 @@ struct kpd_sampler {
     // device state carved from the caller's workspace
     float *x_lig, *h_lig, *x_kp, *h_kp, *v_kp, *eps_h, *eps_x, *kp_enc, *init_kp_com, *init_lig_pos, *t_cur;
     int *counter, *step;
+    long long* edge_accum;
     RunParams* rp;
     void* graph_ws;
     void* model_ws;
@@ -68,6 +69,7 @@ static int carve_sampler(kpd_sampler* s, void* ws, int cap_ll, int cap_kl, int64
     s->init_lig_pos = c.take<float>((int64_t)b.B * 3);
     s->t_cur = c.take<float>(4);
     s->rp = c.take<RunParams>(1);
+    s->edge_accum = c.take<long long>(4);
     s->graph_ws = c.take<char>(kpd_graph_workspace_bytes(&b));
     s->model_ws = c.take<char>(model_ws_bytes(&s->cfg, s->model, &b, cap_ll, cap_kl, s->kk.cap));
     if (bytes) *bytes = c.bytes();
@@ -100,8 +102,8 @@ extern "C" int64_t kpd_sampler_workspace_bytes(const kpd_sampler_config* cfg, co
 
 static int enqueue_step(kpd_sampler* s, cudaStream_t st) {
     KPD_TRY(launch_step_prologue(s->counter, s->step, s->t_cur, s->coef, st));
-    KPD_TRY(kpd_build_graph(&s->batch, s->x_lig, s->x_kp, &s->gp, &s->ll, &s->kl, s->has_lk ? &s->lk : nullptr,
-                            nullptr, nullptr, s->graph_ws, st));
+    KPD_TRY(build_graph_impl(&s->batch, s->x_lig, s->x_kp, &s->gp, &s->ll, &s->kl, s->has_lk ? &s->lk : nullptr,
+                             nullptr, nullptr, s->graph_ws, s->edge_accum, st));
     if (s->cfg.arch == 0) {
         KPD_TRY(kpd_egnn_forward(static_cast<const kpd_egnn_model*>(s->model), &s->batch, s->h_lig, s->x_lig, s->h_kp,
                                  s->x_kp, s->kp_enc, s->t_cur, 0, &s->ll, &s->kl, s->has_lk ? &s->lk : nullptr,
@@ -150,6 +152,18 @@ extern "C" void kpd_sampler_destroy(kpd_sampler* s) {
     delete s;
 }
 
+// mean edges per reverse step of the last run: out = {E_ll, E_kl (= E_lk), E_kk, steps}.  Synchronises.
+extern "C" int kpd_sampler_edge_stats(kpd_sampler* s, double* out) {
+    KPD_REQUIRE(s && out, "kpd_sampler_edge_stats: null argument");
+    long long h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(h, s->edge_accum, sizeof(h), cudaMemcpyDeviceToHost);
+    KPD_REQUIRE(e == cudaSuccess, "kpd_sampler_edge_stats: %s", cudaGetErrorString(e));
+    const double n = h[2] > 0 ? (double)h[2] : 1.0;
+    out[0] = h[0] / n; out[1] = h[1] / n; out[2] = s->has_lk ? (double)s->kk.cap : 0.0; out[3] = (double)h[2];
+    return 0;
+}
+
 extern "C" int32_t kpd_sampler_launches_per_step(const kpd_sampler* s) { return s ? s->launches_per_step : 0; }
 
 static int capture(kpd_sampler* s) {
@@ -188,6 +202,7 @@ extern "C" int kpd_sampler_run(kpd_sampler* s, float* x_kp, const float* h_kp, c
     // small pageable H2D copies: staged by the runtime before the call returns
     CU(cudaMemcpyAsync(s->rp, &rp, sizeof(rp), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s->counter, counter0, sizeof(counter0), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(s->edge_accum, 0, 4 * sizeof(long long), st));
 
     // frame setup (ligand_diffuser.py:348-370)
     KPD_TRY(launch_com(&b, s->x_lig, s->x_kp, 1, 0, s->init_kp_com, st));                // init_kp_com (:348)

@@ -1,0 +1,158 @@
+"""Drop-in denoiser modules: LigRecDynamics (EGNN) and LigRecDynamicsGVP.
+
+Same constructor kwargs, state_dict keys and ``forward(g, timestep, batch_idxs) -> (eps_h,
+eps_x)`` contract as the reference (models/dynamics.py:298-442, models/dynamics_gvp.py:104-255);
+``forward`` builds the ligand edges and evaluates the network in the CUDA library and leaves
+``g`` untouched (the reference's local_scope + remove_lig_edges).  CUDA only.
+"""
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .param_layout import ParamTree, egnn_dynamics_shapes, gvp_dynamics_shapes
+
+
+class _DeviceState:
+    """Per-module caches: packed weights, batch layout, static kk graph, ligand graph buffers."""
+
+    def __init__(self):
+        self.model = None
+        self.model_key = None
+        self.batch = None
+        self.batch_key = None
+        self.kk = None
+        self.kk_key = None
+        self.graphs = None
+
+
+class _DynamicsBase(ParamTree):
+    def _init_state(self):
+        object.__setattr__(self, "_st", _DeviceState())
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _layout(self, g):
+        """DeviceBatch + kk CSR for graph g (cached while the node counts / kk tensors are unchanged)."""
+        st = self._st
+        dev = g.device
+        if torch.device(dev).type != "cuda":
+            raise RuntimeError("keypoint_diffusion_b200 denoisers run on CUDA only (no CPU fallback)")
+        lig_n = g.batch_num_nodes("lig")
+        kp_n = g.batch_num_nodes("kp")
+        key = (tuple(lig_n.tolist()), tuple(kp_n.tolist()), str(dev))
+        if st.batch_key != key:
+            st.batch = ops.DeviceBatch(key[0], key[1], dev)
+            st.batch_key = key
+            st.graphs = None
+            st.kk_key = None
+        ks, kd = g.edges(form="uv", etype="kk")
+        kkey = (ks.data_ptr(), kd.data_ptr(), int(ks.numel()))
+        if st.kk_key != kkey:
+            st.kk = ops.Csr.from_edges(ks, kd, st.batch.n_kp, dev)
+            st.kk_key = kkey
+        return st.batch, st.kk
+
+    def _graphs(self, batch, with_lk):
+        st = self._st
+        if st.graphs is None:
+            gp = ops.GraphParams.from_module(self.ll_k, self.kl_k, self.graph_cutoffs)
+            st.graphs = ops.LigandGraphs(batch, gp, with_lk)
+        return st.graphs
+
+    def graph_params(self) -> ops.GraphParams:
+        return ops.GraphParams.from_module(self.ll_k, self.kl_k, self.graph_cutoffs)
+
+    @staticmethod
+    def _time(timestep, batch):
+        t = timestep.to(torch.float32)
+        if t.numel() == batch.B and batch.B > 1 and bool((t == t[0]).all()):
+            t = t[:1]          # one shared t (the sampling loop): skip the per-complex gather
+        return t.contiguous()
+
+
+class LigRecDynamics(_DynamicsBase):
+    """reference models/dynamics.py:298-442"""
+
+    def __init__(self, atom_nf, rec_nf, n_layers=4, hidden_nf=255, act_fn=nn.SiLU, use_tanh=False, message_norm=1,
+                 no_cg: bool = False, n_keypoints: int = 20, graph_cutoffs: dict = {}, update_kp_feat: bool = False,
+                 norm: bool = False, ll_k: int = 0, kl_k: int = 0, message_norm_effective: bool = False):
+        if act_fn is not nn.SiLU:
+            raise NotImplementedError("only act_fn=nn.SiLU (every shipped config) is implemented in CUDA")
+        super().__init__(egnn_dynamics_shapes(atom_nf, rec_nf, n_layers, hidden_nf, update_kp_feat, norm))
+        self._init_state()
+        self.atom_nf, self.rec_nf, self.n_layers, self.hidden_nf = atom_nf, rec_nf, n_layers, hidden_nf
+        self.use_tanh, self.message_norm, self.no_cg = use_tanh, message_norm, no_cg
+        self.n_keypoints, self.graph_cutoffs = n_keypoints, graph_cutoffs
+        self.update_kp_feat, self.norm, self.ll_k, self.kl_k = update_kp_feat, norm, ll_k, kl_k
+        # the reference's division by z never reaches the graph; False reproduces that
+        self.message_norm_effective = message_norm_effective
+
+    def device_model(self, device) -> ops.EgnnModel:
+        st = self._st
+        key = (self._param_key(), str(device))
+        if st.model_key != key:
+            st.model = ops.EgnnModel(self.state_dict(), atom_nf=self.atom_nf, rec_nf=self.rec_nf,
+                                     hidden_nf=self.hidden_nf, n_layers=self.n_layers, use_tanh=self.use_tanh,
+                                     update_kp_feat=self.update_kp_feat, norm=self.norm,
+                                     message_norm=self.message_norm, device=device,
+                                     z_effective=self.message_norm_effective)
+            st.model_key = key
+        return st.model
+
+    @torch.no_grad()
+    def forward(self, g, timestep: torch.Tensor, batch_idxs: Optional[Dict[str, torch.Tensor]] = None):
+        batch, kk = self._layout(g)
+        model = self.device_model(g.device)
+        lig, kp = g.nodes["lig"].data, g.nodes["kp"].data
+        x_lig, x_kp = lig["x_0"].float().contiguous(), kp["x_0"].float().contiguous()
+        graphs = self._graphs(batch, self.update_kp_feat).build(x_lig, x_kp)
+        return model.forward(batch, graphs, kk if self.update_kp_feat else None, lig["h_0"], x_lig, kp["h_0"], x_kp,
+                             self._time(timestep, batch))
+
+
+class LigRecDynamicsGVP(_DynamicsBase):
+    """reference models/dynamics_gvp.py:104-255"""
+
+    def __init__(self, n_lig_scalars, n_kp_scalars, vector_size: int = 16, n_convs=4, n_hidden_scalars=128,
+                 act_fn=nn.SiLU, message_norm=1, no_cg: bool = False, n_keypoints: int = 20, graph_cutoffs: dict = {},
+                 update_kp: bool = False, ll_k: int = 0, kl_k: int = 0, n_message_gvps: int = 3,
+                 n_update_gvps: int = 2, n_noise_gvps: int = 3, dropout: float = 0.0):
+        if no_cg:
+            raise NotImplementedError("No CG is not implemented for GVP")      # dynamics_gvp.py:111-112
+        if act_fn is not nn.SiLU:
+            raise NotImplementedError("only act_fn=nn.SiLU (every shipped config) is implemented in CUDA")
+        super().__init__(gvp_dynamics_shapes(n_lig_scalars, n_kp_scalars, vector_size, n_convs, n_hidden_scalars,
+                                             update_kp, n_message_gvps, n_update_gvps, n_noise_gvps))
+        self._init_state()
+        self.n_lig_scalars, self.n_kp_scalars, self.vector_size = n_lig_scalars, n_kp_scalars, vector_size
+        self.n_convs, self.n_hidden_scalars, self.message_norm = n_convs, n_hidden_scalars, message_norm
+        self.n_keypoints, self.graph_cutoffs, self.update_kp = n_keypoints, graph_cutoffs, update_kp
+        self.ll_k, self.kl_k = ll_k, kl_k
+        self.n_message_gvps, self.n_update_gvps, self.n_noise_gvps = n_message_gvps, n_update_gvps, n_noise_gvps
+        self.dropout = dropout   # eval-time no-op (models/gvp.py:133-134); sampling never trains
+
+    def device_model(self, device) -> ops.GvpModel:
+        st = self._st
+        key = (self._param_key(), str(device))
+        if st.model_key != key:
+            st.model = ops.GvpModel(self.state_dict(), n_lig_scalars=self.n_lig_scalars,
+                                    n_kp_scalars=self.n_kp_scalars, vector_size=self.vector_size,
+                                    n_convs=self.n_convs, n_hidden_scalars=self.n_hidden_scalars,
+                                    update_kp=self.update_kp, n_message_gvps=self.n_message_gvps,
+                                    n_update_gvps=self.n_update_gvps, n_noise_gvps=self.n_noise_gvps,
+                                    message_norm=self.message_norm, device=device)
+            st.model_key = key
+        return st.model
+
+    @torch.no_grad()
+    def forward(self, g, timestep: torch.Tensor, batch_idxs: Optional[Dict[str, torch.Tensor]] = None):
+        batch, kk = self._layout(g)
+        model = self.device_model(g.device)
+        lig, kp = g.nodes["lig"].data, g.nodes["kp"].data
+        x_lig, x_kp = lig["x_0"].float().contiguous(), kp["x_0"].float().contiguous()
+        graphs = self._graphs(batch, self.update_kp).build(x_lig, x_kp)
+        return model.forward(batch, graphs, kk if self.update_kp else None, lig["h_0"], x_lig, kp["h_0"], x_kp,
+                             kp["v_0"], self._time(timestep, batch))

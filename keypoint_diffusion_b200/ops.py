@@ -194,7 +194,7 @@ class EgnnModel(_Model):
         check(lib.kpd_egnn_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_egnn_create")
 
     def __del__(self):
-        if getattr(self, "handle", None) and self.handle.value:
+        if getattr(self, "handle", None) and self.handle.value and lib is not None:
             lib.kpd_egnn_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -245,7 +245,7 @@ class GvpModel(_Model):
         check(lib.kpd_gvp_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_gvp_create")
 
     def __del__(self):
-        if getattr(self, "handle", None) and self.handle.value:
+        if getattr(self, "handle", None) and self.handle.value and lib is not None:
             lib.kpd_gvp_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -308,7 +308,7 @@ class Sampler:
                                      cap_kl, ptr(self.ws), n, C.byref(self.handle)), "kpd_sampler_create")
 
     def __del__(self):
-        if getattr(self, "handle", None) and self.handle.value:
+        if getattr(self, "handle", None) and self.handle.value and lib is not None:
             lib.kpd_sampler_destroy(self.handle)
             self.handle = C.c_void_p()
 

@@ -1,0 +1,44 @@
+"""Batch helpers with the reference's names (reference utils.py:81-170), on the duck-typed
+graph surface of hetero.HeteroBatch (or a real DGL heterograph)."""
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import hetero
+
+
+def get_batch_info(g) -> Tuple[dict, dict]:
+    """reference utils.py:81-90"""
+    return ({nt: g.batch_num_nodes(nt) for nt in g.ntypes},
+            {et: g.batch_num_edges(et) for et in g.canonical_etypes})
+
+
+def get_batch_idxs(g) -> Dict[str, torch.Tensor]:
+    """reference utils.py:158-170: node -> complex index per node type."""
+    ar = torch.arange(g.batch_size, device=g.device)
+    return {nt: ar.repeat_interleave(g.batch_num_nodes(nt).to(g.device)) for nt in g.ntypes}
+
+
+def get_edges_per_batch(edge_node_idxs: torch.Tensor, batch_size: int, node_batch_idxs: torch.Tensor):
+    """reference utils.py:92-98 (edges grouped by complex)."""
+    if edge_node_idxs.numel() == 0:
+        return torch.zeros(batch_size, dtype=torch.long, device=edge_node_idxs.device)
+    return torch.bincount(node_batch_idxs[edge_node_idxs], minlength=batch_size)
+
+
+def copy_graph(g, n_copies: int, lig_atoms_per_copy: torch.Tensor = None, batched_graph=False) -> List:
+    """reference utils.py:103-156: n_copies of a single-complex graph, optionally with a chosen
+    number of (zero-filled) ligand atoms per copy."""
+    out = []
+    for i in range(n_copies):
+        bnn = {nt: g.batch_num_nodes(nt).clone() for nt in g.ntypes}
+        nd = {nt: {k: v.detach().clone() for k, v in g.nodes[nt].data.items()} for nt in g.ntypes}
+        if lig_atoms_per_copy is not None:
+            n = int(lig_atoms_per_copy[i])
+            bnn["lig"] = torch.tensor([n], device=g.device)
+            nd["lig"] = {k: torch.zeros((n,) + tuple(v.shape[1:]), dtype=v.dtype, device=g.device)
+                         for k, v in g.nodes["lig"].data.items()}
+        edges = {et: tuple(t.clone() for t in g.edges(form="uv", etype=et)) for et in g.canonical_etypes}
+        bne = {et: g.batch_num_edges(et).clone() for et in g.canonical_etypes}
+        out.append(hetero.HeteroBatch(bnn, nd, edges, bne))
+    return out

@@ -1,0 +1,106 @@
+"""CPU: the drop-in modules' constructor / state_dict contract and host-side logic, and that the
+C-ABI library loads and exports every symbol include/kpdiff_b200.h declares (no compute)."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import pytest
+import torch
+import yaml
+
+from helpers import GOLDEN
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _cfgs():
+    return yaml.safe_load(open(GOLDEN / "shipped_configs.yml"))
+
+
+@pytest.mark.parametrize("name", ["egnn_20kp", "egnn_40kp", "egnn_all_atom", "egnn_ca", "gvp_20kp", "gvp_40kp",
+                                  "gvp_all_atom", "gvp_ca"])
+def test_state_dict_layout_matches_reference(name, monkeypatch):
+    """model_from_config(cfg).state_dict() has exactly the reference's keys and shapes, so
+    trained_models/*/model.pt loads with strict=True."""
+    from keypoint_diffusion_b200 import model_from_config
+    monkeypatch.chdir(ROOT)                      # dataset.location is relative, as in the reference
+    inv = json.load(open(GOLDEN / "state_dict_shapes.json"))[name]
+    model = model_from_config(_cfgs()[name])
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == inv
+    # round trip through a checkpoint-shaped dict
+    sd = {k: torch.randn(v) if v != [0] else torch.empty(0) for k, v in inv.items()}
+    model.load_state_dict(sd, strict=True)
+    assert torch.equal(model.state_dict()["gamma.gamma"], sd["gamma.gamma"])
+
+
+def test_constructor_errors_match_reference(monkeypatch):
+    from keypoint_diffusion_b200 import KeypointDiffusion, LigRecDynamicsGVP
+    monkeypatch.chdir(ROOT)
+    d = Path("data/bindingmoad_processed")
+    with pytest.raises(ValueError):
+        KeypointDiffusion(10, 128, d, architecture="transformer")
+    with pytest.raises(ValueError):
+        KeypointDiffusion(10, 128, d, rec_encoder_type="other", rec_encoder_config={"k_closest": 3})
+    with pytest.raises(ValueError):
+        KeypointDiffusion(10, 128, Path("/nonexistent"))
+    with pytest.raises(NotImplementedError):
+        LigRecDynamicsGVP(10, 128, no_cg=True)
+
+
+def test_no_cpu_fallback(monkeypatch):
+    """CPU tensors are refused loudly instead of being computed some other way."""
+    from keypoint_diffusion_b200 import HeteroBatch, LigRecDynamics, synthetic
+    dyn = LigRecDynamics(10, 16, n_layers=1, hidden_nf=15, graph_cutoffs={"ll": 5, "kl": 8}, kl_k=3)
+    g = HeteroBatch.from_pockets([synthetic.keypoint_pocket(0, 5, 16)], [4], 10)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dyn(g, torch.tensor([0.5]), None)
+
+
+def test_library_exports_every_declared_symbol():
+    from keypoint_diffusion_b200 import _lib
+    header = (ROOT / "include" / "kpdiff_b200.h").read_text()
+    declared = set(re.findall(r"\b(kpd_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/kpdiff_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED)
+
+
+def test_hetero_batch_roundtrip():
+    from keypoint_diffusion_b200 import HeteroBatch, hetero, synthetic, utils
+    pk = [synthetic.keypoint_pocket(i, 6, 12, 4) for i in range(2)]
+    g = HeteroBatch.from_pockets(pk, [5, 2, 9], 10)
+    assert g.batch_size == 3 and g.num_nodes("lig") == 16 and g.num_nodes("kp") == 18
+    bi = utils.get_batch_idxs(g)
+    assert bi["lig"].tolist() == [0] * 5 + [1] * 2 + [2] * 9
+    parts = hetero.unbatch(g)
+    assert [p.num_nodes("lig") for p in parts] == [5, 2, 9]
+    g2 = hetero.batch(parts)
+    assert torch.equal(g2.nodes["kp"].data["x_0"], g.nodes["kp"].data["x_0"])
+    assert torch.equal(g2.edges(form="uv", etype="kk")[1], g.edges(form="uv", etype="kk")[1])
+    copies = utils.copy_graph(parts[0], 3, torch.tensor([4, 6, 8]))
+    assert [c.num_nodes("lig") for c in copies] == [4, 6, 8]
+    with g.local_scope():
+        g.nodes["lig"].data["h_0"] = torch.ones(16, 10)
+    assert float(g.nodes["lig"].data["h_0"].abs().sum()) == 0.0
+
+
+def test_ligand_size_distribution():
+    from keypoint_diffusion_b200 import LigandSizeDistribution
+    d = LigandSizeDistribution(ROOT / "data" / "bindingmoad_processed")
+    torch.manual_seed(0)
+    s = d.sample(torch.tensor([336, 5, 9999]), 50)
+    assert s.shape == (3, 50) and int(s.min()) >= 2 and int(s.max()) <= 60
+
+
+def test_edge_capacity_and_packer_offsets():
+    from keypoint_diffusion_b200 import ops, pack
+    b = object.__new__(ops.DeviceBatch)
+    b.lig_n, b.kp_n = [20, 3, 60], [20, 20, 40]
+    gp = ops.GraphParams(ll_k=0, ll_r=5, kl_k=5)
+    assert ops.DeviceBatch.edge_capacity(b, gp) == (20 * 19 + 3 * 2 + 60 * 59, 20 * 5 + 20 * 3 + 40 * 5)
+    gp = ops.GraphParams(ll_k=4, kl_k=0, kl_r=8)
+    assert ops.DeviceBatch.edge_capacity(b, gp) == (20 * 4 + 3 * 2 + 60 * 4, 20 * 20 + 20 * 3 + 40 * 60)
