@@ -43,10 +43,12 @@ struct GvpW {
 // GVP.forward (models/gvp.py:89-116) on a shared-memory tile of TE rows.
 //   S: [TE][lds], input scalars in cols [0,fin); V: [TE][VMAX][3] input vectors (vin used).
 //   On return S cols [0,fout) hold feats_out and V rows [0,vout) hold the gated vectors.
+template <int RM>
 __device__ void gvp_tile(const GvpW& g, float* S, int lds, float* V, float* Vh, float* Bs) {
+    constexpr int TR = 16 * RM;   // rows of this tile
     const int tid = threadIdx.x;
     // Vh = einsum('b v c, v h -> b h c'); sh = sqrt(clamp(sum_c Vh^2, 1e-8))  (:96, :99)
-    for (int idx = tid; idx < TE * g.hd; idx += NT) {
+    for (int idx = tid; idx < TR * g.hd; idx += NT) {
         const int r = idx / g.hd, hh = idx - r * g.hd;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         const float* v = V + r * (VMAX * 3);
@@ -60,7 +62,7 @@ __device__ void gvp_tile(const GvpW& g, float* S, int lds, float* V, float* Vh, 
     }
     __syncthreads();
     // Vu = einsum('b h c, h u -> b u c')  (:97) -> V (the input vectors are dead now)
-    for (int idx = tid; idx < TE * g.vout; idx += NT) {
+    for (int idx = tid; idx < TR * g.vout; idx += NT) {
         const int r = idx / g.vout, u = idx - r * g.vout;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         const float* vh = Vh + r * (VMAX * 3);
@@ -72,18 +74,18 @@ __device__ void gvp_tile(const GvpW& g, float* S, int lds, float* V, float* Vh, 
         o[0] = a0; o[1] = a1; o[2] = a2;
     }
     // feats_out = SiLU(Linear(cat(feats, sh)))  (:101-103)
-    float acc[TE / 16][16];
+    float acc[RM][16];
 #pragma unroll
-    for (int i = 0; i < TE / 16; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
     const int nmain = (g.fout + 3) & ~3;
-    tile_gemm<TE / 16>(S, lds, g.WfT, g.ldf, g.fin + g.hd, nmain, Bs, acc);
+    tile_gemm<RM>(S, lds, g.WfT, g.ldf, g.fin + g.hd, nmain, Bs, acc);
     {
         const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
-        for (int i = 0; i < TE / 16; ++i) {
-            const int r = ty * (TE / 16) + i;
+        for (int i = 0; i < RM; ++i) {
+            const int r = ty * (RM) + i;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int col = 4 * tx + 64 * j;
@@ -100,7 +102,7 @@ __device__ void gvp_tile(const GvpW& g, float* S, int lds, float* V, float* Vh, 
     }
     __syncthreads();
     // gating = Linear(feats_out); vectors_out = act(gating) * Vu  (:105-111)
-    for (int idx = tid; idx < TE * g.vout; idx += NT) {
+    for (int idx = tid; idx < TR * g.vout; idx += NT) {
         const int r = idx / g.vout, u = idx - r * g.vout;
         float a = g.bg[u];
         const float* s = S + r * lds;
@@ -113,10 +115,11 @@ __device__ void gvp_tile(const GvpW& g, float* S, int lds, float* V, float* Vh, 
 }
 
 // scalar LayerNorm over S cols [0,Sdim) (one warp per row) + GVP vector norm (gvp.py:159-166)
+template <int RM>
 __device__ void gvp_layernorm_tile(float* S, int lds, int Sdim, float* V, int nv, const float* w, const float* b) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int rr = 0; rr < TE / 8; ++rr) {
-        const int r = warp * (TE / 8) + rr;
+    for (int rr = 0; rr < 2 * RM; ++rr) {
+        const int r = warp * (2 * RM) + rr;
         float* x = S + r * lds;
         float s = 0.f;
         for (int c = lane; c < Sdim; c += 32) s += x[c];
@@ -147,20 +150,26 @@ struct GvpSmem {
     int* src_s; int* dst_s;
 };
 
+template <int RM>
 __device__ __forceinline__ GvpSmem gvp_carve_smem(float* smem, int lds) {
+    constexpr int TR = 16 * RM;
     GvpSmem m;
     m.S = smem;
-    m.Bs = m.S + TE * lds;
+    m.Bs = m.S + TR * lds;
     m.V = m.Bs + BS_FLOATS;
-    m.Vh = m.V + TE * VMAX * 3;
-    m.src_s = reinterpret_cast<int*>(m.Vh + TE * VMAX * 3);
-    m.dst_s = m.src_s + TE;
+    m.Vh = m.V + TR * VMAX * 3;
+    m.src_s = reinterpret_cast<int*>(m.Vh + TR * VMAX * 3);
+    m.dst_s = m.src_s + TR;
     return m;
 }
 
-static size_t gvp_smem_bytes(int lds) {
-    return sizeof(float) * ((size_t)TE * lds + BS_FLOATS + 2 * TE * VMAX * 3) + sizeof(int) * 2 * TE;
+static size_t gvp_smem_bytes(int lds, int rows) {
+    return sizeof(float) * ((size_t)rows * lds + BS_FLOATS + 2 * rows * VMAX * 3) + sizeof(int) * 2 * rows;
 }
+
+constexpr int RM_EDGE = TE / 16;   // 64-edge tiles (seg_gather's tile size)
+constexpr int RM_NODE = 2;         // 32-node tiles: node counts are small, more CTAs fill the GPU
+constexpr int TN = 16 * RM_NODE;
 
 struct GvpEtypeArgs {
     const int* rowptr; const int* src; const int* dst; int n_dst;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_edge_kernel(const GvpEdgeLaunch L) 
     if (tile_begin >= E) return;
     const int n = min(TE, E - tile_begin);
     extern __shared__ __align__(16) float smem[];
-    GvpSmem m = gvp_carve_smem(smem, L.lds);
+    GvpSmem m = gvp_carve_smem<RM_EDGE>(smem, L.lds);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Sd = L.Sdim, Vd = L.Vdim, lds = L.lds;
 
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_edge_kernel(const GvpEdgeLaunch L) 
         for (int k = lane; k < Vd * 3; k += 32) m.V[r * (VMAX * 3) + 3 + k] = vp[k];
     }
     __syncthreads();
-    for (int i = 0; i < L.n_msg; ++i) gvp_tile(a.msg[i], m.S, lds, m.V, m.Vh, m.Bs);
+    for (int i = 0; i < L.n_msg; ++i) gvp_tile<RM_EDGE>(a.msg[i], m.S, lds, m.V, m.Vh, m.Bs);
 
     SegOut o;
     o.part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
@@ -241,16 +250,20 @@ struct GvpNodeArgs {
     const float *mln_w, *mln_b, *uln_w, *uln_b;
 };
 
-__global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeArgs a) {
+struct GvpNodeLaunch { GvpNodeArgs nt[2]; };
+
+__global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeLaunch L) {
+    const GvpNodeArgs& a = L.nt[blockIdx.y];
     extern __shared__ __align__(16) float smem[];
-    GvpSmem m = gvp_carve_smem(smem, a.lds);
+    GvpSmem m = gvp_carve_smem<RM_NODE>(smem, a.lds);
     const int tid = threadIdx.x;
-    const int n0 = blockIdx.x * TE;
-    const int n = min(TE, a.n - n0);
+    const int n0 = blockIdx.x * TN;
+    if (n0 >= a.n) return;
+    const int n = min(TN, a.n - n0);
     const int Sd = a.Sdim, Vd = a.Vdim, lds = a.lds, W = Sd + 3 * Vd;
     zero_stage(m.Bs);
     // features + aggregated messages / norm  (gvp.py:501-520)
-    for (int idx = tid; idx < TE * W; idx += NT) {
+    for (int idx = tid; idx < TN * W; idx += NT) {
         const int r = idx / W, c = idx - r * W;
         const int nd = n0 + min(r, n - 1);
         float msg = 0.f;
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeArgs a) {
         else m.V[r * (VMAX * 3) + (c - Sd)] = a.v[(size_t)nd * (3 * Vd) + (c - Sd)] + msg;
     }
     __syncthreads();
-    gvp_layernorm_tile(m.S, lds, Sd, m.V, Vd, a.mln_w, a.mln_b);
+    gvp_layernorm_tile<RM_NODE>(m.S, lds, Sd, m.V, Vd, a.mln_w, a.mln_b);
     // stash the normalised features as the residual (rows of this CTA only)
     for (int idx = tid; idx < n * W; idx += NT) {
         const int r = idx / W, c = idx - r * W;
@@ -283,15 +296,15 @@ __global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeArgs a) {
         else a.v[(size_t)(n0 + r) * (3 * Vd) + (c - Sd)] = m.V[r * (VMAX * 3) + (c - Sd)];
     }
     __syncthreads();
-    for (int i = 0; i < a.n_upd; ++i) gvp_tile(a.upd[i], m.S, lds, m.V, m.Vh, m.Bs);
-    for (int idx = tid; idx < TE * W; idx += NT) {
+    for (int i = 0; i < a.n_upd; ++i) gvp_tile<RM_NODE>(a.upd[i], m.S, lds, m.V, m.Vh, m.Bs);
+    for (int idx = tid; idx < TN * W; idx += NT) {
         const int r = idx / W, c = idx - r * W;
         const int nd = n0 + min(r, n - 1);
         if (c < Sd) m.S[r * lds + c] += a.s[(size_t)nd * Sd + c];
         else m.V[r * (VMAX * 3) + (c - Sd)] += a.v[(size_t)nd * (3 * Vd) + (c - Sd)];
     }
     __syncthreads();
-    gvp_layernorm_tile(m.S, lds, Sd, m.V, Vd, a.uln_w, a.uln_b);
+    gvp_layernorm_tile<RM_NODE>(m.S, lds, Sd, m.V, Vd, a.uln_w, a.uln_b);
     for (int idx = tid; idx < n * W; idx += NT) {
         const int r = idx / W, c = idx - r * W;
         if (c < Sd) a.s[(size_t)(n0 + r) * Sd + c] = m.S[r * lds + c];
@@ -309,20 +322,20 @@ struct GvpHeadArgs {
 
 __global__ void __launch_bounds__(NT, 1) gvp_head_kernel(const GvpHeadArgs a) {
     extern __shared__ __align__(16) float smem[];
-    GvpSmem m = gvp_carve_smem(smem, a.lds);
+    GvpSmem m = gvp_carve_smem<RM_NODE>(smem, a.lds);
     const int tid = threadIdx.x;
-    const int n0 = blockIdx.x * TE;
-    const int n = min(TE, a.n - n0);
+    const int n0 = blockIdx.x * TN;
+    const int n = min(TN, a.n - n0);
     const int Sd = a.Sdim, Vd = a.Vdim, lds = a.lds, W = Sd + 3 * Vd;
     zero_stage(m.Bs);
-    for (int idx = tid; idx < TE * W; idx += NT) {
+    for (int idx = tid; idx < TN * W; idx += NT) {
         const int r = idx / W, c = idx - r * W;
         const int nd = n0 + min(r, n - 1);
         if (c < Sd) m.S[r * lds + c] = a.s[(size_t)nd * Sd + c];
         else m.V[r * (VMAX * 3) + (c - Sd)] = a.v[(size_t)nd * (3 * Vd) + (c - Sd)];
     }
     __syncthreads();
-    for (int i = 0; i < a.n_gvps; ++i) gvp_tile(a.g[i], m.S, lds, m.V, m.Vh, m.Bs);
+    for (int i = 0; i < a.n_gvps; ++i) gvp_tile<RM_NODE>(a.g[i], m.S, lds, m.V, m.Vh, m.Bs);
     // to_scalar_output + vectors.squeeze(1)  (dynamics_gvp.py:42-43)
     for (int idx = tid; idx < n * (a.F + 3); idx += NT) {
         const int r = idx / (a.F + 3), c = idx - r * (a.F + 3);
@@ -354,7 +367,7 @@ struct kpd_gvp_model {
     std::vector<GvpLayerW> layers;
     GvpW head[MAXG];
     const float* WoT; const float* bo;
-    size_t smem;
+    size_t smem, smem_node;
 };
 
 struct GvpWs {
@@ -441,10 +454,11 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         m->head[k] = last ? G(m->V, 1, m->S, 64, 0) : G(m->V, m->V, m->S, m->S, 1);   // dynamics_gvp.py:18-25
     }
     m->WoT = P(); m->bo = P();
-    m->smem = gvp_smem_bytes(m->lds);
+    m->smem = gvp_smem_bytes(m->lds, TE);
+    m->smem_node = gvp_smem_bytes(m->lds, TN);
     cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
-    cudaError_t e2 = cudaFuncSetAttribute(gvp_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
-    cudaError_t e3 = cudaFuncSetAttribute(gvp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
+    cudaError_t e2 = cudaFuncSetAttribute(gvp_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_node);
+    cudaError_t e3 = cudaFuncSetAttribute(gvp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_node);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
         delete m;
         KPD_REQUIRE(false, "kpd_gvp_create: cannot set the dynamic shared memory size of the GVP kernels");
@@ -524,26 +538,32 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
         KPD_TRY(check_launch("gvp_edge_kernel"));
         prof_end(PROF_GVP_EDGE, st);
-        for (int nt = 0; nt < W.n_dst; ++nt) {
-            if (N[nt] <= 0) continue;
-            GvpNodeArgs a;
-            memset(&a, 0, sizeof(a));
-            a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
-            a.n_upd = m->cfg.n_update_gvps; a.n_et = 2;
-            a.s = w.s[nt]; a.v = w.v[nt];
-            for (int k = 0; k < 2; ++k) {
-                const int e = nt * 2 + k;
-                a.rowptr[k] = G[e]->rowptr; a.sm[k] = w.sm[e]; a.vm[k] = w.vm[e]; a.part[k] = w.part[e];
+        {
+            GvpNodeLaunch NL;
+            memset(&NL, 0, sizeof(NL));
+            int max_n = 0;
+            for (int nt = 0; nt < W.n_dst; ++nt) {
+                GvpNodeArgs& a = NL.nt[nt];
+                a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
+                a.n_upd = m->cfg.n_update_gvps; a.n_et = 2;
+                a.s = w.s[nt]; a.v = w.v[nt];
+                for (int k = 0; k < 2; ++k) {
+                    const int e = nt * 2 + k;
+                    a.rowptr[k] = G[e]->rowptr; a.sm[k] = w.sm[e]; a.vm[k] = w.vm[e]; a.part[k] = w.part[e];
+                }
+                a.norm_mode = norm_mode; a.norm_const = m->cfg.message_norm;
+                a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
+                a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
+                for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
+                a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
+                if (a.n > max_n) max_n = a.n;
             }
-            a.norm_mode = norm_mode; a.norm_const = m->cfg.message_norm;
-            a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
-            a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
-            for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
-            a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
-            prof_begin(PROF_GVP_NODE, st);
-            gvp_node_kernel<<<cdiv(a.n, TE), NT, m->smem, st>>>(a);
-            KPD_TRY(check_launch("gvp_node_kernel"));
-            prof_end(PROF_GVP_NODE, st);
+            if (max_n > 0) {
+                prof_begin(PROF_GVP_NODE, st);
+                gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
+                KPD_TRY(check_launch("gvp_node_kernel"));
+                prof_end(PROF_GVP_NODE, st);
+            }
         }
     }
     {
@@ -556,7 +576,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         a.WoT = m->WoT; a.bo = m->bo; a.eps_h = eps_h; a.eps_x = eps_x;
         if (a.n > 0) {
             prof_begin(PROF_GVP_HEAD, st);
-            gvp_head_kernel<<<cdiv(a.n, TE), NT, m->smem, st>>>(a);
+            gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);
             KPD_TRY(check_launch("gvp_head_kernel"));
             prof_end(PROF_GVP_HEAD, st);
         }
