@@ -104,6 +104,14 @@ int kpd_linear(const float* X, int32_t ldx, const float* WT, int32_t ldw, const 
                const float* R, int32_t ldr, float* Y, int32_t ldy, int32_t M, int32_t K, int32_t N,
                int32_t act, void* stream);
 
+/* Same operation on the 5th-generation tensor cores (bf16 operands, fp32 accumulation in TMEM):
+ * tcgen05.mma with the weight pre-packed into K-major k-step slabs by pack.pack_tc_weight and fetched
+ * with cp.async.bulk; X is converted to bf16 while it is staged.  N <= 256.  This is the "bf16 GEMM
+ * mode" of the north star: results differ from fp32 at the 1e-3 level and are reported separately. */
+int kpd_tc_linear(const float* X, int32_t ldx, const void* W_packed, const float* bias, const float* R,
+                  int32_t ldr, float* Y, int32_t ldy, int32_t M, int32_t K, int32_t N, int32_t act,
+                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b)+(d) EGNN denoiser.  Replaces LigRecDynamics.forward (models/dynamics.py:342-385),
  * LigRecEGNN.forward (:266-294) and LigRecConv.forward/message (:89-217).

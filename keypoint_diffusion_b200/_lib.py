@@ -68,6 +68,7 @@ def _load():
         "kpd_build_graph": (I, [C.POINTER(KpdBatch), P, P, C.POINTER(KpdGraphParams), C.POINTER(KpdCsr),
                                 C.POINTER(KpdCsr), C.POINTER(KpdCsr), P, P, P, P]),
         "kpd_linear": (I, [P, I, P, I, P, P, I, P, I, I, I, I, I, P]),
+        "kpd_tc_linear": (I, [P, I, P, P, P, I, P, I, I, I, I, I, P]),
         "kpd_egnn_create": (I, [C.POINTER(KpdEgnnConfig), P, C.POINTER(L), I, C.POINTER(P)]),
         "kpd_egnn_destroy": (None, [P]),
         "kpd_egnn_dims": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

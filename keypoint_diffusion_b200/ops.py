@@ -154,6 +154,18 @@ def linear(x, wt, bias=None, residual=None, act=0, n_out=None):
     return y
 
 
+def tc_linear(x, w_packed, n_out, bias=None, residual=None, act=0):
+    """Y = act(X @ W^T + b) (+R) on tcgen05 tensor cores (bf16 operands, fp32 accumulate); w_packed from
+    pack.pack_tc_weight."""
+    _require_cuda(x, w_packed)
+    M, K = x.shape
+    y = torch.empty(M, n_out, dtype=torch.float32, device=x.device)
+    check(lib.kpd_tc_linear(ptr(x), x.stride(0), ptr(w_packed), ptr(bias), ptr(residual),
+                            residual.stride(0) if residual is not None else 0, ptr(y), y.stride(0), M, K, n_out, act,
+                            _stream()), "kpd_tc_linear")
+    return y
+
+
 class _Model:
     arch = -1
 

@@ -176,3 +176,18 @@ def pack_gvp(sd: Dict[str, torch.Tensor], *, n_lig_scalars, n_kp_scalars, vector
         put_gvp(f"{q}gvps.{i}")
     w, b = _linT(sd, q + "to_scalar_output"); put(w); put(b)
     return blob.finish(device), offs
+
+
+def pack_tc_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Linear weight [N, K] -> bf16 "k-step slabs" for the tcgen05 kernels (csrc/tc.cuh):
+    for every k-step of 16 input features, 2 k-chunks x (NB/8) row groups x (8 rows x 8 bf16 = 128 B), i.e. the
+    no-swizzle K-major canonical UMMA layout, so one slab is one contiguous bulk copy.  N is padded to a
+    multiple of 16 (NB), K to a multiple of 16, with zeros."""
+    w = w.detach().float().cpu()
+    N, K = w.shape
+    NB = (N + 15) // 16 * 16
+    ks = (K + 15) // 16
+    wp = torch.zeros(NB, ks * 16)
+    wp[:N, :K] = w
+    out = wp.view(NB // 8, 8, ks, 2, 8).permute(2, 3, 0, 1, 4).contiguous()
+    return out.to(torch.bfloat16).reshape(-1)
