@@ -197,6 +197,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=None, help="reverse steps per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="headline mode: fp32 (SIMT, parity-green) or bf16 (tcgen05 tensor cores, GVP only)")
+    ap.add_argument("--no-bf16-block", action="store_true", help="skip the separately-reported bf16 measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -296,6 +299,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
+    if args.precision == "bf16":
+        if arch != "gvp":
+            raise SystemExit("the bf16 tensor-core mode exists for the GVP denoiser only (round 1)")
+        model.dynamics.set_precision("bf16")
     launches0 = int(_lib.lib.kpd_launch_count())
     for _ in range(max(args.warmup, 0)):
         one_sample_device()
@@ -304,7 +311,7 @@ def main():
     dt, _ = timed(one_sample_device, args.steps)
     clk = clocks.finish()
     value = world * B * args.steps / dt
-    sampler = next(iter(model._samplers.values()))
+    sampler = list(model._samplers.values())[-1]
     lps = sampler.launches_per_step
 
     one_sample_e2e()
@@ -316,7 +323,7 @@ def main():
 
     out = {"metric": metric, "value": value, "unit": "ligands/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "clocks": clk,
+           "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clk,
            "e2e": {"value": e2e_value, "unit": "ligands/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
            "reverse_steps_per_s": 1000 * args.steps / dt, "launches_per_reverse_step": lps}
 
@@ -368,7 +375,35 @@ def main():
                            "kernel_ms_per_reverse_step": tot.value / n_rev,
                            "kernel_share_of_step": (tot.value / n_rev) / (dt / args.steps * 1e3 / 1000.0),
                            "flops_per_edge": fe, "mean_edges_per_step": {"ll": e_ll, "kl": e_kl, "lk": e_kl, "kk": e_kk},
-                           "note": "fp32 SIMT tile GEMM in round 1; fraction is against the measured bf16 tensor peak"}
+                           "note": ("fp32 SIMT tile GEMM (parity mode); fraction is against the measured bf16 tensor peak"
+                                    if args.precision == "fp32" else
+                                    "tcgen05 bf16 tile GEMM + SIMT vector/gather/reduce phases in one fused kernel")}
+
+    # ------------------------------------------------------------------ bf16 tensor-core mode, stated separately
+    if arch == "gvp" and args.precision == "fp32" and not args.no_bf16_block:
+        model.dynamics.set_precision("bf16")
+        one_sample_device()
+        one_sample_device()
+        dt16, _ = timed(one_sample_device, args.steps)
+        blk = {"value": world * B * args.steps / dt16, "unit": "ligands/s", "ms_per_step": dt16 / args.steps * 1e3,
+               "dtype": "bf16 operands, fp32 accumulate (tcgen05)",
+               "accuracy": "denoiser output within ~2e-3 of fp32 (tests/test_gpu_tensorcore.py); not the parity mode"}
+        if not args.no_roofline:
+            _lib.check(_lib.lib.kpd_profile_enable(2, 1000 * n_layers + 16))
+            model.sample_from_encoded_receptors(g_dev, init_lig_pos=init_dev, seed=1234, use_cuda_graph=False,
+                                                return_device_tensors=True)
+            torch.cuda.synchronize()
+            tot16, cnt16 = C.c_double(), C.c_int32()
+            _lib.check(_lib.lib.kpd_profile_collect(C.byref(tot16), C.byref(cnt16)))
+            _lib.lib.kpd_profile_enable(0, 0)
+            avg16 = tot16.value / max(cnt16.value, 1)
+            ach16 = (flops_per_step * n_rev / max(cnt16.value, 1)) / (avg16 * 1e-3) / 1e12 if avg16 > 0 else 0.0
+            blk["roofline"] = {"bound": "tensor", "achieved": ach16, "peak": peak, "unit": "TFLOP/s", "frac": ach16 / peak,
+                               "kernel": "gvp_edge_tc_kernel", "avg_launch_ms": avg16, "launches_timed": int(cnt16.value),
+                               "kernel_ms_per_reverse_step": tot16.value / n_rev,
+                               "kernel_share_of_step": (tot16.value / n_rev) / (dt16 / args.steps * 1e3 / 1000.0)}
+        out["bf16_mode"] = blk
+        model.dynamics.set_precision("fp32")
 
     # gpu launches in the two timed regions: replayed graphs do not re-count, so derive from the captured sequence
     per_run = lps * 1000 + 9

@@ -200,9 +200,9 @@ __device__ __forceinline__ void seg_reduce_column(const float* __restrict__ C, i
 //   rows [r0,r1) of the CSR; tiles of TE edges; part is [ntiles][2][pw].
 __device__ __forceinline__ float seg_gather(const float* __restrict__ out, int ld_out,
                                             const float* __restrict__ part, int pw, int r0, int r1,
-                                            int d, int c) {
+                                            int d, int c, int tile = TE) {
     if (r1 <= r0) return 0.0f;
-    const int t0 = r0 / TE, t1 = (r1 - 1) / TE;
+    const int t0 = r0 / tile, t1 = (r1 - 1) / tile;
     if (t0 == t1) {
         // complete inside one tile -- unless the tile boundary coincides, still a direct store
         return out[(size_t)d * ld_out + c];

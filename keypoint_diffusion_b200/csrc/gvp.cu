@@ -22,6 +22,7 @@
 //   head:         n_noise_gvps x (Wh, Wu, WfT, bf, WgT, bg), WoT, bo
 //   etypes(l) = (ll, kl, lk, kk) if update_kp and l != n_convs-1 else (ll, kl)
 #include "common.cuh"
+#include "tc.cuh"
 #include <string.h>
 #include <vector>
 
@@ -37,6 +38,8 @@ struct GvpW {
     const float* bf;    // [ldf]
     const float* WgT;   // [fout][vout]
     const float* bg;    // [vout]
+    const uint4* WfP;   // bf16 mode: to_feats_out weight as tcgen05 k-step slabs (pack_tc_weight)
+    const uint4* WgP;   // bf16 mode: gates weight, rows padded to 16
     int vin, vout, hd, fin, fout, ldf, sigmoid_gate;
 };
 
@@ -180,7 +183,7 @@ struct GvpEtypeArgs {
 
 struct GvpEdgeLaunch {
     GvpEtypeArgs e[4];
-    int Sdim, Vdim, n_msg, lds, pw, rbf_dim;
+    int Sdim, Vdim, n_msg, lds, pw, rbf_dim, kch;
     float rbf_step, rbf_sigma;
 };
 
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_edge_kernel(const GvpEdgeLaunch L) 
 }
 
 struct GvpNodeArgs {
-    int n, Sdim, Vdim, lds, pw, n_upd, n_et;
+    int n, Sdim, Vdim, lds, pw, n_upd, n_et, kch, edge_tile;
     float* s; float* v;                        // node features, updated in place
     const int* rowptr[2]; const float* sm[2]; const float* vm[2]; const float* part[2];
     int norm_mode; float norm_const;           // 0 const, 1 per-etype mean, 2 mean in-degree + 1
@@ -269,8 +272,8 @@ __global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeLaunch L) 
         float msg = 0.f;
         for (int e = 0; e < a.n_et; ++e) {
             const int r0 = a.rowptr[e][nd], r1 = a.rowptr[e][nd + 1];
-            float g = c < Sd ? seg_gather(a.sm[e], Sd, a.part[e], a.pw, r0, r1, nd, c)
-                             : seg_gather(a.vm[e], 3 * Vd, a.part[e] + Sd, a.pw, r0, r1, nd, c - Sd);
+            float g = c < Sd ? seg_gather(a.sm[e], Sd, a.part[e], a.pw, r0, r1, nd, c, a.edge_tile)
+                             : seg_gather(a.vm[e], 3 * Vd, a.part[e] + Sd, a.pw, r0, r1, nd, c - Sd, a.edge_tile);
             if (a.norm_mode == 1) g = g / (float)max(r1 - r0, 1);      // fn.mean per edge type
             msg += g;
         }
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeLaunch L) 
 }
 
 struct GvpHeadArgs {
-    int n, Sdim, Vdim, lds, n_gvps, F, Fp, hid_out;
+    int n, Sdim, Vdim, lds, n_gvps, F, Fp, hid_out, kch;
     const float* s; const float* v;
     GvpW g[MAXG];
     const float* WoT; const float* bo;
@@ -349,6 +352,8 @@ __global__ void __launch_bounds__(NT, 1) gvp_head_kernel(const GvpHeadArgs a) {
     }
 }
 
+#include "gvp_tc.inl"
+
 }  // namespace kpd
 
 using namespace kpd;
@@ -367,7 +372,11 @@ struct kpd_gvp_model {
     std::vector<GvpLayerW> layers;
     GvpW head[MAXG];
     const float* WoT; const float* bo;
-    size_t smem, smem_node;
+    size_t smem, smem_node, smem_tc;
+    int kch;           // k-chunks of the bf16 tile (tensor-core mode)
+    int mode;          // 0 = fp32 SIMT (parity mode), 1 = bf16 tcgen05
+    bool tc_ready;
+    std::vector<GvpW*> all_gvps;   // enumeration order of kpd_gvp_attach_tc
 };
 
 struct GvpWs {
@@ -425,6 +434,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         g.vin = vin; g.vout = vout; g.hd = vin > vout ? vin : vout; g.fin = fin; g.fout = fout;
         g.ldf = (fout + 3) & ~3; g.sigmoid_gate = sig;
         g.Wh = P(); g.Wu = P(); g.WfT = P(); g.bf = P(); g.WgT = P(); g.bg = P();
+        g.WfP = nullptr; g.WgP = nullptr;
         return g;
     };
     int expect = 8 + cfg->n_noise_gvps * 6 + 2;
@@ -454,6 +464,21 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         m->head[k] = last ? G(m->V, 1, m->S, 64, 0) : G(m->V, m->V, m->S, m->S, 1);   // dynamics_gvp.py:18-25
     }
     m->WoT = P(); m->bo = P();
+    for (auto& L : m->layers) {
+        for (int e = 0; e < L.n_et; ++e)
+            for (int k = 0; k < cfg->n_message_gvps; ++k) m->all_gvps.push_back(&L.msg[e][k]);
+        for (int nt = 0; nt < L.n_dst; ++nt)
+            for (int k = 0; k < cfg->n_update_gvps; ++k) m->all_gvps.push_back(&L.upd[nt][k]);
+    }
+    for (int k = 0; k < cfg->n_noise_gvps; ++k) m->all_gvps.push_back(&m->head[k]);
+    {
+        int wmax = m->S + cfg->rbf_dim + m->V + 1;
+        if (wmax < 64 + m->V) wmax = 64 + m->V;
+        m->kch = 2 * ((wmax + 15) / 16);
+        m->smem_tc = gvp_tc_smem_bytes(m->kch);
+        m->mode = 0;
+        m->tc_ready = false;
+    }
     m->smem = gvp_smem_bytes(m->lds, TE);
     m->smem_node = gvp_smem_bytes(m->lds, TN);
     cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
@@ -468,6 +493,38 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
 }
 
 extern "C" void kpd_gvp_destroy(kpd_gvp_model* m) { delete m; }
+
+// bf16 tensor-core mode: tc_blob holds, for every GVP in creation order (per conv: message GVPs per edge
+// type, update GVPs per node type; then the noise head), the packed to_feats_out weight and the packed
+// gates weight (pack.pack_tc_weight); byte_offsets has two entries per GVP.
+extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n) {
+    KPD_REQUIRE(m && tc_blob && byte_offsets, "kpd_gvp_attach_tc: null argument");
+    KPD_REQUIRE(n == 2 * (int)m->all_gvps.size(), "kpd_gvp_attach_tc: expected %d offsets, got %d", 2 * (int)m->all_gvps.size(), n);
+    KPD_REQUIRE((reinterpret_cast<uintptr_t>(tc_blob) & 127) == 0, "kpd_gvp_attach_tc: blob must be 128-byte aligned");
+    KPD_REQUIRE(m->S % 16 == 0, "kpd_gvp_attach_tc: n_hidden_scalars must be a multiple of 16 for the tensor-core mode");
+    KPD_REQUIRE(m->smem_tc <= 227 * 1024, "kpd_gvp_attach_tc: tile needs %zu B of shared memory", m->smem_tc);
+    const char* base = static_cast<const char*>(tc_blob);
+    for (size_t i = 0; i < m->all_gvps.size(); ++i) {
+        KPD_REQUIRE(byte_offsets[2 * i] % 16 == 0 && byte_offsets[2 * i + 1] % 16 == 0, "kpd_gvp_attach_tc: unaligned offset");
+        m->all_gvps[i]->WfP = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i]);
+        m->all_gvps[i]->WgP = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i + 1]);
+    }
+    cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
+    cudaError_t e2 = cudaFuncSetAttribute(gvp_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
+    cudaError_t e3 = cudaFuncSetAttribute(gvp_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
+    KPD_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_tc);
+    m->tc_ready = true;
+    return 0;
+}
+
+// mode 0 = fp32 SIMT (parity mode), 1 = bf16 operands on tcgen05 tensor cores
+extern "C" int kpd_gvp_set_mode(kpd_gvp_model* m, int32_t mode) {
+    KPD_REQUIRE(m, "kpd_gvp_set_mode: null model");
+    KPD_REQUIRE(mode == 0 || mode == 1, "kpd_gvp_set_mode: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    KPD_REQUIRE(mode == 0 || m->tc_ready, "kpd_gvp_set_mode: call kpd_gvp_attach_tc first");
+    m->mode = mode;
+    return 0;
+}
 
 extern "C" int kpd_gvp_dims(const kpd_gvp_model* m, int* n_kp_scalars, int* vector_size) {
     KPD_REQUIRE(m, "kpd_gvp_dims: null model");
@@ -534,9 +591,18 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TE);
             if (t > max_tiles) max_tiles = t;
         }
+        L.kch = m->kch;
+        const bool tcm = m->mode == 1;
         prof_begin(PROF_GVP_EDGE, st);
-        gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
-        KPD_TRY(check_launch("gvp_edge_kernel"));
+        if (tcm) {
+            int tiles_tc = 1;
+            for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TCR); if (t > tiles_tc) tiles_tc = t; }
+            gvp_edge_tc_kernel<<<dim3(tiles_tc, W.n_et), NT, m->smem_tc, st>>>(L);
+            KPD_TRY(check_launch("gvp_edge_tc_kernel"));
+        } else {
+            gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
+            KPD_TRY(check_launch("gvp_edge_kernel"));
+        }
         prof_end(PROF_GVP_EDGE, st);
         {
             GvpNodeLaunch NL;
@@ -545,7 +611,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             for (int nt = 0; nt < W.n_dst; ++nt) {
                 GvpNodeArgs& a = NL.nt[nt];
                 a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
-                a.n_upd = m->cfg.n_update_gvps; a.n_et = 2;
+                a.n_upd = m->cfg.n_update_gvps; a.n_et = 2; a.kch = m->kch; a.edge_tile = tcm ? TCR : TE;
                 a.s = w.s[nt]; a.v = w.v[nt];
                 for (int k = 0; k < 2; ++k) {
                     const int e = nt * 2 + k;
@@ -560,8 +626,13 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             }
             if (max_n > 0) {
                 prof_begin(PROF_GVP_NODE, st);
-                gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
-                KPD_TRY(check_launch("gvp_node_kernel"));
+                if (tcm) {
+                    gvp_node_tc_kernel<<<dim3(cdiv(max_n, TCR), W.n_dst), NT, m->smem_tc, st>>>(NL);
+                    KPD_TRY(check_launch("gvp_node_tc_kernel"));
+                } else {
+                    gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
+                    KPD_TRY(check_launch("gvp_node_kernel"));
+                }
                 prof_end(PROF_GVP_NODE, st);
             }
         }
@@ -576,8 +647,14 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         a.WoT = m->WoT; a.bo = m->bo; a.eps_h = eps_h; a.eps_x = eps_x;
         if (a.n > 0) {
             prof_begin(PROF_GVP_HEAD, st);
-            gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);
-            KPD_TRY(check_launch("gvp_head_kernel"));
+            a.kch = m->kch;
+            if (m->mode == 1) {
+                gvp_head_tc_kernel<<<cdiv(a.n, TCR), NT, m->smem_tc, st>>>(a);
+                KPD_TRY(check_launch("gvp_head_tc_kernel"));
+            } else {
+                gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);
+                KPD_TRY(check_launch("gvp_head_kernel"));
+            }
             prof_end(PROF_GVP_HEAD, st);
         }
     }

@@ -133,6 +133,16 @@ class LigRecDynamicsGVP(_DynamicsBase):
         self.ll_k, self.kl_k = ll_k, kl_k
         self.n_message_gvps, self.n_update_gvps, self.n_noise_gvps = n_message_gvps, n_update_gvps, n_noise_gvps
         self.dropout = dropout   # eval-time no-op (models/gvp.py:133-134); sampling never trains
+        # 'fp32': SIMT kernels, <=1e-4 parity with the reference; 'bf16': tcgen05 tensor cores with bf16
+        # operands / fp32 accumulation (the north star's separately-reported bf16 GEMM mode)
+        self.precision = "fp32"
+
+    def set_precision(self, precision: str):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        self.precision = precision
+        if self._st.model is not None:
+            self._st.model.set_precision(precision)
 
     def device_model(self, device) -> ops.GvpModel:
         st = self._st
@@ -143,8 +153,10 @@ class LigRecDynamicsGVP(_DynamicsBase):
                                     n_convs=self.n_convs, n_hidden_scalars=self.n_hidden_scalars,
                                     update_kp=self.update_kp, n_message_gvps=self.n_message_gvps,
                                     n_update_gvps=self.n_update_gvps, n_noise_gvps=self.n_noise_gvps,
-                                    message_norm=self.message_norm, device=device)
+                                    message_norm=self.message_norm, device=device, precision=self.precision)
             st.model_key = key
+        if st.model.precision != self.precision:
+            st.model.set_precision(self.precision)
         return st.model
 
     @torch.no_grad()

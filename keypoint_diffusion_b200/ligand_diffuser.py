@@ -159,9 +159,10 @@ class KeypointDiffusion(nn.Module):
     def _sampler(self, g, steps_per_graph, use_cuda_graph) -> ops.Sampler:
         batch, kk = self._layout(g)
         model = self.dynamics.device_model(g.device)
-        key = (id(batch), id(kk), id(model), steps_per_graph, use_cuda_graph)
+        key = (id(batch), id(kk), id(model), steps_per_graph, use_cuda_graph, getattr(model, "precision", "fp32"))
         if key not in self._samplers:
-            self._samplers.clear()
+            if len(self._samplers) > 3:
+                self._samplers.clear()
             self._samplers[key] = ops.Sampler(model, batch, self.dynamics.graph_params(), kk, self.coef_table(g.device),
                                               self.n_timesteps, self.n_lig_features, steps_per_graph=steps_per_graph,
                                               use_cuda_graph=use_cuda_graph,

@@ -234,7 +234,7 @@ class GvpModel(_Model):
 
     def __init__(self, sd: Dict[str, torch.Tensor], *, n_lig_scalars, n_kp_scalars, vector_size, n_convs,
                  n_hidden_scalars, update_kp, n_message_gvps, n_update_gvps, n_noise_gvps, message_norm, device,
-                 rbf_dmax=15.0, rbf_dim=16):
+                 rbf_dmax=15.0, rbf_dim=16, precision="fp32"):
         super().__init__()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -255,6 +255,23 @@ class GvpModel(_Model):
                            n_update_gvps, n_noise_gvps, int(bool(update_kp)), mode, mn, float(rbf_dmax), int(rbf_dim))
         arr = (C.c_int64 * len(offs))(*offs)
         check(lib.kpd_gvp_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_gvp_create")
+        self.precision = "fp32"
+        self.tc_blob = None
+        if n_hidden_scalars % 16 == 0:
+            self.tc_blob, toffs = pack.pack_gvp_tc(sd, n_convs=n_convs, update_kp=update_kp,
+                                                   n_message_gvps=n_message_gvps, n_update_gvps=n_update_gvps,
+                                                   n_noise_gvps=n_noise_gvps, device=self.device)
+            tarr = (C.c_int64 * len(toffs))(*toffs)
+            check(lib.kpd_gvp_attach_tc(self.handle, ptr(self.tc_blob), tarr, len(toffs)), "kpd_gvp_attach_tc")
+        if precision != "fp32":
+            self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        """'fp32' (SIMT, parity mode) or 'bf16' (tcgen05 tensor cores, fp32 accumulation)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        check(lib.kpd_gvp_set_mode(self.handle, 1 if precision == "bf16" else 0), "kpd_gvp_set_mode")
+        self.precision = precision
 
     def __del__(self):
         if getattr(self, "handle", None) and self.handle.value and lib is not None:

@@ -191,3 +191,31 @@ def pack_tc_weight(w: torch.Tensor) -> torch.Tensor:
     wp[:N, :K] = w
     out = wp.view(NB // 8, 8, ks, 2, 8).permute(2, 3, 0, 1, 4).contiguous()
     return out.to(torch.bfloat16).reshape(-1)
+
+
+def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gvps, n_update_gvps, n_noise_gvps,
+                device) -> Tuple[torch.Tensor, List[int]]:
+    """bf16 tensor-core weights of every GVP, in the library's creation order (csrc/gvp.cu kpd_gvp_attach_tc):
+    per conv the message GVPs per edge type, then the update GVPs per node type; then the noise head.
+    Two entries per GVP: to_feats_out (rows padded to 16) and scalar_to_vector_gates (rows padded to 16).
+    Returns one bf16 device blob (every entry 128-byte aligned) and byte offsets."""
+    names = []
+    for l in range(n_convs):
+        q = f"noise_predictor.conv_layers.{l}."
+        etypes = gvp_layer_etypes(l, n_convs, update_kp)
+        for et in etypes:
+            names += [f"{q}edge_message_fns.{'_'.join(et)}.{i}" for i in range(n_message_gvps)]
+        for nt in (["lig", "kp"] if len(etypes) == 4 else ["lig"]):
+            names += [f"{q}node_update_fns.{nt}.{i}" for i in range(n_update_gvps)]
+    names += [f"noise_predictor.noise_predictor.gvps.{i}" for i in range(n_noise_gvps)]
+    parts, offs, n = [], [], 0
+    for name in names:
+        for key in (".to_feats_out.0.weight", ".scalar_to_vector_gates.weight"):
+            t = pack_tc_weight(sd[name + key])
+            pad = (-t.numel()) % 64                      # 64 bf16 = 128 bytes
+            offs.append(2 * n)
+            parts.append(t)
+            if pad:
+                parts.append(torch.zeros(pad, dtype=torch.bfloat16))
+            n += t.numel() + pad
+    return torch.cat(parts).to(device), offs

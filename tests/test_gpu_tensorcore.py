@@ -29,3 +29,51 @@ def test_tc_linear_matches_bf16_reference(M, K, N, act):
     print(f"tc_linear M={M} K={K} N={N}: rel_err vs bf16-operand reference {err:.2e}; "
           f"vs fp32 {rel_err(y.cpu(), (x.double() @ w.double().t() + b.double()) if not act else ref):.2e}")
     assert err < 2e-5
+
+
+@pytest.mark.parametrize("name", ["gvp_small_sum", "gvp_small_mean", "gvp_small_zero"])
+def test_gvp_bf16_mode_small(name):
+    """bf16 tensor-core mode of the GVP denoiser vs the golden fp32 outputs of the reference code:
+    operands are rounded to bf16 (8-bit mantissa), so the bar is 3e-2 of the output scale, stated
+    separately from the 1e-4 fp32 bar."""
+    from helpers import load_golden
+    from test_gpu_parity import build_model, device_inputs, run_forward
+    from keypoint_diffusion_b200 import ops
+    dev = torch.device("cuda:0")
+    fx = load_golden(name)
+    kw = fx["kwargs"]
+    model = build_model("gvp", fx["state_dict"], kw, fx["atom_nf"], fx["rec_nf"], dev)
+    batch, kk, t_in = device_inputs(fx["inputs"], dev)
+    gp = ops.GraphParams.from_module(kw.get("ll_k", 0), kw.get("kl_k", 0), kw["graph_cutoffs"])
+    graphs = ops.LigandGraphs(batch, gp, True).build(t_in["lig_x"], t_in["kp_x"])
+    out = fx["outputs"]["0.5"]
+    h32, x32 = run_forward("gvp", model, batch, graphs, kk, t_in, 0.5, dev)
+    model.set_precision("bf16")
+    h16, x16 = run_forward("gvp", model, batch, graphs, kk, t_in, 0.5, dev)
+    torch.cuda.synchronize()
+    eh, ex = rel_err(h16.cpu(), out["eps_h"]), rel_err(x16.cpu(), out["eps_x"])
+    print(f"{name} bf16 mode: rel_err eps_h={eh:.2e} eps_x={ex:.2e} (fp32 mode {rel_err(h32.cpu(), out['eps_h']):.1e})")
+    assert eh < 3e-2 and ex < 3e-2
+
+
+def test_gvp_bf16_mode_full_size():
+    import yaml
+    from helpers import GOLDEN, flat_batch, oracle_cfg, oracle_forward
+    from test_gpu_parity import _full_size_case, build_model, device_inputs, run_forward
+    from keypoint_diffusion_b200 import ops
+    dev = torch.device("cuda:0")
+    cfgs = yaml.safe_load(open(GOLDEN / "shipped_configs.yml"))
+    sd, kw, rec_nf, inputs = _full_size_case("gvp", cfgs)
+    cfg = oracle_cfg("gvp", kw, 10, rec_nf)
+    model = build_model("gvp", sd, kw, 10, rec_nf, dev)
+    model.set_precision("bf16")
+    batch, kk, t_in = device_inputs(inputs, dev)
+    gp = ops.GraphParams.from_module(kw["ll_k"], kw["kl_k"], kw["graph_cutoffs"])
+    graphs = ops.LigandGraphs(batch, gp, True).build(t_in["lig_x"], t_in["kp_x"])
+    fb = flat_batch(inputs)
+    ref_h, ref_x = oracle_forward("gvp", sd, cfg, fb, torch.full((fb.B,), 0.5))
+    eps_h, eps_x = run_forward("gvp", model, batch, graphs, kk, t_in, 0.5, dev)
+    torch.cuda.synchronize()
+    eh, ex = rel_err(eps_h.cpu(), ref_h), rel_err(eps_x.cpu(), ref_x)
+    print(f"gvp full size bf16 mode: rel_err eps_h={eh:.2e} eps_x={ex:.2e}")
+    assert eh < 3e-2 and ex < 3e-2
