@@ -517,6 +517,17 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
     return 0;
 }
 
+// debug: read (and reset) the phase timers of the tensor-core kernels (cycles summed over CTAs)
+extern "C" int kpd_debug_tc_times(unsigned long long* out16) {
+    KPD_REQUIRE(out16, "kpd_debug_tc_times: null argument");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, g_tc_times, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_times, z, sizeof(z));
+    KPD_REQUIRE(e == cudaSuccess, "kpd_debug_tc_times: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // mode 0 = fp32 SIMT (parity mode), 1 = bf16 operands on tcgen05 tensor cores
 extern "C" int kpd_gvp_set_mode(kpd_gvp_model* m, int32_t mode) {
     KPD_REQUIRE(m, "kpd_gvp_set_mode: null model");
@@ -597,7 +608,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         if (tcm) {
             int tiles_tc = 1;
             for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TCR); if (t > tiles_tc) tiles_tc = t; }
-            gvp_edge_tc_kernel<<<dim3(tiles_tc, W.n_et), NT, m->smem_tc, st>>>(L);
+            gvp_edge_tc_kernel<<<dim3(tiles_tc, W.n_et), NT_TC, m->smem_tc, st>>>(L);
             KPD_TRY(check_launch("gvp_edge_tc_kernel"));
         } else {
             gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
@@ -627,7 +638,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             if (max_n > 0) {
                 prof_begin(PROF_GVP_NODE, st);
                 if (tcm) {
-                    gvp_node_tc_kernel<<<dim3(cdiv(max_n, TCR), W.n_dst), NT, m->smem_tc, st>>>(NL);
+                    gvp_node_tc_kernel<<<dim3(cdiv(max_n, TC_NODE_ROWS), W.n_dst), NT_TC, m->smem_tc, st>>>(NL);
                     KPD_TRY(check_launch("gvp_node_tc_kernel"));
                 } else {
                     gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
@@ -649,7 +660,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             prof_begin(PROF_GVP_HEAD, st);
             a.kch = m->kch;
             if (m->mode == 1) {
-                gvp_head_tc_kernel<<<cdiv(a.n, TCR), NT, m->smem_tc, st>>>(a);
+                gvp_head_tc_kernel<<<cdiv(a.n, TC_NODE_ROWS), NT_TC, m->smem_tc, st>>>(a);
                 KPD_TRY(check_launch("gvp_head_tc_kernel"));
             } else {
                 gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);
