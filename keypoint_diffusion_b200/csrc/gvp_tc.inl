@@ -20,8 +20,11 @@ constexpr int NT_TC = 512;            // 16 warps: the SIMT phases of these kern
 constexpr int TC_WSM = 2 * VMAX * VMAX + 256 + 32;   // floats: Wh, Wu, feats bias, gate bias staged per GVP
 
 // bf16 mode does not need fp32-faithful transcendentals
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// one MUFU op per element: silu(x) = x * sigmoid(x) = h + h * tanh(h), sigmoid(x) = 0.5 + 0.5 * tanh(h), h = x / 2
+// (the exp + reciprocal form costs two MUFU ops and made the SiLU epilogue SFU-bound)
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float silu_fast(float x) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 constexpr int TC_KCS = (TCR / 8) * 128;   // bytes between k-chunks of the A tile
 constexpr int TC_STAGES = 8;
 constexpr int TC_SLAB_MAX = 2 * (256 / 8) * 128;   // one k-step of a 256-row weight
