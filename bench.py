@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=None, help="reverse steps per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16x3"],
                     help="headline mode: fp32 (SIMT, parity-green) or bf16 (tcgen05 tensor cores, GVP only)")
     ap.add_argument("--no-bf16-block", action="store_true", help="skip the separately-reported bf16 measurement")
     args = ap.parse_args()
@@ -299,10 +299,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
-    if args.precision == "bf16":
+    if args.precision != "fp32":
         if arch != "gvp":
-            raise SystemExit("the bf16 tensor-core mode exists for the GVP denoiser only (round 1)")
-        model.dynamics.set_precision("bf16")
+            raise SystemExit("the tensor-core modes exist for the GVP denoiser only")
+        model.dynamics.set_precision(args.precision)
     launches0 = int(_lib.lib.kpd_launch_count())
     for _ in range(max(args.warmup, 0)):
         one_sample_device()

@@ -184,11 +184,16 @@ int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, const int64_t* 
                    int32_t n_offsets, kpd_gvp_model** out);
 void kpd_gvp_destroy(kpd_gvp_model* m);
 int kpd_gvp_dims(const kpd_gvp_model* m, int* n_kp_scalars, int* vector_size);
-/* bf16 tensor-core mode (the "bf16 GEMM mode" the north star reports separately): the scalar Linear of
- * every GVP and its gates run as tcgen05.mma on 128-row tiles (csrc/gvp_tc.inl).  tc_blob holds, for
- * every GVP in creation order, the packed to_feats_out and gates weights (pack.pack_gvp_tc);
- * byte_offsets has two entries per GVP.  mode: 0 = fp32 SIMT (default, parity mode), 1 = bf16. */
-int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n);
+/* Tensor-core modes: the scalar Linear of every GVP and its gates run as tcgen05.mma with fp32 accumulation in
+ * TMEM (csrc/gvp_ws.inl, csrc/gvp_tc.inl).  tc_blob holds, for every GVP in creation order, the packed
+ * to_feats_out and gates weights (pack.pack_gvp_tc); byte_offsets has two entries per GVP.
+ *   nsplit = 1: bf16 operands                        -> mode 1, the "bf16 GEMM mode" the north star reports
+ *               separately (outputs within ~2e-3 of fp32);
+ *   nsplit = 2: bf16 (hi, lo) pairs, three MMAs per product (hi*hi + lo*hi + hi*lo) -> mode 2, "bf16x3":
+ *               fp32-grade operands, meets the 1e-4 parity bar on the tensor cores.
+ * mode: 0 = fp32 SIMT (reference arithmetic), 1 = bf16, 2 = bf16x3. */
+int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n,
+                      int32_t nsplit);
 int kpd_gvp_set_mode(kpd_gvp_model* m, int32_t mode);
 int64_t kpd_gvp_workspace_bytes(const kpd_gvp_model* m, const kpd_batch* batch,
                                 int32_t cap_ll, int32_t cap_kl, int32_t cap_kk);

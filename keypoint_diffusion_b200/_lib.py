@@ -78,7 +78,7 @@ def _load():
         "kpd_egnn_encode_kp": (I, [P, P, I, P, P, P]),
         "kpd_gvp_create": (I, [C.POINTER(KpdGvpConfig), P, C.POINTER(L), I, C.POINTER(P)]),
         "kpd_gvp_destroy": (None, [P]),
-        "kpd_gvp_attach_tc": (I, [P, P, C.POINTER(L), I]),
+        "kpd_gvp_attach_tc": (I, [P, P, C.POINTER(L), I, I]),
         "kpd_gvp_set_mode": (I, [P, I]),
         "kpd_gvp_dims": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "kpd_gvp_workspace_bytes": (L, [P, C.POINTER(KpdBatch), I, I, I]),

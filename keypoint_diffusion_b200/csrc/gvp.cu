@@ -40,6 +40,8 @@ struct GvpW {
     const float* bg;    // [vout]
     const uint4* WfP;   // bf16 mode: to_feats_out weight as tcgen05 k-step slabs (pack_tc_weight)
     const uint4* WgP;   // bf16 mode: gates weight, rows padded to 16
+    const uint4* WfP2;  // bf16x3 mode: the same two weights as interleaved (hi, lo) k-step slabs
+    const uint4* WgP2;
     int vin, vout, hd, fin, fout, ldf, sigmoid_gate;
 };
 
@@ -177,6 +179,7 @@ constexpr int TN = 16 * RM_NODE;
 struct GvpEtypeArgs {
     const int* rowptr; const int* src; const int* dst; int n_dst;
     const float* s_src; const float* v_src; const float* xs; const float* xd;
+    const __nv_bfloat16* s_hi; const __nv_bfloat16* s_lo;   // tensor-core modes: bf16 planes of s_src
     GvpW msg[MAXG];
     float* sm; float* vm; float* part;
 };
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_head_kernel(const GvpHeadArgs a) {
 }
 
 #include "gvp_tc.inl"
+#include "gvp_ws.inl"
 
 }  // namespace kpd
 
@@ -372,15 +376,16 @@ struct kpd_gvp_model {
     std::vector<GvpLayerW> layers;
     GvpW head[MAXG];
     const float* WoT; const float* bo;
-    size_t smem, smem_node, smem_tc;
+    size_t smem, smem_node, smem_tc, smem_ws1, smem_ws2;
     int kch;           // k-chunks of the bf16 tile (tensor-core mode)
-    int mode;          // 0 = fp32 SIMT (parity mode), 1 = bf16 tcgen05
-    bool tc_ready;
+    int mode;          // 0 = fp32 SIMT, 1 = bf16 tcgen05, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
+    bool tc_ready, tc2_ready;
     std::vector<GvpW*> all_gvps;   // enumeration order of kpd_gvp_attach_tc
 };
 
 struct GvpWs {
     float *s[2], *v[2], *sm[4], *vm[4], *part[4], *tin, *tenc;
+    __nv_bfloat16 *s_hi[2], *s_lo[2];
 };
 
 static int gvp_ntiles(int cap) { return cdiv(cap > 0 ? cap : 1, TE) + 1; }
@@ -403,6 +408,10 @@ static GvpWs gvp_carve(const kpd_gvp_model* m, const kpd_batch* b, const int cap
     const int win = (m->F > m->C ? m->F : m->C) + 1;
     w.tin = c.take<float>((int64_t)maxN * win);
     w.tenc = c.take<float>((int64_t)maxN * m->S);
+    for (int nt = 0; nt < 2; ++nt) {
+        w.s_hi[nt] = c.take<__nv_bfloat16>((int64_t)N[nt] * m->S);
+        w.s_lo[nt] = c.take<__nv_bfloat16>((int64_t)N[nt] * m->S);
+    }
     if (bytes) *bytes = c.bytes();
     return w;
 }
@@ -434,7 +443,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         g.vin = vin; g.vout = vout; g.hd = vin > vout ? vin : vout; g.fin = fin; g.fout = fout;
         g.ldf = (fout + 3) & ~3; g.sigmoid_gate = sig;
         g.Wh = P(); g.Wu = P(); g.WfT = P(); g.bf = P(); g.WgT = P(); g.bg = P();
-        g.WfP = nullptr; g.WgP = nullptr;
+        g.WfP = nullptr; g.WgP = nullptr; g.WfP2 = nullptr; g.WgP2 = nullptr;
         return g;
     };
     int expect = 8 + cfg->n_noise_gvps * 6 + 2;
@@ -476,8 +485,11 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         if (wmax < 64 + m->V) wmax = 64 + m->V;
         m->kch = 2 * ((wmax + 15) / 16);
         m->smem_tc = gvp_tc_smem_bytes(m->kch);
+        m->smem_ws1 = ws::smem_bytes<WsBf16>(m->kch);
+        m->smem_ws2 = ws::smem_bytes<WsSplit>(m->kch);
         m->mode = 0;
         m->tc_ready = false;
+        m->tc2_ready = false;
     }
     m->smem = gvp_smem_bytes(m->lds, TE);
     m->smem_node = gvp_smem_bytes(m->lds, TN);
@@ -497,17 +509,32 @@ extern "C" void kpd_gvp_destroy(kpd_gvp_model* m) { delete m; }
 // bf16 tensor-core mode: tc_blob holds, for every GVP in creation order (per conv: message GVPs per edge
 // type, update GVPs per node type; then the noise head), the packed to_feats_out weight and the packed
 // gates weight (pack.pack_tc_weight); byte_offsets has two entries per GVP.
-extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n) {
+extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n,
+                                 int32_t nsplit) {
     KPD_REQUIRE(m && tc_blob && byte_offsets, "kpd_gvp_attach_tc: null argument");
+    KPD_REQUIRE(nsplit == 1 || nsplit == 2, "kpd_gvp_attach_tc: nsplit must be 1 (bf16) or 2 (bf16 hi/lo)");
     KPD_REQUIRE(n == 2 * (int)m->all_gvps.size(), "kpd_gvp_attach_tc: expected %d offsets, got %d", 2 * (int)m->all_gvps.size(), n);
     KPD_REQUIRE((reinterpret_cast<uintptr_t>(tc_blob) & 127) == 0, "kpd_gvp_attach_tc: blob must be 128-byte aligned");
     KPD_REQUIRE(m->S % 16 == 0, "kpd_gvp_attach_tc: n_hidden_scalars must be a multiple of 16 for the tensor-core mode");
-    KPD_REQUIRE(m->smem_tc <= 227 * 1024, "kpd_gvp_attach_tc: tile needs %zu B of shared memory", m->smem_tc);
+    KPD_REQUIRE(m->smem_tc <= 227 * 1024 && m->smem_ws1 <= 227 * 1024 && m->smem_ws2 <= 227 * 1024,
+                "kpd_gvp_attach_tc: tile needs %zu / %zu / %zu B of shared memory", m->smem_tc, m->smem_ws1, m->smem_ws2);
     const char* base = static_cast<const char*>(tc_blob);
     for (size_t i = 0; i < m->all_gvps.size(); ++i) {
         KPD_REQUIRE(byte_offsets[2 * i] % 16 == 0 && byte_offsets[2 * i + 1] % 16 == 0, "kpd_gvp_attach_tc: unaligned offset");
-        m->all_gvps[i]->WfP = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i]);
-        m->all_gvps[i]->WgP = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i + 1]);
+        const uint4* wf = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i]);
+        const uint4* wg = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i + 1]);
+        if (nsplit == 1) { m->all_gvps[i]->WfP = wf; m->all_gvps[i]->WgP = wg; }
+        else { m->all_gvps[i]->WfP2 = wf; m->all_gvps[i]->WgP2 = wg; }
+    }
+    if (nsplit == 2) {
+        cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws2);
+        m->tc2_ready = true;
+        return 0;
+    }
+    {
+        cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1);
+        KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws1);
     }
     cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
     cudaError_t e2 = cudaFuncSetAttribute(gvp_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
@@ -531,8 +558,9 @@ extern "C" int kpd_debug_tc_times(unsigned long long* out16) {
 // mode 0 = fp32 SIMT (parity mode), 1 = bf16 operands on tcgen05 tensor cores
 extern "C" int kpd_gvp_set_mode(kpd_gvp_model* m, int32_t mode) {
     KPD_REQUIRE(m, "kpd_gvp_set_mode: null model");
-    KPD_REQUIRE(mode == 0 || mode == 1, "kpd_gvp_set_mode: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
-    KPD_REQUIRE(mode == 0 || m->tc_ready, "kpd_gvp_set_mode: call kpd_gvp_attach_tc first");
+    KPD_REQUIRE(mode >= 0 && mode <= 2, "kpd_gvp_set_mode: mode must be 0 (fp32 SIMT), 1 (bf16) or 2 (bf16x3 tensor cores)");
+    KPD_REQUIRE(mode != 1 || m->tc_ready, "kpd_gvp_set_mode: call kpd_gvp_attach_tc(nsplit = 1) first");
+    KPD_REQUIRE(mode != 2 || m->tc2_ready, "kpd_gvp_set_mode: call kpd_gvp_attach_tc(nsplit = 2) first");
     m->mode = mode;
     return 0;
 }
@@ -579,6 +607,15 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     KPD_REQUIRE(ce == cudaSuccess, "kpd_gvp_forward: memset failed: %s", cudaGetErrorString(ce));
     KPD_TRY(launch_copy_rows(v_kp, V * 3, w.v[1], V * 3, N[1], V * 3, st));
 
+    auto split_planes = [&](int n_types) -> int {
+        const int mx = N[0] > N[1] ? N[0] : N[1];
+        if (m->mode == 0 || mx == 0) return 0;
+        const int blocks = cdiv(cdiv(mx * S, 8), 256);
+        split_planes_kernel<<<dim3(blocks, n_types), 256, 0, st>>>(w.s[0], N[0], w.s[1], N[1], S, w.s_hi[0], w.s_lo[0],
+                                                                    w.s_hi[1], w.s_lo[1]);
+        return check_launch("split_planes_kernel");
+    };
+    KPD_TRY(split_planes(2));
     const int src_nt[4] = {0, 1, 0, 1}, dst_nt[4] = {0, 0, 1, 1};
     const float* X[2] = {x_lig, x_kp};
     const int norm_mode = m->cfg.norm_mode;
@@ -596,6 +633,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             GvpEtypeArgs& a = L.e[e];
             a.rowptr = G[e]->rowptr; a.src = G[e]->src; a.dst = G[e]->dst; a.n_dst = G[e]->n_dst;
             a.s_src = w.s[src_nt[e]]; a.v_src = w.v[src_nt[e]];
+            a.s_hi = w.s_hi[src_nt[e]]; a.s_lo = w.s_lo[src_nt[e]];
             a.xs = X[src_nt[e]]; a.xd = X[dst_nt[e]];
             for (int k = 0; k < L.n_msg; ++k) a.msg[k] = W.msg[e][k];
             a.sm = w.sm[e]; a.vm = w.vm[e]; a.part = w.part[e];
@@ -604,12 +642,14 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         }
         L.kch = m->kch;
         const bool tcm = m->mode == 1;
+        const int edge_rows = m->mode == 1 ? WsBf16::R : m->mode == 2 ? WsSplit::R : TE;
         prof_begin(PROF_GVP_EDGE, st);
-        if (tcm) {
+        if (m->mode != 0) {
             int tiles_tc = 1;
-            for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TCR); if (t > tiles_tc) tiles_tc = t; }
-            gvp_edge_tc_kernel<<<dim3(tiles_tc, W.n_et), NT_TC, m->smem_tc, st>>>(L);
-            KPD_TRY(check_launch("gvp_edge_tc_kernel"));
+            for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, edge_rows); if (t > tiles_tc) tiles_tc = t; }
+            if (m->mode == 1) gvp_edge_ws_kernel<WsBf16><<<dim3(tiles_tc, W.n_et), WsBf16::NT, m->smem_ws1, st>>>(L);
+            else gvp_edge_ws_kernel<WsSplit><<<dim3(tiles_tc, W.n_et), WsSplit::NT, m->smem_ws2, st>>>(L);
+            KPD_TRY(check_launch("gvp_edge_ws_kernel"));
         } else {
             gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
             KPD_TRY(check_launch("gvp_edge_kernel"));
@@ -622,7 +662,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             for (int nt = 0; nt < W.n_dst; ++nt) {
                 GvpNodeArgs& a = NL.nt[nt];
                 a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
-                a.n_upd = m->cfg.n_update_gvps; a.n_et = 2; a.kch = m->kch; a.edge_tile = tcm ? TCR : TE;
+                a.n_upd = m->cfg.n_update_gvps; a.n_et = 2; a.kch = m->kch; a.edge_tile = edge_rows;
                 a.s = w.s[nt]; a.v = w.v[nt];
                 for (int k = 0; k < 2; ++k) {
                     const int e = nt * 2 + k;
@@ -645,6 +685,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
                     KPD_TRY(check_launch("gvp_node_kernel"));
                 }
                 prof_end(PROF_GVP_NODE, st);
+                if (l + 1 < m->cfg.n_convs) KPD_TRY(split_planes(W.n_dst));
             }
         }
     }

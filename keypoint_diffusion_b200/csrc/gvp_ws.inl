@@ -1,0 +1,584 @@
+// Warp-specialised tensor-core GVP kernels (included inside namespace kpd by gvp.cu).
+//
+// A tile is R rows (edges or nodes).  Its scalar features live in shared memory ONLY as bf16 in the UMMA
+// K-major canonical layout (tc.cuh), i.e. directly as the A operand of tcgen05.mma; with NS = 2 there are two
+// planes (hi, lo = bf16(x - hi)) and every product runs as three MMAs (hi*hi + lo*hi + hi*lo): the "bf16x3"
+// mode, which keeps ~16 mantissa bits per operand and meets the 1e-4 fp32 parity bar (tools/
+// split_precision_study.py); NS = 1 is the plain bf16 mode.  Vector channels never touch shared memory
+// during the chain: lane (row, c) of a SIMT warp owns component c of all vector channels of one row in
+// registers, so Vh = V^T Wh, Vu = Vh^T Wu and the gating are register FMAs against broadcast weights.
+//
+// Warp roles (one CTA): R/8 SIMT warps | 1 MMA-issuing warp (one lane) | 1 weight-producer warp (one lane).
+//   producer: streams every GVP's packed to_feats_out weight as k-step slabs through a cp.async.bulk ring
+//             (full/empty mbarriers) and the small gates weight into a double buffer;
+//   MMA warp: issues the k-steps over the feats columns as soon as those are complete (feats_ready) -- i.e.
+//             while the SIMT warps still compute Vh -- then the k-steps over the |Vh| columns (tail_ready),
+//             commits acc_done; after epilogue 1 (feats_ready again) it issues the gates GEMM and, right
+//             behind it, the NEXT GVP's main k-steps;
+//   SIMT:     Vh, |Vh| -> A, Vu, epilogue 1 (TMEM -> bias + SiLU -> bf16 planes of A), epilogue 2 (gates ->
+//             sigmoid -> V), gathers, LayerNorms and the deterministic segmented reduction.
+// SIMT-only synchronisation uses named barrier 1; cross-role synchronisation uses mbarriers only.
+namespace ws {
+
+constexpr int WH_LD = 20;                                   // Wh staged as [17][20] (zero padded)
+constexpr int WSM = VMAX * WH_LD + VMAX * 16 + 256 + 16;    // floats per GVP: Wh | Wu [17][16] | bf | bg
+constexpr int VS_LD = 52;                                   // fp32 vector staging row (48 used)
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t GATE_COL = 256;
+
+template <int R_, int NS_>
+struct Cfg {
+    static constexpr int R = R_, NS = NS_;
+    static constexpr int NW = R / 8;                 // SIMT warps: 8 rows each, lanes = (row, xyz component)
+    static constexpr int NT_SIMT = 32 * NW;
+    static constexpr int NT = NT_SIMT + 64;
+    static constexpr int KCS = (R / 8) * 128 + 16;   // bytes between k-chunks of A (+16: bank rotation for column walks)
+    static constexpr int STAGES = NS == 1 ? 8 : 4;
+    static constexpr int SLAB = NS * 8192;           // one ring stage: one k-step of a 256-row weight (hi [, lo])
+    static constexpr int WG_BYTES = NS * 8192;       // gates weight: 16 k-steps x 512 B (hi [, lo])
+    static constexpr int NCG = NW / 4;               // column groups of the epilogues (4 TMEM lane quarters x NCG)
+};
+
+struct Sm {
+    unsigned char* A[2];
+    unsigned char* ring;
+    unsigned char* Wg[2];
+    float* wsm;
+    float* gate;      // [16][R]
+    int *src_s, *dst_s, *seg, *rp;
+    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done;
+    uint32_t* tmem_slot;
+    int* warp_cnt;
+};
+
+template <class C>
+__host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C::KCS + 127) & ~(size_t)127; }
+
+template <class C>
+static size_t smem_bytes(int kch) {
+    return C::NS * plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + 2 * C::WG_BYTES + sizeof(float) * MAXG * WSM +
+           sizeof(float) * 16 * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 8) + 16 + 128;
+}
+
+template <class C>
+__device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
+    Sm m;
+    m.A[0] = smem;
+    m.A[1] = smem + (C::NS - 1) * plane_bytes<C>(kch);
+    m.ring = smem + C::NS * plane_bytes<C>(kch);
+    m.Wg[0] = m.ring + C::STAGES * C::SLAB;
+    m.Wg[1] = m.Wg[0] + C::WG_BYTES;
+    m.wsm = reinterpret_cast<float*>(m.Wg[1] + C::WG_BYTES);
+    m.gate = m.wsm + MAXG * WSM;
+    m.src_s = reinterpret_cast<int*>(m.gate + 16 * C::R);
+    m.dst_s = m.src_s + C::R;
+    m.seg = m.dst_s + C::R;            // [R + 8]
+    m.rp = m.seg + C::R + 8;           // [2R]
+    m.warp_cnt = m.rp + 2 * C::R;      // [8]
+    m.full = reinterpret_cast<uint64_t*>(m.warp_cnt + 8);
+    m.empty = m.full + C::STAGES;
+    m.wg_full = m.empty + C::STAGES;   // [2]
+    m.wg_empty = m.wg_full + 2;        // [2]
+    m.feats_ready = m.wg_empty + 2;
+    m.tail_ready = m.feats_ready + 1;
+    m.acc_done = m.tail_ready + 1;
+    m.gates_done = m.acc_done + 1;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.gates_done + 1);
+    return m;
+}
+
+template <class C>
+__device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(C::NT_SIMT) : "memory"); }
+
+// barriers + TMEM + zeroed A planes + the small fp32 weights of the chain; ends with a __syncthreads()
+template <class C>
+__device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_gvps) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], 1); }
+        tc::mbar_init(m.feats_ready, C::NW);
+        tc::mbar_init(m.tail_ready, C::NW);
+        tc::mbar_init(m.acc_done, 1);
+        tc::mbar_init(m.gates_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == C::NW) { tc::tmem_alloc(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish(); }
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const int nz = (int)(C::NS * plane_bytes<C>(kch) / 16);
+    for (int i = tid; i < nz; i += C::NT) reinterpret_cast<uint4*>(m.A[0])[i] = z;
+    for (int idx = tid; idx < n_gvps * WSM; idx += C::NT) {
+        const int gi = idx / WSM, o = idx - gi * WSM;
+        const GvpW& g = gv[gi];
+        float val = 0.f;
+        if (o < VMAX * WH_LD) {
+            const int k = o / WH_LD, hh = o - k * WH_LD;
+            if (k < g.vin && hh < g.hd) val = g.Wh[k * g.hd + hh];
+        } else if (o < VMAX * WH_LD + VMAX * 16) {
+            const int q = o - VMAX * WH_LD, h = q >> 4, u = q & 15;
+            if (h < g.hd && u < g.vout) val = g.Wu[h * g.vout + u];
+        } else if (o < VMAX * WH_LD + VMAX * 16 + 256) {
+            const int f = o - (VMAX * WH_LD + VMAX * 16);
+            if (f < g.fout) val = g.bf[f];
+        } else {
+            const int u = o - (VMAX * WH_LD + VMAX * 16 + 256);
+            if (u < g.vout) val = g.bg[u];
+        }
+        m.wsm[idx] = val;
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    return *m.tmem_slot;
+}
+
+template <class C>
+__device__ __forceinline__ void teardown(uint32_t tmem) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == C::NW) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ producer (one thread)
+template <class C>
+__device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m) {
+    uint32_t it = 0;
+    for (int g = 0; g < n_gvps; ++g) {
+        const GvpW& w = gv[g];
+        const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksg = NBf >> 4;
+        const uint32_t slab = C::NS * 2 * (NBf / 8) * 128;
+        const int b = g & 1;
+        if (g >= 2) tc::mbar_wait(&m.wg_empty[b], ((g >> 1) - 1) & 1);      // gates MMA g-2 has consumed this buffer
+        tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
+        const uint4* WfP = C::NS == 2 ? w.WfP2 : w.WfP;
+        tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
+        for (int j = 0; j < ksf; ++j, ++it) {
+            const uint32_t st = it % C::STAGES;
+            if (it >= (uint32_t)C::STAGES) tc::mbar_wait(&m.empty[st], ((it / C::STAGES) - 1) & 1);
+            tc::mbar_arrive_expect_tx(&m.full[st], slab);
+            tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ MMA issuer (one thread)
+template <class C>
+__device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_t tmem) {
+    uint32_t it = 0;
+    tc::mbar_wait(m.feats_ready, 0);
+    tc::fence_after_sync();
+    for (int g = 0; g < n_gvps; ++g) {
+        const GvpW& w = gv[g];
+        const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksm = w.fin >> 4, ksg = NBf >> 4;
+        const uint32_t idesc = tc::make_idesc_bf16(C::R, NBf);
+        const uint32_t b_k = (NBf / 8) * 128, slab1 = 2 * b_k;
+        for (int j = 0; j < ksf; ++j, ++it) {
+            if (j == ksm) { tc::mbar_wait(m.tail_ready, g & 1); tc::fence_after_sync(); }
+            const uint32_t st = it % C::STAGES;
+            tc::mbar_wait(&m.full[st], (it / C::STAGES) & 1);
+            tc::fence_after_sync();
+            const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
+            const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+            const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
+            tc::mma_bf16_ss(tmem, a0, b0, idesc, j > 0 ? 1u : 0u);
+            if (C::NS == 2) {
+                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
+                tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);
+                tc::mma_bf16_ss(tmem, a0, b1, idesc, 1u);
+            }
+            tc::mma_commit(&m.empty[st]);
+        }
+        tc::mma_commit(m.acc_done);
+        // epilogue 1 of this GVP done: feats_out is in A, the accumulator columns are free again
+        tc::mbar_wait(m.feats_ready, (g + 1) & 1);
+        tc::fence_after_sync();
+        tc::mbar_wait(&m.wg_full[g & 1], (g >> 1) & 1);
+        tc::fence_after_sync();
+        const uint32_t idg = tc::make_idesc_bf16(C::R, 16);
+        const uint32_t wg = tc::smem_u32(m.Wg[0] + (g & 1) * C::WG_BYTES);
+        for (int j = 0; j < ksg; ++j) {
+            const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+            const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
+            tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, j > 0 ? 1u : 0u);
+            if (C::NS == 2) {
+                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                const uint64_t b1 = tc::make_smem_desc(wg + j * 1024 + 512, 256, 128);
+                tc::mma_bf16_ss(tmem + GATE_COL, a1, b0, idg, 1u);
+                tc::mma_bf16_ss(tmem + GATE_COL, a0, b1, idg, 1u);
+            }
+        }
+        tc::mma_commit(m.gates_done);
+        tc::mma_commit(&m.wg_empty[g & 1]);
+    }
+}
+
+// ------------------------------------------------------------------ SIMT helpers
+__device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int NS>
+__device__ __forceinline__ float act_silu(float x) { return NS == 1 ? silu_fast(x) : silu_acc(x); }
+template <int NS>
+__device__ __forceinline__ float act_sigmoid(float x) { return NS == 1 ? sigmoid_fast(x) : sigmoid_acc(x); }
+
+// store one value into the bf16 plane(s) at (row, col)
+template <class C>
+__device__ __forceinline__ void put_scalar(const Sm& m, int row, int col, float x) {
+    const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (row >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
+    const __nv_bfloat16 hi = __float2bfloat16(x);
+    *reinterpret_cast<__nv_bfloat16*>(m.A[0] + off) = hi;
+    if (C::NS == 2) *reinterpret_cast<__nv_bfloat16*>(m.A[1] + off) = __float2bfloat16(x - __bfloat162float(hi));
+}
+
+// 8 consecutive columns (one k-chunk) of one row
+template <class C>
+__device__ __forceinline__ void put_chunk(const Sm& m, int row, int kc, const float (&f)[8]) {
+    const uint32_t off = (uint32_t)(kc * C::KCS + (row >> 3) * 128 + (row & 7) * 16);
+    uint4 hi;
+    hi.x = tc::pack_bf16x2(f[0], f[1]); hi.y = tc::pack_bf16x2(f[2], f[3]);
+    hi.z = tc::pack_bf16x2(f[4], f[5]); hi.w = tc::pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(m.A[0] + off) = hi;
+    if (C::NS == 2) {
+        uint4 lo;
+        lo.x = tc::pack_bf16x2(f[0] - __uint_as_float(hi.x << 16), f[1] - __uint_as_float(hi.x & 0xffff0000u));
+        lo.y = tc::pack_bf16x2(f[2] - __uint_as_float(hi.y << 16), f[3] - __uint_as_float(hi.y & 0xffff0000u));
+        lo.z = tc::pack_bf16x2(f[4] - __uint_as_float(hi.z << 16), f[5] - __uint_as_float(hi.z & 0xffff0000u));
+        lo.w = tc::pack_bf16x2(f[6] - __uint_as_float(hi.w << 16), f[7] - __uint_as_float(hi.w & 0xffff0000u));
+        *reinterpret_cast<uint4*>(m.A[1] + off) = lo;
+    }
+}
+
+// value of (row, col) read back from the plane(s)
+template <class C>
+__device__ __forceinline__ float get_scalar(const Sm& m, int row, int col) {
+    const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (row >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
+    float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(m.A[0] + off));
+    if (C::NS == 2) x += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(m.A[1] + off));
+    return x;
+}
+
+// all SIMT lanes made their shared-memory writes -> publish to the async proxy and arrive (one per warp)
+__device__ __forceinline__ void publish(uint64_t* bar) {
+    tc::fence_proxy_async();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
+}
+
+// lane geometry of the register-resident vectors
+struct Lane {
+    int row;     // tile row owned by this lane
+    int c;       // xyz component
+    int bl;      // first lane of this row's triple
+    bool own;    // false for the 8 spare lanes (they mirror row 7 of the warp and never store)
+};
+__device__ __forceinline__ Lane lane_geometry() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Lane L;
+    const int rr = lane < 24 ? lane / 3 : 7;
+    L.c = lane < 24 ? lane - 3 * rr : (lane - 24) % 3;
+    L.row = 8 * warp + rr;
+    L.bl = 3 * rr;
+    L.own = lane < 24;
+    return L;
+}
+__device__ __forceinline__ float sum3(float x, const Lane& L) {
+    const float t1 = __shfl_sync(0xffffffffu, x, L.bl + (L.c + 1) % 3);
+    const float t2 = __shfl_sync(0xffffffffu, x, L.bl + (L.c + 2) % 3);
+    return x + t1 + t2;
+}
+
+// one 32-column chunk of epilogue 1: bias + SiLU -> bf16 plane(s) of A (static register indexing only)
+template <class C>
+__device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
+                                           const Sm& m, int row) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+        if (c0 + 8 * kc < NBf) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int col = c0 + 8 * kc + e;
+                f[e] = col < fout ? act_silu<C::NS>(__uint_as_float(v[8 * kc + e]) + bf_s[col]) : 0.0f;
+            }
+            put_chunk<C>(m, row, (c0 >> 3) + kc, f);
+        }
+    }
+}
+
+// GVP.forward (models/gvp.py:89-116), SIMT side, for GVP number gi of the chain.
+// In: v[0..vin) (registers), feats in A[:, 0:fin) already published.  Out: v[0..vout), feats_out in A[:, 0:fout)
+// published through feats_ready.
+template <class C>
+__device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uint32_t tmem, float (&v)[VMAX], const Lane& L,
+                                         int rows_valid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* Wh_s = m.wsm + gi * WSM;
+    const float* Wu_s = Wh_s + VMAX * WH_LD;
+    const float* bf_s = Wu_s + VMAX * 16;
+    const float* bg_s = bf_s + 256;
+    const int NBf = (g.fout + 15) & ~15;
+    // a. Vh = V^T Wh (gvp.py:96); sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
+    float vh[VMAX];
+#pragma unroll
+    for (int h = 0; h < VMAX; ++h) vh[h] = 0.f;
+#pragma unroll
+    for (int k = 0; k < VMAX; ++k) {
+        const float4* w4 = reinterpret_cast<const float4*>(Wh_s + k * WH_LD);
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        const float w16 = Wh_s[k * WH_LD + 16];
+        const float x = v[k];
+        vh[0] = fmaf(x, w0.x, vh[0]); vh[1] = fmaf(x, w0.y, vh[1]); vh[2] = fmaf(x, w0.z, vh[2]); vh[3] = fmaf(x, w0.w, vh[3]);
+        vh[4] = fmaf(x, w1.x, vh[4]); vh[5] = fmaf(x, w1.y, vh[5]); vh[6] = fmaf(x, w1.z, vh[6]); vh[7] = fmaf(x, w1.w, vh[7]);
+        vh[8] = fmaf(x, w2.x, vh[8]); vh[9] = fmaf(x, w2.y, vh[9]); vh[10] = fmaf(x, w2.z, vh[10]); vh[11] = fmaf(x, w2.w, vh[11]);
+        vh[12] = fmaf(x, w3.x, vh[12]); vh[13] = fmaf(x, w3.y, vh[13]); vh[14] = fmaf(x, w3.z, vh[14]); vh[15] = fmaf(x, w3.w, vh[15]);
+        vh[16] = fmaf(x, w16, vh[16]);
+    }
+#pragma unroll
+    for (int h = 0; h < VMAX; ++h) {
+        const float s = sum3(vh[h] * vh[h], L);
+        if (L.own && (h % 3) == L.c && h < g.hd) put_scalar<C>(m, L.row, g.fin + h, sqrtf(fmaxf(s, 1e-8f)));
+    }
+    publish(m.tail_ready);
+    // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
+    float vu[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) vu[u] = 0.f;
+#pragma unroll
+    for (int h = 0; h < VMAX; ++h) {
+        const float4* w4 = reinterpret_cast<const float4*>(Wu_s + h * 16);
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        const float x = vh[h];
+        vu[0] = fmaf(x, w0.x, vu[0]); vu[1] = fmaf(x, w0.y, vu[1]); vu[2] = fmaf(x, w0.z, vu[2]); vu[3] = fmaf(x, w0.w, vu[3]);
+        vu[4] = fmaf(x, w1.x, vu[4]); vu[5] = fmaf(x, w1.y, vu[5]); vu[6] = fmaf(x, w1.z, vu[6]); vu[7] = fmaf(x, w1.w, vu[7]);
+        vu[8] = fmaf(x, w2.x, vu[8]); vu[9] = fmaf(x, w2.y, vu[9]); vu[10] = fmaf(x, w2.z, vu[10]); vu[11] = fmaf(x, w2.w, vu[11]);
+        vu[12] = fmaf(x, w3.x, vu[12]); vu[13] = fmaf(x, w3.y, vu[13]); vu[14] = fmaf(x, w3.z, vu[14]); vu[15] = fmaf(x, w3.w, vu[15]);
+    }
+    // c. epilogue 1: feats_out = SiLU(acc + b) -> A[:, 0:fout)   (gvp.py:101-103)
+    const int q = warp & 3, cg = warp >> 2;
+    const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
+    const bool valid_e = C::R == 128 ? true : lane < 16;
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+    tc::mbar_wait(m.acc_done, gi & 1);
+    tc::fence_after_sync();
+    {
+        constexpr int cpw = 256 / C::NCG;
+        const int row0 = C::R == 128 ? 32 * q : 16 * q;
+        const int cend = row0 < rows_valid ? min(NBf, cg * cpw + cpw) : 0;   // warps of empty row quarters skip
+        for (int cb = cg * cpw; cb < cend; cb += 64) {
+            uint32_t v0[32], v1[32];
+            const bool two = cb + 32 < cend;
+            tc::tmem_ld_x32(taddr + cb, v0);
+            if (two) tc::tmem_ld_x32(taddr + cb + 32, v1);
+            tc::tmem_ld_wait();
+            if (valid_e) {
+                epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
+                if (two) epi1_chunk<C>(v1, cb + 32, g.fout, NBf, bf_s, m, row_e);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    publish(m.feats_ready);
+    // d. epilogue 2: vectors_out = act(gating) * Vu   (gvp.py:105-111)
+    tc::mbar_wait(m.gates_done, gi & 1);
+    tc::fence_after_sync();
+    {
+        constexpr int CG = 16 / C::NCG;          // gate columns per warp
+        uint32_t gv[CG];
+        if constexpr (CG == 4) tc::tmem_ld_x4(taddr + GATE_COL + cg * CG, gv);
+        else tc::tmem_ld_x8(taddr + GATE_COL + cg * CG, gv);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < CG; ++i) {
+            const int u = cg * CG + i;
+            float a = __uint_as_float(gv[i]) + bg_s[u];
+            if (g.sigmoid_gate) a = act_sigmoid<C::NS>(a);
+            if (valid_e) m.gate[u * C::R + row_e] = a;
+        }
+    }
+    simt_bar<C>();
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = vu[u] * m.gate[u * C::R + L.row];
+    v[16] = 0.f;
+}
+
+// Segment table of a dst-sorted tile: seg[0..nseg) = first row of every run of equal dst, seg[nseg] = n;
+// the count goes to seg[R + 1].  All SIMT threads call it; ends with a SIMT barrier.
+template <class C>
+__device__ __forceinline__ void build_segments(const Sm& m, int n) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int W = C::R / 32;
+    bool start = false;
+    unsigned bal = 0;
+    if (tid < C::R) {
+        start = tid < n && (tid == 0 || m.dst_s[tid] != m.dst_s[tid - 1]);
+        bal = __ballot_sync(0xffffffffu, start);
+        if (lane == 0) m.warp_cnt[warp] = __popc(bal);
+    }
+    simt_bar<C>();
+    if (tid < C::R) {
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += m.warp_cnt[w];
+        if (start) m.seg[base + __popc(bal & ((1u << lane) - 1u))] = tid;
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < W; ++w) tot += m.warp_cnt[w];
+            m.seg[tot] = n;
+            m.seg[C::R + 1] = tot;
+        }
+    }
+    simt_bar<C>();
+}
+
+}  // namespace ws
+
+using WsBf16 = ws::Cfg<128, 1>;    // bf16 operands, 128-row tiles (M = 128)
+using WsSplit = ws::Cfg<64, 2>;    // bf16 hi/lo operands (three MMAs per product), 64-row tiles (M = 64)
+
+// fp32 node scalars -> bf16 hi (and lo) planes, row-major [n][S]: what the edge kernels gather with 16-byte cp.async
+__global__ void split_planes_kernel(const float* __restrict__ s0, int n0, const float* __restrict__ s1, int n1, int S,
+                                    __nv_bfloat16* __restrict__ h0, __nv_bfloat16* __restrict__ l0,
+                                    __nv_bfloat16* __restrict__ h1, __nv_bfloat16* __restrict__ l1) {
+    const float* s = blockIdx.y == 0 ? s0 : s1;
+    __nv_bfloat16* hp = blockIdx.y == 0 ? h0 : h1;
+    __nv_bfloat16* lp = blockIdx.y == 0 ? l0 : l1;
+    const int n = blockIdx.y == 0 ? n0 : n1;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= (size_t)n * S) return;
+    const float4 a = *reinterpret_cast<const float4*>(s + i), b = *reinterpret_cast<const float4*>(s + i + 4);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi, lo;
+    hi.x = tc::pack_bf16x2(f[0], f[1]); hi.y = tc::pack_bf16x2(f[2], f[3]);
+    hi.z = tc::pack_bf16x2(f[4], f[5]); hi.w = tc::pack_bf16x2(f[6], f[7]);
+    lo.x = tc::pack_bf16x2(f[0] - __uint_as_float(hi.x << 16), f[1] - __uint_as_float(hi.x & 0xffff0000u));
+    lo.y = tc::pack_bf16x2(f[2] - __uint_as_float(hi.y << 16), f[3] - __uint_as_float(hi.y & 0xffff0000u));
+    lo.z = tc::pack_bf16x2(f[4] - __uint_as_float(hi.z << 16), f[5] - __uint_as_float(hi.z & 0xffff0000u));
+    lo.w = tc::pack_bf16x2(f[6] - __uint_as_float(hi.w << 16), f[7] - __uint_as_float(hi.w & 0xffff0000u));
+    *reinterpret_cast<uint4*>(hp + i) = hi;
+    *reinterpret_cast<uint4*>(lp + i) = lo;
+}
+
+// ------------------------------------------------------------------ edge kernel
+// GVPMultiEdgeConv.message + aggregation (models/gvp.py:472-497, :540-550) for all edge types in one launch
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_constant__ GvpEdgeLaunch L) {
+    const GvpEtypeArgs& a = L.e[blockIdx.y];
+    const int E = a.rowptr[a.n_dst];
+    const int tile_begin = blockIdx.x * C::R;
+    if (tile_begin >= E) return;
+    const int n = min(C::R, E - tile_begin);
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    TC_T(e0);
+    ws::Sm m = ws::carve<C>(smem_ws, L.kch);
+    const uint32_t tmem = ws::setup<C>(m, L.kch, a.msg, L.n_msg);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Sd = L.Sdim, Vd = L.Vdim;
+    if (warp == C::NW) {
+        if (lane == 0) ws::issue<C>(a.msg, L.n_msg, m, tmem);
+    } else if (warp == C::NW + 1) {
+        if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m);
+    } else {
+        TC_T(e1);
+        if (tid < C::R) {
+            const int e = tile_begin + min(tid, n - 1);
+            const int s = a.src[e], d = a.dst[e];
+            m.src_s[tid] = s;
+            m.dst_s[tid] = d;
+            m.rp[2 * tid] = a.rowptr[d];
+            m.rp[2 * tid + 1] = a.rowptr[d + 1];
+        }
+        ws::simt_bar<C>();
+        // s_src: 16-byte cp.async straight into the canonical bf16 plane(s); consecutive lanes = consecutive rows
+        {
+            const int items = C::R * (Sd >> 3);
+            for (int idx = tid; idx < items; idx += C::NT_SIMT) {
+                const int r = idx % C::R, kc = idx / C::R;
+                const uint32_t off = (uint32_t)(kc * C::KCS + (r >> 3) * 128 + (r & 7) * 16);
+                const size_t g = (size_t)m.src_s[r] * Sd + 8 * kc;
+                cp_async16(m.A[0] + off, a.s_hi + g);
+                if (C::NS == 2) cp_async16(m.A[1] + off, a.s_lo + g);
+            }
+            cp_async_commit();
+        }
+        // geometry + v_src -> registers (gvp.py:474-480)
+        const ws::Lane Ln = ws::lane_geometry();
+        float v[VMAX];
+        {
+            const int s = m.src_s[Ln.row], d = m.dst_s[Ln.row];
+            const float dxc = a.xs[3 * s + Ln.c] - a.xd[3 * d + Ln.c];
+            const float d2 = ws::sum3(dxc * dxc, Ln);
+            const float dij = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
+            v[0] = dxc / dij;
+            const float* vp = a.v_src + (size_t)s * (Vd * 3) + Ln.c;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[1 + k] = k < Vd ? vp[3 * k] : 0.f;
+            for (int k = Ln.c; k < L.rbf_dim; k += 3) {
+                const float z = (dij - (float)k * L.rbf_step) / L.rbf_sigma;
+                const float val = expf(-(z * z));
+                if (Ln.own) ws::put_scalar<C>(m, Ln.row, Sd + k, val);
+            }
+        }
+        ws::build_segments<C>(m, n);
+        cp_async_wait<0>();
+        ws::publish(m.feats_ready);
+        TC_T(e2);
+        for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R);
+        TC_T(e3);
+        // ---- deterministic segmented reduction by destination (all MMAs and bulk copies have completed)
+        float* VS = reinterpret_cast<float*>(m.ring);
+        if (Ln.own) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) if (u < Vd) VS[Ln.row * ws::VS_LD + 3 * u + Ln.c] = v[u];
+        }
+        ws::simt_bar<C>();
+        {
+            constexpr int GRP = 160;
+            constexpr int NGRP = C::NT_SIMT / GRP;
+            const int grp = tid / GRP, p = tid - grp * GRP;
+            const int nsp = Sd >> 1, nvp = (Vd * 3 + 1) >> 1;
+            const int nseg = m.seg[C::R + 1];
+            float* part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
+            float* part1 = a.part + ((size_t)blockIdx.x * 2 + 1) * L.pw;
+            if (grp < NGRP && p < nsp + nvp) {
+                const bool scal = p < nsp;
+                const int col = scal ? 2 * p : 2 * (p - nsp);
+                const bool has2 = scal || col + 1 < Vd * 3;
+                const unsigned char* p0 = m.A[0] + (size_t)(col >> 3) * C::KCS + (col & 7) * 2;
+                const unsigned char* p1 = m.A[1] + (size_t)(col >> 3) * C::KCS + (col & 7) * 2;
+                for (int sg = grp; sg < nseg; sg += NGRP) {
+                    const int ra = m.seg[sg], rb = m.seg[sg + 1];
+                    float s0 = 0.f, s1 = 0.f;
+                    if (scal) {
+                        for (int j = ra; j < rb; ++j) {
+                            const uint32_t ro = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                            const uint32_t wv = *reinterpret_cast<const uint32_t*>(p0 + ro);
+                            float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+                            if (C::NS == 2) {
+                                const uint32_t wl = *reinterpret_cast<const uint32_t*>(p1 + ro);
+                                x0 += __uint_as_float(wl << 16); x1 += __uint_as_float(wl & 0xffff0000u);
+                            }
+                            s0 += x0; s1 += x1;
+                        }
+                    } else {
+                        for (int j = ra; j < rb; ++j) {
+                            const float2 x = *reinterpret_cast<const float2*>(VS + j * ws::VS_LD + col);
+                            s0 += x.x; s1 += x.y;
+                        }
+                    }
+                    const bool from_prev = (ra == 0) && (m.rp[2 * ra] < tile_begin);
+                    const bool into_next = (rb == n) && (m.rp[2 * ra + 1] > tile_begin + n);
+                    float* t;
+                    if (from_prev) t = part0 + (scal ? col : Sd + col);
+                    else if (into_next) t = part1 + (scal ? col : Sd + col);
+                    else t = scal ? a.sm + (size_t)m.dst_s[ra] * Sd + col : a.vm + (size_t)m.dst_s[ra] * (Vd * 3) + col;
+                    t[0] = s0;
+                    if (has2) t[1] = s1;
+                }
+            }
+        }
+        TC_T(e4);
+        TC_ACC(8, e0, e1); TC_ACC(9, e1, e2); TC_ACC(10, e2, e3); TC_ACC(11, e3, e4); TC_ACC(13, 0, 1);
+    }
+    ws::teardown<C>(tmem);
+}

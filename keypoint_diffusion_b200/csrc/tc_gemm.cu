@@ -10,19 +10,23 @@ namespace kpd {
 
 constexpr int TCG_STAGES = 4;
 
-// slab j of a packed weight with NB (multiple of 16, <= 256) rows: 2 k-chunks x (NB/8) groups x 128 B
+// W is packed per 256-row output block (pack.pack_tc_weight); slab j of a block with NB rows (multiple of 16,
+// <= 256): 2 k-chunks x (NB/8) groups x 128 B
 __global__ void __launch_bounds__(128, 1)
 tc_linear_kernel(const float* __restrict__ X, int ldx, const uint4* __restrict__ Wp, const float* __restrict__ bias,
-                 const float* __restrict__ R, int ldr, float* __restrict__ Y, int ldy, int M, int K, int N, int NB,
+                 const float* __restrict__ R, int ldr, float* __restrict__ Y, int ldy, int M, int K, int N, int NBmax,
                  int act) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    int NB = N - 256 * (int)blockIdx.y;                // rows of this output block, padded to 16
+    NB = NB > 256 ? 256 : (NB + 15) & ~15;
     const int ksteps = (K + 15) / 16;
     const int a_kstride = 16 * 128;                    // 128 rows -> 16 groups x 128 B per k-chunk
     unsigned char* a_s = smem_raw;                     // [2*ksteps][16][128 B]
-    unsigned char* b_s = a_s + (size_t)2 * ksteps * a_kstride;   // [STAGES][2][NB/8][128 B]
+    unsigned char* b_s = a_s + (size_t)2 * ksteps * a_kstride;   // [STAGES][2][NBmax/8][128 B]
     const int b_kstride = (NB / 8) * 128;
     const int slab_bytes = 2 * b_kstride;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)TCG_STAGES * slab_bytes);   // full[S], empty[S], done
+    const int slab_stride = 2 * (NBmax / 8) * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)TCG_STAGES * slab_stride);   // full[S], empty[S], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TCG_STAGES + 1);
     uint64_t* full = bars;
     uint64_t* empty = bars + TCG_STAGES;
@@ -31,7 +35,8 @@ tc_linear_kernel(const float* __restrict__ X, int ldx, const uint4* __restrict__
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.x * 128;
     const int nblk = blockIdx.y;                       // 256-column block of the output
-    const uint4* Wblk = Wp + (size_t)nblk * ksteps * (slab_bytes / 16);
+    // all blocks before this one are full (256 rows): their slabs are 2 * 32 * 128 B per k-step
+    const uint4* Wblk = Wp + (size_t)nblk * ksteps * (2 * 32 * 128 / 16);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < NB) tmem_cols <<= 1;
 
@@ -64,29 +69,25 @@ tc_linear_kernel(const float* __restrict__ X, int ldx, const uint4* __restrict__
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- one thread: weight slabs through a bulk-copy ring, MMAs into TMEM
-    if (tid == 0) {
-        const uint32_t idesc = tc::make_idesc_bf16(128, NB);
-        const int pre = ksteps < TCG_STAGES ? ksteps : TCG_STAGES;
-        for (int j = 0; j < pre; ++j) {
-            tc::mbar_arrive_expect_tx(&full[j], slab_bytes);
-            tc::bulk_g2s(b_s + (size_t)j * slab_bytes, Wblk + (size_t)j * (slab_bytes / 16), slab_bytes, &full[j]);
-        }
+    // ---- warp 1 lane 0 feeds the weight ring (cp.async.bulk), thread 0 issues the MMAs into TMEM
+    if (tid == 32) {
         for (int j = 0; j < ksteps; ++j) {
             const int st = j % TCG_STAGES;
-            const uint32_t ph = (j / TCG_STAGES) & 1;
-            tc::mbar_wait(&full[st], ph);
+            if (j >= TCG_STAGES) tc::mbar_wait(&empty[st], ((j / TCG_STAGES) - 1) & 1);
+            tc::mbar_arrive_expect_tx(&full[st], slab_bytes);
+            tc::bulk_g2s(b_s + (size_t)st * slab_stride, Wblk + (size_t)j * (slab_bytes / 16), slab_bytes, &full[st]);
+        }
+    }
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, NB);
+        for (int j = 0; j < ksteps; ++j) {
+            const int st = j % TCG_STAGES;
+            tc::mbar_wait(&full[st], (j / TCG_STAGES) & 1);
             tc::fence_after_sync();
             const uint64_t adesc = tc::make_smem_desc(tc::smem_u32(a_s + (size_t)2 * j * a_kstride), a_kstride, 128);
-            const uint64_t bdesc = tc::make_smem_desc(tc::smem_u32(b_s + (size_t)st * slab_bytes), b_kstride, 128);
+            const uint64_t bdesc = tc::make_smem_desc(tc::smem_u32(b_s + (size_t)st * slab_stride), b_kstride, 128);
             tc::mma_bf16_ss(tmem_base, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
             tc::mma_commit(&empty[st]);
-            if (j + TCG_STAGES < ksteps) {
-                tc::mbar_wait(&empty[st], ph);          // MMA j has consumed the slab
-                tc::mbar_arrive_expect_tx(&full[st], slab_bytes);
-                tc::bulk_g2s(b_s + (size_t)st * slab_bytes, Wblk + (size_t)(j + TCG_STAGES) * (slab_bytes / 16),
-                             slab_bytes, &full[st]);
-            }
         }
         tc::mma_commit(done);
     }
@@ -131,8 +132,8 @@ static size_t tc_linear_smem(int K, int NB) {
 int launch_tc_linear(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y,
                      int ldy, int M, int K, int N, int act, cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
-    KPD_REQUIRE(N <= 256, "tc_linear: N > 256 not supported yet (N=%d)", N);
-    const int NB = (N + 15) / 16 * 16;
+    const int NB = N >= 256 ? 256 : (N + 15) / 16 * 16;
+    const int nblocks = cdiv(N, 256);
     const size_t smem = tc_linear_smem(K, NB);
     KPD_REQUIRE(smem <= 227 * 1024, "tc_linear: K=%d needs %zu B of shared memory", K, smem);
     static size_t configured = 0;
@@ -141,7 +142,7 @@ int launch_tc_linear(const float* X, int ldx, const void* Wp, const float* bias,
         KPD_REQUIRE(e == cudaSuccess, "tc_linear: cannot set %zu B shared memory: %s", smem, cudaGetErrorString(e));
         configured = smem;
     }
-    tc_linear_kernel<<<dim3(cdiv(M, 128), 1), 128, smem, st>>>(X, ldx, static_cast<const uint4*>(Wp), bias, R, ldr, Y, ldy,
+    tc_linear_kernel<<<dim3(cdiv(M, 128), nblocks), 128, smem, st>>>(X, ldx, static_cast<const uint4*>(Wp), bias, R, ldr, Y, ldy,
                                                                 M, K, N, NB, act);
     return check_launch("tc_linear_kernel");
 }

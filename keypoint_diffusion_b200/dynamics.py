@@ -133,13 +133,14 @@ class LigRecDynamicsGVP(_DynamicsBase):
         self.ll_k, self.kl_k = ll_k, kl_k
         self.n_message_gvps, self.n_update_gvps, self.n_noise_gvps = n_message_gvps, n_update_gvps, n_noise_gvps
         self.dropout = dropout   # eval-time no-op (models/gvp.py:133-134); sampling never trains
-        # 'fp32': SIMT kernels, <=1e-4 parity with the reference; 'bf16': tcgen05 tensor cores with bf16
-        # operands / fp32 accumulation (the north star's separately-reported bf16 GEMM mode)
+        # 'fp32': SIMT kernels in the reference's own arithmetic; 'bf16x3': tcgen05 tensor cores with split
+        # (hi, lo) bf16 operands and fp32 accumulation, inside the 1e-4 parity bar; 'bf16': tcgen05 with plain
+        # bf16 operands (the north star's separately-reported bf16 GEMM mode)
         self.precision = "fp32"
 
     def set_precision(self, precision: str):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if precision not in ops.GvpModel.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(ops.GvpModel.PRECISIONS)}, got {precision!r}")
         self.precision = precision
         if self._st.model is not None:
             self._st.model.set_precision(precision)

@@ -256,21 +256,27 @@ class GvpModel(_Model):
         arr = (C.c_int64 * len(offs))(*offs)
         check(lib.kpd_gvp_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_gvp_create")
         self.precision = "fp32"
-        self.tc_blob = None
+        self.tc_blob = self.tc_blob2 = None
         if n_hidden_scalars % 16 == 0:
-            self.tc_blob, toffs = pack.pack_gvp_tc(sd, n_convs=n_convs, update_kp=update_kp,
-                                                   n_message_gvps=n_message_gvps, n_update_gvps=n_update_gvps,
-                                                   n_noise_gvps=n_noise_gvps, device=self.device)
+            kw = dict(n_convs=n_convs, update_kp=update_kp, n_message_gvps=n_message_gvps, n_update_gvps=n_update_gvps,
+                      n_noise_gvps=n_noise_gvps, device=self.device)
+            self.tc_blob, toffs = pack.pack_gvp_tc(sd, **kw)
             tarr = (C.c_int64 * len(toffs))(*toffs)
-            check(lib.kpd_gvp_attach_tc(self.handle, ptr(self.tc_blob), tarr, len(toffs)), "kpd_gvp_attach_tc")
+            check(lib.kpd_gvp_attach_tc(self.handle, ptr(self.tc_blob), tarr, len(toffs), 1), "kpd_gvp_attach_tc")
+            self.tc_blob2, toffs = pack.pack_gvp_tc(sd, split=True, **kw)
+            tarr = (C.c_int64 * len(toffs))(*toffs)
+            check(lib.kpd_gvp_attach_tc(self.handle, ptr(self.tc_blob2), tarr, len(toffs), 2), "kpd_gvp_attach_tc")
         if precision != "fp32":
             self.set_precision(precision)
 
+    PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+
     def set_precision(self, precision: str):
-        """'fp32' (SIMT, parity mode) or 'bf16' (tcgen05 tensor cores, fp32 accumulation)."""
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
-        check(lib.kpd_gvp_set_mode(self.handle, 1 if precision == "bf16" else 0), "kpd_gvp_set_mode")
+        """'fp32' (SIMT, the reference's arithmetic), 'bf16x3' (tcgen05 tensor cores with split bf16 operands:
+        fp32-grade, inside the 1e-4 parity bar) or 'bf16' (tcgen05, plain bf16 operands, ~2e-3)."""
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}, got {precision!r}")
+        check(lib.kpd_gvp_set_mode(self.handle, self.PRECISIONS[precision]), "kpd_gvp_set_mode")
         self.precision = precision
 
     def __del__(self):

@@ -178,26 +178,47 @@ def pack_gvp(sd: Dict[str, torch.Tensor], *, n_lig_scalars, n_kp_scalars, vector
     return blob.finish(device), offs
 
 
-def pack_tc_weight(w: torch.Tensor) -> torch.Tensor:
+def _tc_block(wp: torch.Tensor, split: bool) -> torch.Tensor:
+    """[NB, ks*16] fp32 -> k-step slabs [ks][hi(, lo)][2 k-chunks][NB/8][8 rows][8] bf16."""
+    NB, K16 = wp.shape
+    ks = K16 // 16
+
+    def slabs(x):
+        return x.view(NB // 8, 8, ks, 2, 8).permute(2, 3, 0, 1, 4).contiguous().view(ks, 1, -1)
+
+    hi = wp.to(torch.bfloat16)
+    if not split:
+        return slabs(hi).reshape(-1)
+    lo = (wp - hi.float()).to(torch.bfloat16)
+    return torch.cat([slabs(hi), slabs(lo)], dim=1).reshape(-1)
+
+
+def pack_tc_weight(w: torch.Tensor, split: bool = False) -> torch.Tensor:
     """nn.Linear weight [N, K] -> bf16 "k-step slabs" for the tcgen05 kernels (csrc/tc.cuh):
     for every k-step of 16 input features, 2 k-chunks x (NB/8) row groups x (8 rows x 8 bf16 = 128 B), i.e. the
-    no-swizzle K-major canonical UMMA layout, so one slab is one contiguous bulk copy.  N is padded to a
-    multiple of 16 (NB), K to a multiple of 16, with zeros."""
+    no-swizzle K-major canonical UMMA layout, so one slab is one contiguous bulk copy.  K is padded to a multiple
+    of 16 with zeros.  Output rows are packed in blocks of 256 (UMMA N <= 256); the last block is padded to a
+    multiple of 16 rows (NB).  split=True interleaves, per k-step, the slab of hi = bf16(w) and the slab of
+    lo = bf16(w - hi) (the bf16x3 mode)."""
     w = w.detach().float().cpu()
     N, K = w.shape
-    NB = (N + 15) // 16 * 16
     ks = (K + 15) // 16
-    wp = torch.zeros(NB, ks * 16)
-    wp[:N, :K] = w
-    out = wp.view(NB // 8, 8, ks, 2, 8).permute(2, 3, 0, 1, 4).contiguous()
-    return out.to(torch.bfloat16).reshape(-1)
+    parts = []
+    for n0 in range(0, N, 256):
+        n = min(256, N - n0)
+        NB = (n + 15) // 16 * 16
+        wp = torch.zeros(NB, ks * 16)
+        wp[:n, :K] = w[n0:n0 + n]
+        parts.append(_tc_block(wp, split))
+    return torch.cat(parts)
 
 
 def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gvps, n_update_gvps, n_noise_gvps,
-                device) -> Tuple[torch.Tensor, List[int]]:
+                device, split: bool = False) -> Tuple[torch.Tensor, List[int]]:
     """bf16 tensor-core weights of every GVP, in the library's creation order (csrc/gvp.cu kpd_gvp_attach_tc):
     per conv the message GVPs per edge type, then the update GVPs per node type; then the noise head.
     Two entries per GVP: to_feats_out (rows padded to 16) and scalar_to_vector_gates (rows padded to 16).
+    split=True packs (hi, lo) slab pairs for the bf16x3 mode.
     Returns one bf16 device blob (every entry 128-byte aligned) and byte offsets."""
     names = []
     for l in range(n_convs):
@@ -211,7 +232,7 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
     parts, offs, n = [], [], 0
     for name in names:
         for key in (".to_feats_out.0.weight", ".scalar_to_vector_gates.weight"):
-            t = pack_tc_weight(sd[name + key])
+            t = pack_tc_weight(sd[name + key], split)
             pad = (-t.numel()) % 64                      # 64 bf16 = 128 bytes
             offs.append(2 * n)
             parts.append(t)
