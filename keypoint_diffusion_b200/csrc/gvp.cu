@@ -555,6 +555,17 @@ extern "C" int kpd_debug_tc_times(unsigned long long* out16) {
     return 0;
 }
 
+// same for the warp-specialised kernels (gvp_ws.inl)
+extern "C" int kpd_debug_ws_times(unsigned long long* out16) {
+    KPD_REQUIRE(out16, "kpd_debug_ws_times: null argument");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, g_ws_times, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_ws_times, z, sizeof(z));
+    KPD_REQUIRE(e == cudaSuccess, "kpd_debug_ws_times: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // mode 0 = fp32 SIMT (parity mode), 1 = bf16 operands on tcgen05 tensor cores
 extern "C" int kpd_gvp_set_mode(kpd_gvp_model* m, int32_t mode) {
     KPD_REQUIRE(m, "kpd_gvp_set_mode: null model");

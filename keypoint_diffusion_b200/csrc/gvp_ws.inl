@@ -18,6 +18,11 @@
 //   SIMT:     Vh, |Vh| -> A, Vu, epilogue 1 (TMEM -> bias + SiLU -> bf16 planes of A), epilogue 2 (gates ->
 //             sigmoid -> V), gathers, LayerNorms and the deterministic segmented reduction.
 // SIMT-only synchronisation uses named barrier 1; cross-role synchronisation uses mbarriers only.
+// phase timers of the warp-specialised kernels (cycles, SIMT thread 0, summed over CTAs):
+// [0..6] gvp_simt: Vh+|Vh|, Vu, wait acc, epilogue 1, wait gates, epilogue 2, calls
+__device__ unsigned long long g_ws_times[16];
+#define WS_ACC(slot, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_ws_times[slot], (unsigned long long)((b) - (a))); } while (0)
+
 namespace ws {
 
 constexpr int WH_LD = 20;                                   // Wh staged as [17][20] (zero padded)
@@ -215,8 +220,16 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
 }
 
 // ------------------------------------------------------------------ SIMT helpers
-__device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// fp32-grade logistic on two MUFU ops (ex2 and rcp are good to ~2^-22; no range fix-ups: 1 + 2^t never overflows
+// to a value rcp cannot take, and a huge argument gives rcp(inf) = 0, the right limit)
+__device__ __forceinline__ float sigmoid_acc(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+__device__ __forceinline__ float silu_acc(float x) { return x * sigmoid_acc(x); }
 
 template <int NS>
 __device__ __forceinline__ float act_silu(float x) { return NS == 1 ? silu_fast(x) : silu_acc(x); }
@@ -272,6 +285,7 @@ struct Lane {
     int c;       // xyz component
     int bl;      // first lane of this row's triple
     bool own;    // false for the 8 spare lanes (they mirror row 7 of the warp and never store)
+    uint32_t rowoff;   // byte offset of the row inside a k-chunk of A
 };
 __device__ __forceinline__ Lane lane_geometry() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -281,6 +295,7 @@ __device__ __forceinline__ Lane lane_geometry() {
     L.row = 8 * warp + rr;
     L.bl = 3 * rr;
     L.own = lane < 24;
+    L.rowoff = (uint32_t)((L.row >> 3) * 128 + (L.row & 7) * 16);
     return L;
 }
 __device__ __forceinline__ float sum3(float x, const Lane& L) {
@@ -293,16 +308,54 @@ __device__ __forceinline__ float sum3(float x, const Lane& L) {
 template <class C>
 __device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
                                            const Sm& m, int row) {
+    // fout is a multiple of 8 (host-checked): a chunk is either all feats_out or all padding
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
         if (c0 + 8 * kc < NBf) {
             float f[8];
+            if (c0 + 8 * kc < fout) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bf_s + c0 + 8 * kc);
+                const float4 b1 = *reinterpret_cast<const float4*>(bf_s + c0 + 8 * kc + 4);
+                f[0] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 0]) + b0.x); f[1] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 1]) + b0.y);
+                f[2] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 2]) + b0.z); f[3] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 3]) + b0.w);
+                f[4] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 4]) + b1.x); f[5] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 5]) + b1.y);
+                f[6] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 6]) + b1.z); f[7] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 7]) + b1.w);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int col = c0 + 8 * kc + e;
-                f[e] = col < fout ? act_silu<C::NS>(__uint_as_float(v[8 * kc + e]) + bf_s[col]) : 0.0f;
+                for (int e = 0; e < 8; ++e) f[e] = 0.f;
             }
             put_chunk<C>(m, row, (c0 >> 3) + kc, f);
+        }
+    }
+}
+
+// M = 64 accumulators: 64 columns loaded with the 16x256b shape (all 32 lanes hold data: rows t/4 and t/4 + 8 of the
+// warp's 16-lane TMEM quarter, column pairs 2(t%4) + 8i).  bias + SiLU -> bf16x2 -> A plane(s), 4-byte stores.
+template <class C>
+__device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
+                                            const Sm& m, int row_a, int lane) {
+    const int cp = 2 * (lane & 3);
+    const uint32_t ro = (uint32_t)((row_a >> 3) * 128 + (row_a & 7) * 16 + cp * 2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int col = c0 + 8 * i;
+        if (col < NBf) {
+            float fa0 = 0.f, fa1 = 0.f, fb0 = 0.f, fb1 = 0.f;
+            if (col < fout) {
+                const float2 b = *reinterpret_cast<const float2*>(bf_s + col + cp);
+                fa0 = act_silu<C::NS>(__uint_as_float(v[4 * i + 0]) + b.x); fa1 = act_silu<C::NS>(__uint_as_float(v[4 * i + 1]) + b.y);
+                fb0 = act_silu<C::NS>(__uint_as_float(v[4 * i + 2]) + b.x); fb1 = act_silu<C::NS>(__uint_as_float(v[4 * i + 3]) + b.y);
+            }
+            const uint32_t off = (uint32_t)((col >> 3) * C::KCS) + ro;
+            const uint32_t ha = tc::pack_bf16x2(fa0, fa1), hb = tc::pack_bf16x2(fb0, fb1);
+            *reinterpret_cast<uint32_t*>(m.A[0] + off) = ha;
+            *reinterpret_cast<uint32_t*>(m.A[0] + off + 128) = hb;       // row + 8: next 8-row group
+            if (C::NS == 2) {
+                *reinterpret_cast<uint32_t*>(m.A[1] + off) =
+                    tc::pack_bf16x2(fa0 - __uint_as_float(ha << 16), fa1 - __uint_as_float(ha & 0xffff0000u));
+                *reinterpret_cast<uint32_t*>(m.A[1] + off + 128) =
+                    tc::pack_bf16x2(fb0 - __uint_as_float(hb << 16), fb1 - __uint_as_float(hb & 0xffff0000u));
+            }
         }
     }
 }
@@ -320,6 +373,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const float* bg_s = bf_s + 256;
     const int NBf = (g.fout + 15) & ~15;
     // a. Vh = V^T Wh (gvp.py:96); sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
+    TC_T(t0);
     float vh[VMAX];
 #pragma unroll
     for (int h = 0; h < VMAX; ++h) vh[h] = 0.f;
@@ -335,12 +389,28 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         vh[12] = fmaf(x, w3.x, vh[12]); vh[13] = fmaf(x, w3.y, vh[13]); vh[14] = fmaf(x, w3.z, vh[14]); vh[15] = fmaf(x, w3.w, vh[15]);
         vh[16] = fmaf(x, w16, vh[16]);
     }
+    {
+        float sq[18];
 #pragma unroll
-    for (int h = 0; h < VMAX; ++h) {
-        const float s = sum3(vh[h] * vh[h], L);
-        if (L.own && (h % 3) == L.c && h < g.hd) put_scalar<C>(m, L.row, g.fin + h, sqrtf(fmaxf(s, 1e-8f)));
+        for (int h = 0; h < VMAX; ++h) sq[h] = sum3(vh[h] * vh[h], L);
+        sq[17] = 0.f;
+        // lane c of the row's triple stores h = c, c + 3, ...  (sqrt.approx: 2^-23 relative, far inside both modes' bars)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int h = 3 * j + L.c;
+            const float val = L.c == 0 ? sq[3 * j] : (L.c == 1 ? sq[3 * j + 1] : sq[3 * j + 2]);
+            if (L.own && h < g.hd) {
+                const int col = g.fin + h;
+                const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (col & 7) * 2) + L.rowoff;
+                const float x = sqrt_fast(fmaxf(val, 1e-8f));
+                const __nv_bfloat16 hi = __float2bfloat16(x);
+                *reinterpret_cast<__nv_bfloat16*>(m.A[0] + off) = hi;
+                if (C::NS == 2) *reinterpret_cast<__nv_bfloat16*>(m.A[1] + off) = __float2bfloat16(x - __bfloat162float(hi));
+            }
+        }
     }
     publish(m.tail_ready);
+    TC_T(t1);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
     float vu[16];
 #pragma unroll
@@ -360,29 +430,43 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
     const bool valid_e = C::R == 128 ? true : lane < 16;
     const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+    TC_T(t2);
     tc::mbar_wait(m.acc_done, gi & 1);
     tc::fence_after_sync();
+    TC_T(t3);
     {
         constexpr int cpw = 256 / C::NCG;
         const int row0 = C::R == 128 ? 32 * q : 16 * q;
         const int cend = row0 < rows_valid ? min(NBf, cg * cpw + cpw) : 0;   // warps of empty row quarters skip
-        for (int cb = cg * cpw; cb < cend; cb += 64) {
-            uint32_t v0[32], v1[32];
-            const bool two = cb + 32 < cend;
-            tc::tmem_ld_x32(taddr + cb, v0);
-            if (two) tc::tmem_ld_x32(taddr + cb + 32, v1);
-            tc::tmem_ld_wait();
-            if (valid_e) {
+        if constexpr (C::R == 128) {
+            for (int cb = cg * cpw; cb < cend; cb += 64) {
+                uint32_t v0[32], v1[32];
+                const bool two = cb + 32 < cend;
+                tc::tmem_ld_x32(taddr + cb, v0);
+                if (two) tc::tmem_ld_x32(taddr + cb + 32, v1);
+                tc::tmem_ld_wait();
                 epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
                 if (two) epi1_chunk<C>(v1, cb + 32, g.fout, NBf, bf_s, m, row_e);
+            }
+        } else {
+            for (int cb = cg * cpw; cb < cend; cb += 128) {
+                uint32_t v0[32], v1[32];
+                const bool two = cb + 64 < cend;
+                tc::tmem_ld_16x256b_x8(taddr + cb, v0);
+                if (two) tc::tmem_ld_16x256b_x8(taddr + cb + 64, v1);
+                tc::tmem_ld_wait();
+                epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                if (two) epi1_frag64<C>(v1, cb + 64, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
             }
         }
     }
     tc::fence_before_sync();
     publish(m.feats_ready);
+    TC_T(t4);
     // d. epilogue 2: vectors_out = act(gating) * Vu   (gvp.py:105-111)
     tc::mbar_wait(m.gates_done, gi & 1);
     tc::fence_after_sync();
+    TC_T(t5);
     {
         constexpr int CG = 16 / C::NCG;          // gate columns per warp
         uint32_t gv[CG];
@@ -401,6 +485,9 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
 #pragma unroll
     for (int u = 0; u < 16; ++u) v[u] = vu[u] * m.gate[u * C::R + L.row];
     v[16] = 0.f;
+    TC_T(t6);
+    WS_ACC(0, t0, t1); WS_ACC(1, t1, t2); WS_ACC(2, t2, t3); WS_ACC(3, t3, t4); WS_ACC(4, t4, t5); WS_ACC(5, t5, t6);
+    WS_ACC(6, 0, 1);
 }
 
 // Segment table of a dst-sorted tile: seg[0..nseg) = first row of every run of equal dst, seg[nseg] = n;
@@ -578,7 +665,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             }
         }
         TC_T(e4);
-        TC_ACC(8, e0, e1); TC_ACC(9, e1, e2); TC_ACC(10, e2, e3); TC_ACC(11, e3, e4); TC_ACC(13, 0, 1);
+        WS_ACC(8, e0, e1); WS_ACC(9, e1, e2); WS_ACC(10, e2, e3); WS_ACC(11, e3, e4); WS_ACC(13, 0, 1);
     }
     ws::teardown<C>(tmem);
 }

@@ -19,8 +19,8 @@ dev = torch.device("cuda:0")
 cfg = bench.load_config(cfg_name)
 arch = cfg["diffusion"].get("architecture", "egnn")
 model = bench.build_model(cfg, dev)
-if len(sys.argv) > 4 and sys.argv[4] == "bf16":
-    model.dynamics.set_precision("bf16")
+if len(sys.argv) > 4 and sys.argv[4] != "fp32":
+    model.dynamics.set_precision(sys.argv[4])
 pocket = bench.make_pocket(kind, 0, cfg, arch)
 g = HeteroBatch.from_pockets([pocket], [n_atoms] * B, 10).to(dev)
 sampler = model._sampler(g, 50, False)
