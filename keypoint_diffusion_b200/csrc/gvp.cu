@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_edge_kernel(const GvpEdgeLaunch L) 
 struct GvpNodeArgs {
     int n, Sdim, Vdim, lds, pw, n_upd, n_et, kch, edge_tile;
     float* s; float* v;                        // node features, updated in place
+    __nv_bfloat16* s_hi; __nv_bfloat16* s_lo;  // tensor-core modes: bf16 planes of the updated s (for the next gathers)
     const int* rowptr[2]; const float* sm[2]; const float* vm[2]; const float* part[2];
     int norm_mode; float norm_const;           // 0 const, 1 per-etype mean, 2 mean in-degree + 1
     const int* node_batch; const int* ptr;
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeLaunch L) 
 struct GvpHeadArgs {
     int n, Sdim, Vdim, lds, n_gvps, F, Fp, hid_out, kch;
     const float* s; const float* v;
+    const __nv_bfloat16* s_hi; const __nv_bfloat16* s_lo;
     GvpW g[MAXG];
     const float* WoT; const float* bo;
     float* eps_h; float* eps_x;
@@ -376,7 +378,7 @@ struct kpd_gvp_model {
     std::vector<GvpLayerW> layers;
     GvpW head[MAXG];
     const float* WoT; const float* bo;
-    size_t smem, smem_node, smem_tc, smem_ws1, smem_ws2;
+    size_t smem, smem_node, smem_tc, smem_ws1, smem_ws2, smem_ws1n;
     int kch;           // k-chunks of the bf16 tile (tensor-core mode)
     int mode;          // 0 = fp32 SIMT, 1 = bf16 tcgen05, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
     bool tc_ready, tc2_ready;
@@ -487,6 +489,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         m->smem_tc = gvp_tc_smem_bytes(m->kch);
         m->smem_ws1 = ws::smem_bytes<WsBf16>(m->kch);
         m->smem_ws2 = ws::smem_bytes<WsSplit>(m->kch);
+        m->smem_ws1n = ws::smem_bytes<WsBf16N>(m->kch);
         m->mode = 0;
         m->tc_ready = false;
         m->tc2_ready = false;
@@ -528,12 +531,16 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
     }
     if (nsplit == 2) {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws2);
         m->tc2_ready = true;
         return 0;
     }
     {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsBf16N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsBf16N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws1);
     }
     cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
@@ -556,11 +563,11 @@ extern "C" int kpd_debug_tc_times(unsigned long long* out16) {
 }
 
 // same for the warp-specialised kernels (gvp_ws.inl)
-extern "C" int kpd_debug_ws_times(unsigned long long* out16) {
-    KPD_REQUIRE(out16, "kpd_debug_ws_times: null argument");
+extern "C" int kpd_debug_ws_times(unsigned long long* out64) {
+    KPD_REQUIRE(out64, "kpd_debug_ws_times: null argument");
     cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, g_ws_times, sizeof(unsigned long long) * 16);
-    unsigned long long z[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out64, g_ws_times, sizeof(unsigned long long) * 64);
+    unsigned long long z[64] = {0};
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_ws_times, z, sizeof(z));
     KPD_REQUIRE(e == cudaSuccess, "kpd_debug_ws_times: %s", cudaGetErrorString(e));
     return 0;
@@ -652,7 +659,6 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             if (t > max_tiles) max_tiles = t;
         }
         L.kch = m->kch;
-        const bool tcm = m->mode == 1;
         const int edge_rows = m->mode == 1 ? WsBf16::R : m->mode == 2 ? WsSplit::R : TE;
         prof_begin(PROF_GVP_EDGE, st);
         if (m->mode != 0) {
@@ -674,7 +680,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
                 GvpNodeArgs& a = NL.nt[nt];
                 a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
                 a.n_upd = m->cfg.n_update_gvps; a.n_et = 2; a.kch = m->kch; a.edge_tile = edge_rows;
-                a.s = w.s[nt]; a.v = w.v[nt];
+                a.s = w.s[nt]; a.v = w.v[nt]; a.s_hi = w.s_hi[nt]; a.s_lo = w.s_lo[nt];
                 for (int k = 0; k < 2; ++k) {
                     const int e = nt * 2 + k;
                     a.rowptr[k] = G[e]->rowptr; a.sm[k] = w.sm[e]; a.vm[k] = w.vm[e]; a.part[k] = w.part[e];
@@ -688,15 +694,17 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             }
             if (max_n > 0) {
                 prof_begin(PROF_GVP_NODE, st);
-                if (tcm) {
-                    gvp_node_tc_kernel<<<dim3(cdiv(max_n, TC_NODE_ROWS), W.n_dst), NT_TC, m->smem_tc, st>>>(NL);
-                    KPD_TRY(check_launch("gvp_node_tc_kernel"));
+                if (m->mode == 1) {
+                    gvp_node_ws_kernel<WsBf16N><<<dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsBf16N::NT, m->smem_ws1n, st>>>(NL);
+                    KPD_TRY(check_launch("gvp_node_ws_kernel"));
+                } else if (m->mode == 2) {
+                    gvp_node_ws_kernel<WsSplit><<<dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsSplit::NT, m->smem_ws2, st>>>(NL);
+                    KPD_TRY(check_launch("gvp_node_ws_kernel"));
                 } else {
                     gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
                     KPD_TRY(check_launch("gvp_node_kernel"));
                 }
                 prof_end(PROF_GVP_NODE, st);
-                if (l + 1 < m->cfg.n_convs) KPD_TRY(split_planes(W.n_dst));
             }
         }
     }
@@ -705,15 +713,18 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         memset(&a, 0, sizeof(a));
         a.n = N[0]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.n_gvps = m->cfg.n_noise_gvps;
         a.F = m->F; a.Fp = m->Fp; a.hid_out = 64;
-        a.s = w.s[0]; a.v = w.v[0];
+        a.s = w.s[0]; a.v = w.v[0]; a.s_hi = w.s_hi[0]; a.s_lo = w.s_lo[0];
         for (int k = 0; k < a.n_gvps; ++k) a.g[k] = m->head[k];
         a.WoT = m->WoT; a.bo = m->bo; a.eps_h = eps_h; a.eps_x = eps_x;
         if (a.n > 0) {
             prof_begin(PROF_GVP_HEAD, st);
             a.kch = m->kch;
             if (m->mode == 1) {
-                gvp_head_tc_kernel<<<cdiv(a.n, TC_NODE_ROWS), NT_TC, m->smem_tc, st>>>(a);
-                KPD_TRY(check_launch("gvp_head_tc_kernel"));
+                gvp_head_ws_kernel<WsBf16N><<<cdiv(a.n, NODE_ROWS), WsBf16N::NT, m->smem_ws1n, st>>>(a);
+                KPD_TRY(check_launch("gvp_head_ws_kernel"));
+            } else if (m->mode == 2) {
+                gvp_head_ws_kernel<WsSplit><<<cdiv(a.n, NODE_ROWS), WsSplit::NT, m->smem_ws2, st>>>(a);
+                KPD_TRY(check_launch("gvp_head_ws_kernel"));
             } else {
                 gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);
                 KPD_TRY(check_launch("gvp_head_kernel"));

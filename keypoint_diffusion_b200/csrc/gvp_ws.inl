@@ -20,7 +20,7 @@
 // SIMT-only synchronisation uses named barrier 1; cross-role synchronisation uses mbarriers only.
 // phase timers of the warp-specialised kernels (cycles, SIMT thread 0, summed over CTAs):
 // [0..6] gvp_simt: Vh+|Vh|, Vu, wait acc, epilogue 1, wait gates, epilogue 2, calls
-__device__ unsigned long long g_ws_times[16];
+__device__ unsigned long long g_ws_times[64];   // edge kernel: base 0, node kernel: base 16, head kernel: base 32 (+8..13: kernel phases)
 #define WS_ACC(slot, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_ws_times[slot], (unsigned long long)((b) - (a))); } while (0)
 
 namespace ws {
@@ -365,7 +365,7 @@ __device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[32], int c0, int
 // published through feats_ready.
 template <class C>
 __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uint32_t tmem, float (&v)[VMAX], const Lane& L,
-                                         int rows_valid) {
+                                         int rows_valid, int tb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* Wh_s = m.wsm + gi * WSM;
     const float* Wu_s = Wh_s + VMAX * WH_LD;
@@ -486,8 +486,8 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     for (int u = 0; u < 16; ++u) v[u] = vu[u] * m.gate[u * C::R + L.row];
     v[16] = 0.f;
     TC_T(t6);
-    WS_ACC(0, t0, t1); WS_ACC(1, t1, t2); WS_ACC(2, t2, t3); WS_ACC(3, t3, t4); WS_ACC(4, t4, t5); WS_ACC(5, t5, t6);
-    WS_ACC(6, 0, 1);
+    WS_ACC(tb + 0, t0, t1); WS_ACC(tb + 1, t1, t2); WS_ACC(tb + 2, t2, t3); WS_ACC(tb + 3, t3, t4); WS_ACC(tb + 4, t4, t5);
+    WS_ACC(tb + 5, t5, t6); WS_ACC(tb + 6, 0, 1);
 }
 
 // Segment table of a dst-sorted tile: seg[0..nseg) = first row of every run of equal dst, seg[nseg] = n;
@@ -522,6 +522,7 @@ __device__ __forceinline__ void build_segments(const Sm& m, int n) {
 
 using WsBf16 = ws::Cfg<128, 1>;    // bf16 operands, 128-row tiles (M = 128)
 using WsSplit = ws::Cfg<64, 2>;    // bf16 hi/lo operands (three MMAs per product), 64-row tiles (M = 64)
+using WsBf16N = ws::Cfg<64, 1>;    // bf16 operands, 64-row tiles: node / head kernels (few rows per launch)
 
 // fp32 node scalars -> bf16 hi (and lo) planes, row-major [n][S]: what the edge kernels gather with 16-byte cp.async
 __global__ void split_planes_kernel(const float* __restrict__ s0, int n0, const float* __restrict__ s1, int n1, int S,
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         cp_async_wait<0>();
         ws::publish(m.feats_ready);
         TC_T(e2);
-        for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R);
+        for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R, 0);
         TC_T(e3);
         // ---- deterministic segmented reduction by destination (all MMAs and bulk copies have completed)
         float* VS = reinterpret_cast<float*>(m.ring);
@@ -666,6 +667,360 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         }
         TC_T(e4);
         WS_ACC(8, e0, e1); WS_ACC(9, e1, e2); WS_ACC(10, e2, e3); WS_ACC(11, e3, e4); WS_ACC(13, 0, 1);
+    }
+    ws::teardown<C>(tmem);
+}
+
+// ------------------------------------------------------------------ node kernel
+namespace ws {
+
+// 8 consecutive columns [c0, c0+8) of the aggregated message of node d for one edge type (see seg_gather)
+__device__ __forceinline__ void seg_gather8(const float* __restrict__ out, int ld_out, const float* __restrict__ part, int pw,
+                                            int r0, int r1, int d, int c0, int tile, float (&acc)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (r1 <= r0) return;
+    const int t0 = r0 / tile, t1 = (r1 - 1) / tile;
+    auto add = [&](const float* p) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    };
+    if (t0 == t1) { add(out + (size_t)d * ld_out + c0); return; }
+    add(part + ((size_t)t0 * 2 + 1) * pw + c0);
+    for (int t = t0 + 1; t <= t1; ++t) add(part + ((size_t)t * 2 + 0) * pw + c0);
+}
+
+// LayerNorm over a row held as 8 consecutive features per lane (features 8*lane .. 8*lane+7; lanes beyond Sdim idle)
+__device__ __forceinline__ void warp_layernorm8(float (&x)[8], bool act, int Sdim, const float* w, const float* b, int lane) {
+    float s = 0.f;
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += x[i];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)Sdim;
+    float v = 0.f;
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = x[i] - mean; v += d * d; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = 1.0f / sqrtf(v / (float)Sdim + 1e-5f);
+    if (act) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * lane), w1 = *reinterpret_cast<const float4*>(w + 8 * lane + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(b + 8 * lane), b1 = *reinterpret_cast<const float4*>(b + 8 * lane + 4);
+        x[0] = (x[0] - mean) * rstd * w0.x + b0.x; x[1] = (x[1] - mean) * rstd * w0.y + b0.y;
+        x[2] = (x[2] - mean) * rstd * w0.z + b0.z; x[3] = (x[3] - mean) * rstd * w0.w + b0.w;
+        x[4] = (x[4] - mean) * rstd * w1.x + b1.x; x[5] = (x[5] - mean) * rstd * w1.y + b1.y;
+        x[6] = (x[6] - mean) * rstd * w1.z + b1.z; x[7] = (x[7] - mean) * rstd * w1.w + b1.w;
+    }
+}
+
+// vector part of GVPLayerNorm (gvp.py:163-165) on the register-resident vectors of one row:
+// vn = sqrt(mean_u clamp(|v_u|^2, 1e-8) + eps) + eps
+__device__ __forceinline__ float vec_norm(const float (&v)[VMAX], int nv, const Lane& L) {
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const float n2 = sum3(v[u] * v[u], L);
+        if (u < nv) q += fmaxf(n2, 1e-8f);
+    }
+    return sqrtf(q / (float)nv + 1e-5f) + 1e-5f;
+}
+
+// 8 consecutive feats of one row read back from the bf16 plane(s)
+template <class C>
+__device__ __forceinline__ void get_chunk(const Sm& m, int row, int kc, float (&f)[8]) {
+    const uint32_t off = (uint32_t)(kc * C::KCS + (row >> 3) * 128 + (row & 7) * 16);
+    const uint4 hi = *reinterpret_cast<const uint4*>(m.A[0] + off);
+    f[0] = __uint_as_float(hi.x << 16); f[1] = __uint_as_float(hi.x & 0xffff0000u);
+    f[2] = __uint_as_float(hi.y << 16); f[3] = __uint_as_float(hi.y & 0xffff0000u);
+    f[4] = __uint_as_float(hi.z << 16); f[5] = __uint_as_float(hi.z & 0xffff0000u);
+    f[6] = __uint_as_float(hi.w << 16); f[7] = __uint_as_float(hi.w & 0xffff0000u);
+    if (C::NS == 2) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(m.A[1] + off);
+        f[0] += __uint_as_float(lo.x << 16); f[1] += __uint_as_float(lo.x & 0xffff0000u);
+        f[2] += __uint_as_float(lo.y << 16); f[3] += __uint_as_float(lo.y & 0xffff0000u);
+        f[4] += __uint_as_float(lo.z << 16); f[5] += __uint_as_float(lo.z & 0xffff0000u);
+        f[6] += __uint_as_float(lo.w << 16); f[7] += __uint_as_float(lo.w & 0xffff0000u);
+    }
+}
+
+// 8 fp32 values -> bf16 hi (and lo) planes in global memory (row-major, 16-byte stores)
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* hp, __nv_bfloat16* lp, size_t i, const float (&f)[8]) {
+    uint4 hi, lo;
+    hi.x = tc::pack_bf16x2(f[0], f[1]); hi.y = tc::pack_bf16x2(f[2], f[3]);
+    hi.z = tc::pack_bf16x2(f[4], f[5]); hi.w = tc::pack_bf16x2(f[6], f[7]);
+    lo.x = tc::pack_bf16x2(f[0] - __uint_as_float(hi.x << 16), f[1] - __uint_as_float(hi.x & 0xffff0000u));
+    lo.y = tc::pack_bf16x2(f[2] - __uint_as_float(hi.y << 16), f[3] - __uint_as_float(hi.y & 0xffff0000u));
+    lo.z = tc::pack_bf16x2(f[4] - __uint_as_float(hi.z << 16), f[5] - __uint_as_float(hi.z & 0xffff0000u));
+    lo.w = tc::pack_bf16x2(f[6] - __uint_as_float(hi.w << 16), f[7] - __uint_as_float(hi.w & 0xffff0000u));
+    *reinterpret_cast<uint4*>(hp + i) = hi;
+    *reinterpret_cast<uint4*>(lp + i) = lo;
+}
+
+}  // namespace ws
+
+// node / head tiles hold NODE_ROWS valid rows of the C::R-row MMA tile: node counts per launch are small, so
+// more, lighter CTAs (one wave) beat full tiles; rows are dealt round-robin to the SIMT warps for the scalar phases
+constexpr int NODE_ROWS = 32;
+
+// GVPMultiEdgeConv.forward after the message pass (models/gvp.py:501-536): messages / norm, residual,
+// GVPLayerNorm, update GVPs, residual, GVPLayerNorm; both node types in one launch.
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_constant__ GvpNodeLaunch L) {
+    const GvpNodeArgs& a = L.nt[blockIdx.y];
+    const int n0 = blockIdx.x * NODE_ROWS;
+    if (n0 >= a.n) return;
+    const int n = min(NODE_ROWS, a.n - n0);
+    constexpr int RPW = NODE_ROWS / C::NW;     // rows per warp in the scalar phases (row = warp + NW * j)
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    TC_T(n0t);
+    ws::Sm m = ws::carve<C>(smem_ws, a.kch);
+    const uint32_t tmem = ws::setup<C>(m, a.kch, a.upd, a.n_upd);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Sd = a.Sdim, Vd = a.Vdim;
+    if (warp == C::NW) {
+        if (lane == 0) ws::issue<C>(a.upd, a.n_upd, m, tmem);
+    } else if (warp == C::NW + 1) {
+        if (lane == 0) ws::produce<C>(a.upd, a.n_upd, m);
+    } else {
+        const ws::Lane Ln = ws::lane_geometry();
+        const bool act = 8 * lane < Sd;
+        // ---- phase 0: per-row metadata -> shared memory (one round trip for the whole tile)
+        int* meta = m.src_s;                                   // [R][4]: r0, r1 of both edge types
+        float* nvs = reinterpret_cast<float*>(m.src_s + 4 * C::R);   // [R]: the message normaliser
+        if (tid < C::R) {
+            const int nd = n0 + min(tid, n - 1);
+            for (int e = 0; e < 2; ++e) {
+                meta[4 * tid + 2 * e] = e < a.n_et ? a.rowptr[e][nd] : 0;
+                meta[4 * tid + 2 * e + 1] = e < a.n_et ? a.rowptr[e][nd + 1] : 0;
+            }
+            float nv = a.norm_const;
+            if (a.norm_mode == 1) nv = 1.0f;
+            else if (a.norm_mode == 2) {
+                const int b = a.node_batch[nd];
+                const int p0 = a.ptr[b], p1 = a.ptr[b + 1];
+                int tot = 0;
+                for (int e = 0; e < a.n_et; ++e) tot += a.rowptr[e][p1] - a.rowptr[e][p0];
+                nv = (float)tot / (float)(p1 - p0) + 1.0f;
+            }
+            nvs[tid] = nv;
+        }
+        ws::simt_bar<C>();
+        TC_T(n1t);
+        // ---- phase 1a: scalars, RPW rows per warp with every load of the batch in flight together:
+        //      features + messages / norm, LayerNorm -> residual (global) + A
+        {
+            const int lg = a.edge_tile == 128 ? 7 : 6;
+            float x[RPW][8];
+            float4 ga[RPW][2][2], sa[RPW][2];
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int r = warp + C::NW * j;
+                const int nd = n0 + min(r, n - 1);
+                const int col = act ? 8 * lane : 0;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r0 = meta[4 * r + 2 * e], r1 = meta[4 * r + 2 * e + 1];
+                    const int t0 = r0 >> lg, t1 = (max(r1, 1) - 1) >> lg;
+                    // whole CSR row inside one tile: the direct sum; else the first tile's "continues" partial
+                    const float* p = (r1 <= r0 || t0 == t1) ? a.sm[e] + (size_t)nd * Sd : a.part[e] + ((size_t)t0 * 2 + 1) * a.pw;
+                    ga[j][e][0] = __ldg(reinterpret_cast<const float4*>(p + col));
+                    ga[j][e][1] = __ldg(reinterpret_cast<const float4*>(p + col + 4));
+                }
+                sa[j][0] = __ldg(reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col));
+                sa[j][1] = __ldg(reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col + 4));
+            }
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int r = warp + C::NW * j;
+                float msg[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) msg[i] = 0.f;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r0 = meta[4 * r + 2 * e], r1 = meta[4 * r + 2 * e + 1];
+                    if (r1 > r0) {
+                        float g8[8] = {ga[j][e][0].x, ga[j][e][0].y, ga[j][e][0].z, ga[j][e][0].w,
+                                       ga[j][e][1].x, ga[j][e][1].y, ga[j][e][1].z, ga[j][e][1].w};
+                        const int t0 = r0 >> lg, t1 = (r1 - 1) >> lg;
+                        for (int t = t0 + 1; t <= t1; ++t) {      // rare: the row continues into further tiles
+                            const float* q = a.part[e] + ((size_t)t * 2 + 0) * a.pw + (act ? 8 * lane : 0);
+                            const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
+                            g8[0] += q0.x; g8[1] += q0.y; g8[2] += q0.z; g8[3] += q0.w;
+                            g8[4] += q1.x; g8[5] += q1.y; g8[6] += q1.z; g8[7] += q1.w;
+                        }
+                        const float cnt = a.norm_mode == 1 ? (float)(r1 - r0) : 1.0f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) msg[i] += a.norm_mode == 1 ? g8[i] / cnt : g8[i];
+                    }
+                }
+                const float nv = nvs[r];
+                x[j][0] = sa[j][0].x + msg[0] / nv; x[j][1] = sa[j][0].y + msg[1] / nv;
+                x[j][2] = sa[j][0].z + msg[2] / nv; x[j][3] = sa[j][0].w + msg[3] / nv;
+                x[j][4] = sa[j][1].x + msg[4] / nv; x[j][5] = sa[j][1].y + msg[5] / nv;
+                x[j][6] = sa[j][1].z + msg[6] / nv; x[j][7] = sa[j][1].w + msg[7] / nv;
+                ws::warp_layernorm8(x[j], act, Sd, a.mln_w, a.mln_b, lane);
+                if (act) {
+                    if (r < n) {
+                        float* sp = a.s + (size_t)(n0 + r) * Sd + 8 * lane;
+                        *reinterpret_cast<float4*>(sp) = make_float4(x[j][0], x[j][1], x[j][2], x[j][3]);
+                        *reinterpret_cast<float4*>(sp + 4) = make_float4(x[j][4], x[j][5], x[j][6], x[j][7]);
+                    }
+                    ws::put_chunk<C>(m, r, lane, x[j]);
+                }
+            }
+        }
+        // ---- phase 1b: vectors of lane (row, c) -> registers; residual stash in global
+        TC_T(n2t);
+        float v[VMAX];
+        {
+            const int nd = n0 + min(Ln.row, n - 1);
+            const float nv = nvs[Ln.row];
+#pragma unroll
+            for (int u = 0; u < VMAX; ++u) v[u] = 0.f;
+            for (int e = 0; e < a.n_et; ++e) {
+                const int r0 = meta[4 * Ln.row + 2 * e], r1 = meta[4 * Ln.row + 2 * e + 1];
+                const float cnt = a.norm_mode == 1 ? (float)max(r1 - r0, 1) : 1.0f;
+                if (r1 > r0) {
+                    const int t0 = r0 / a.edge_tile, t1 = (r1 - 1) / a.edge_tile;
+                    float g[16];
+                    if (t0 == t1) {            // the common case: one tile holds the whole CSR row -> 16 independent loads
+                        const float* p = a.vm[e] + (size_t)nd * (3 * Vd) + Ln.c;
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) g[u] = u < Vd ? __ldg(p + 3 * u) : 0.f;
+                    } else {
+                        const float* p = a.part[e] + ((size_t)t0 * 2 + 1) * a.pw + Sd + Ln.c;
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) g[u] = u < Vd ? p[3 * u] : 0.f;
+                        for (int t = t0 + 1; t <= t1; ++t) {
+                            const float* q = a.part[e] + ((size_t)t * 2 + 0) * a.pw + Sd + Ln.c;
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) if (u < Vd) g[u] += q[3 * u];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) v[u] += a.norm_mode == 1 ? g[u] / cnt : g[u];
+                }
+            }
+            const float* vp = a.v + (size_t)nd * (3 * Vd) + Ln.c;
+            float vr[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) vr[u] = u < Vd ? __ldg(vp + 3 * u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = vr[u] + v[u] / nv;
+            const float vn = ws::vec_norm(v, Vd, Ln);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = v[u] / vn;
+            if (Ln.own && Ln.row < n) {
+                float* vo = a.v + (size_t)nd * (3 * Vd) + Ln.c;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) if (u < Vd) vo[3 * u] = v[u];
+            }
+        }
+        ws::publish(m.feats_ready);
+        TC_T(n3t);
+        // ---- phase 2: update GVPs on the tensor cores
+        for (int i = 0; i < a.n_upd; ++i) ws::gvp_simt<C>(a.upd[i], i, m, tmem, v, Ln, n, 16);
+        // ---- phase 3: residual + GVPLayerNorm -> global (fp32 + the bf16 planes the next edge kernel gathers)
+        TC_T(n4t);
+        {
+            float x[RPW][8];
+            float4 sa[RPW][2];
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int r = warp + C::NW * j;
+                const int nd = n0 + min(r, n - 1);
+                const int col = act ? 8 * lane : 0;
+                sa[j][0] = *reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col);
+                sa[j][1] = *reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col + 4);
+            }
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int r = warp + C::NW * j;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[j][i] = 0.f;
+                if (act) {
+                    ws::get_chunk<C>(m, r, lane, x[j]);
+                    x[j][0] += sa[j][0].x; x[j][1] += sa[j][0].y; x[j][2] += sa[j][0].z; x[j][3] += sa[j][0].w;
+                    x[j][4] += sa[j][1].x; x[j][5] += sa[j][1].y; x[j][6] += sa[j][1].z; x[j][7] += sa[j][1].w;
+                }
+                ws::warp_layernorm8(x[j], act, Sd, a.uln_w, a.uln_b, lane);
+                if (act && r < n) {
+                    const size_t o = (size_t)(n0 + r) * Sd + 8 * lane;
+                    *reinterpret_cast<float4*>(a.s + o) = make_float4(x[j][0], x[j][1], x[j][2], x[j][3]);
+                    *reinterpret_cast<float4*>(a.s + o + 4) = make_float4(x[j][4], x[j][5], x[j][6], x[j][7]);
+                    ws::store_planes8(a.s_hi, a.s_lo, o, x[j]);
+                }
+            }
+        }
+        {
+            const int nd = n0 + min(Ln.row, n - 1);
+            const float* vp = a.v + (size_t)nd * (3 * Vd) + Ln.c;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = u < Vd ? v[u] + vp[3 * u] : 0.f;
+            const float vn = ws::vec_norm(v, Vd, Ln);
+            if (Ln.own && Ln.row < n) {
+                float* vo = a.v + (size_t)nd * (3 * Vd) + Ln.c;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) if (u < Vd) vo[3 * u] = v[u] / vn;
+            }
+        }
+        TC_T(n5t);
+        WS_ACC(24, n0t, n1t); WS_ACC(25, n1t, n2t); WS_ACC(26, n2t, n3t); WS_ACC(27, n3t, n4t); WS_ACC(28, n4t, n5t); WS_ACC(29, 0, 1);
+    }
+    ws::teardown<C>(tmem);
+}
+
+// NoisePredictionBlock (models/dynamics_gvp.py:38-44): noise GVPs + Linear(64 -> atom_nf); eps_x = vectors.squeeze(1)
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_constant__ GvpHeadArgs a) {
+    const int n0 = blockIdx.x * NODE_ROWS;
+    if (n0 >= a.n) return;
+    const int n = min(NODE_ROWS, a.n - n0);
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    ws::Sm m = ws::carve<C>(smem_ws, a.kch);
+    const uint32_t tmem = ws::setup<C>(m, a.kch, a.g, a.n_gvps);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Sd = a.Sdim, Vd = a.Vdim;
+    if (warp == C::NW) {
+        if (lane == 0) ws::issue<C>(a.g, a.n_gvps, m, tmem);
+    } else if (warp == C::NW + 1) {
+        if (lane == 0) ws::produce<C>(a.g, a.n_gvps, m);
+    } else {
+        const ws::Lane Ln = ws::lane_geometry();
+        {
+            const int items = NODE_ROWS * (Sd >> 3);
+            for (int idx = tid; idx < items; idx += C::NT_SIMT) {
+                const int r = idx % NODE_ROWS, kc = idx / NODE_ROWS;
+                const uint32_t off = (uint32_t)(kc * C::KCS + (r >> 3) * 128 + (r & 7) * 16);
+                const size_t g = (size_t)(n0 + min(r, n - 1)) * Sd + 8 * kc;
+                cp_async16(m.A[0] + off, a.s_hi + g);
+                if (C::NS == 2) cp_async16(m.A[1] + off, a.s_lo + g);
+            }
+            cp_async_commit();
+        }
+        float v[VMAX];
+        {
+            const float* vp = a.v + (size_t)(n0 + min(Ln.row, n - 1)) * (3 * Vd) + Ln.c;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = u < Vd ? vp[3 * u] : 0.f;
+            v[16] = 0.f;
+        }
+        cp_async_wait<0>();
+        ws::publish(m.feats_ready);
+        for (int i = 0; i < a.n_gvps; ++i) ws::gvp_simt<C>(a.g[i], i, m, tmem, v, Ln, n, 32);
+        // to_scalar_output + vectors.squeeze(1)  (dynamics_gvp.py:42-43)
+        for (int idx = tid; idx < n * a.F; idx += C::NT_SIMT) {
+            const int r = idx / a.F, c = idx - r * a.F;
+            float s = a.bo[c];
+            for (int k = 0; k < a.hid_out; ++k) s = fmaf(ws::get_scalar<C>(m, r, k), a.WoT[k * a.Fp + c], s);
+            a.eps_h[(size_t)(n0 + r) * a.F + c] = s;
+        }
+        if (Ln.own && Ln.row < n) a.eps_x[(size_t)(n0 + Ln.row) * 3 + Ln.c] = v[0];
     }
     ws::teardown<C>(tmem);
 }
