@@ -364,6 +364,26 @@ __global__ void __launch_bounds__(NT, 1) gvp_head_kernel(const GvpHeadArgs a) {
 
 using namespace kpd;
 
+// launch with thread-block clusters of `cl` CTAs along x (grid.x is rounded up to a multiple of cl)
+template <typename Arg>
+static void launch_clustered(void (*kernel)(Arg), dim3 grid, int threads, size_t smem, cudaStream_t st, int cl, const Arg& arg) {
+    grid.x = (grid.x + cl - 1) / cl * cl;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+
 struct GvpLayerW {
     int n_et, n_dst;
     GvpW msg[4][MAXG];
@@ -562,6 +582,25 @@ extern "C" int kpd_debug_tc_times(unsigned long long* out16) {
     return 0;
 }
 
+// event trace of one edge-kernel CTA (only with -DKPD_WS_TRACE): out = [n][3] (tag, warp, clock); returns n via *count
+extern "C" int kpd_debug_ws_trace(unsigned long long* out, int32_t cap, int32_t* count) {
+#ifdef KPD_WS_TRACE
+    cudaError_t e = cudaDeviceSynchronize();
+    int n = 0;
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&n, g_ws_trace_n, sizeof(int));
+    if (n > 2048) n = 2048;
+    if (n > cap) n = cap;
+    if (e == cudaSuccess && n > 0) e = cudaMemcpyFromSymbol(out, g_ws_trace, sizeof(unsigned long long) * 3 * n);
+    KPD_REQUIRE(e == cudaSuccess, "kpd_debug_ws_trace: %s", cudaGetErrorString(e));
+    *count = n;
+    return 0;
+#else
+    (void)out; (void)cap;
+    *count = 0;
+    return 0;
+#endif
+}
+
 // same for the warp-specialised kernels (gvp_ws.inl)
 extern "C" int kpd_debug_ws_times(unsigned long long* out64) {
     KPD_REQUIRE(out64, "kpd_debug_ws_times: null argument");
@@ -664,8 +703,8 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         if (m->mode != 0) {
             int tiles_tc = 1;
             for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, edge_rows); if (t > tiles_tc) tiles_tc = t; }
-            if (m->mode == 1) gvp_edge_ws_kernel<WsBf16><<<dim3(tiles_tc, W.n_et), WsBf16::NT, m->smem_ws1, st>>>(L);
-            else gvp_edge_ws_kernel<WsSplit><<<dim3(tiles_tc, W.n_et), WsSplit::NT, m->smem_ws2, st>>>(L);
+            if (m->mode == 1) launch_clustered(gvp_edge_ws_kernel<WsBf16>, dim3(tiles_tc, W.n_et), WsBf16::NT, m->smem_ws1, st, WsBf16::CL, L);
+            else launch_clustered(gvp_edge_ws_kernel<WsSplit>, dim3(tiles_tc, W.n_et), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, L);
             KPD_TRY(check_launch("gvp_edge_ws_kernel"));
         } else {
             gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
@@ -695,10 +734,10 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             if (max_n > 0) {
                 prof_begin(PROF_GVP_NODE, st);
                 if (m->mode == 1) {
-                    gvp_node_ws_kernel<WsBf16N><<<dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsBf16N::NT, m->smem_ws1n, st>>>(NL);
+                    launch_clustered(gvp_node_ws_kernel<WsBf16N>, dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsBf16N::NT, m->smem_ws1n, st, WsBf16N::CL, NL);
                     KPD_TRY(check_launch("gvp_node_ws_kernel"));
                 } else if (m->mode == 2) {
-                    gvp_node_ws_kernel<WsSplit><<<dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsSplit::NT, m->smem_ws2, st>>>(NL);
+                    launch_clustered(gvp_node_ws_kernel<WsSplit>, dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, NL);
                     KPD_TRY(check_launch("gvp_node_ws_kernel"));
                 } else {
                     gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
@@ -720,10 +759,10 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             prof_begin(PROF_GVP_HEAD, st);
             a.kch = m->kch;
             if (m->mode == 1) {
-                gvp_head_ws_kernel<WsBf16N><<<cdiv(a.n, NODE_ROWS), WsBf16N::NT, m->smem_ws1n, st>>>(a);
+                launch_clustered(gvp_head_ws_kernel<WsBf16N>, dim3(cdiv(a.n, NODE_ROWS)), WsBf16N::NT, m->smem_ws1n, st, WsBf16N::CL, a);
                 KPD_TRY(check_launch("gvp_head_ws_kernel"));
             } else if (m->mode == 2) {
-                gvp_head_ws_kernel<WsSplit><<<cdiv(a.n, NODE_ROWS), WsSplit::NT, m->smem_ws2, st>>>(a);
+                launch_clustered(gvp_head_ws_kernel<WsSplit>, dim3(cdiv(a.n, NODE_ROWS)), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, a);
                 KPD_TRY(check_launch("gvp_head_ws_kernel"));
             } else {
                 gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);

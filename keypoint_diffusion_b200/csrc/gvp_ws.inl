@@ -23,6 +23,17 @@
 __device__ unsigned long long g_ws_times[64];   // edge kernel: base 0, node kernel: base 16, head kernel: base 32 (+8..13: kernel phases)
 #define WS_ACC(slot, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_ws_times[slot], (unsigned long long)((b) - (a))); } while (0)
 
+// event trace of ONE CTA (block (1, 1) of the edge kernel) for timeline analysis: (tag, warp, clock) triples
+#ifdef KPD_WS_TRACE
+__device__ unsigned long long g_ws_trace[3 * 2048];
+__device__ int g_ws_trace_n;
+#define WS_TRACE(tag) do { if (blockIdx.x == 1 && blockIdx.y == 1 && (threadIdx.x & 31) == 0) { \
+        const int _i = atomicAdd(&g_ws_trace_n, 1); \
+        if (_i < 2048) { g_ws_trace[3 * _i] = (tag); g_ws_trace[3 * _i + 1] = threadIdx.x >> 5; g_ws_trace[3 * _i + 2] = clock64(); } } } while (0)
+#else
+#define WS_TRACE(tag) do { } while (0)
+#endif
+
 namespace ws {
 
 constexpr int WH_LD = 20;                                   // Wh staged as [17][20] (zero padded)
@@ -31,13 +42,15 @@ constexpr int VS_LD = 52;                                   // fp32 vector stagi
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t GATE_COL = 256;
 
-template <int R_, int NS_>
+template <int R_, int NS_, int CL_>
 struct Cfg {
     static constexpr int R = R_, NS = NS_;
+    static constexpr int CL = CL_;                   // CTAs per cluster: neighbouring tiles share ONE weight stream (multicast)
     static constexpr int NW = R / 8;                 // SIMT warps: 8 rows each, lanes = (row, xyz component)
     static constexpr int NT_SIMT = 32 * NW;
     static constexpr int NT = NT_SIMT + 64;
-    static constexpr int KCS = (R / 8) * 128 + 16;   // bytes between k-chunks of A (+16: bank rotation for column walks)
+    static constexpr int MMA_M = R * NS;             // NS = 2 stacks the hi and lo rows of a tile into ONE 128-row A operand
+    static constexpr int KCS = (MMA_M / 8) * 128 + 16;   // bytes between k-chunks of A (+16: bank rotation for column walks)
     static constexpr int STAGES = NS == 1 ? 8 : 4;
     static constexpr int SLAB = NS * 8192;           // one ring stage: one k-step of a 256-row weight (hi [, lo])
     static constexpr int WG_BYTES = NS * 8192;       // gates weight: 16 k-steps x 512 B (hi [, lo])
@@ -56,12 +69,23 @@ struct Sm {
     int* warp_cnt;
 };
 
+// bytes of the A operand (all MMA_M rows)
 template <class C>
 __host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C::KCS + 127) & ~(size_t)127; }
 
+// Byte offset of tile row r inside a k-chunk of A.  NS = 1: plain canonical rows.  NS = 2: MMA rows are ordered
+// (16-row group q, plane, row % 16): TMEM lanes [32q, 32q+16) hold the hi rows and [32q+16, 32q+32) the lo rows of
+// tile rows [16q, 16q+16), so one warp reads both halves of a row's accumulator (16x256b loads) and adds them.
+// The lo row of r sits 256 bytes after its hi row.
+template <class C>
+__device__ __forceinline__ uint32_t row_off(int r) {
+    if (C::NS == 2) return (uint32_t)((4 * (r >> 4) + ((r >> 3) & 1)) * 128 + (r & 7) * 16);
+    return (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+}
+
 template <class C>
 static size_t smem_bytes(int kch) {
-    return C::NS * plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + 2 * C::WG_BYTES + sizeof(float) * MAXG * WSM +
+    return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + 2 * C::WG_BYTES + sizeof(float) * MAXG * WSM +
            sizeof(float) * 16 * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 8) + 16 + 128;
 }
 
@@ -69,8 +93,8 @@ template <class C>
 __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     Sm m;
     m.A[0] = smem;
-    m.A[1] = smem + (C::NS - 1) * plane_bytes<C>(kch);
-    m.ring = smem + C::NS * plane_bytes<C>(kch);
+    m.A[1] = smem + (C::NS - 1) * 256;            // lo rows: 2 row groups after their hi rows
+    m.ring = smem + plane_bytes<C>(kch);
     m.Wg[0] = m.ring + C::STAGES * C::SLAB;
     m.Wg[1] = m.Wg[0] + C::WG_BYTES;
     m.wsm = reinterpret_cast<float*>(m.Wg[1] + C::WG_BYTES);
@@ -100,7 +124,7 @@ template <class C>
 __device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_gvps) {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], 1); }
+        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], 1); }
         tc::mbar_init(m.feats_ready, C::NW);
         tc::mbar_init(m.tail_ready, C::NW);
@@ -110,7 +134,7 @@ __device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_
     }
     if (warp == C::NW) { tc::tmem_alloc(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish(); }
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const int nz = (int)(C::NS * plane_bytes<C>(kch) / 16);
+    const int nz = (int)(plane_bytes<C>(kch) / 16);
     for (int i = tid; i < nz; i += C::NT) reinterpret_cast<uint4*>(m.A[0])[i] = z;
     for (int idx = tid; idx < n_gvps * WSM; idx += C::NT) {
         const int gi = idx / WSM, o = idx - gi * WSM;
@@ -134,6 +158,7 @@ __device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
+    if (C::CL > 1) tc::cluster_sync();      // every CTA's barriers exist before a peer multicasts into it
     tc::fence_after_sync();
     return *m.tmem_slot;
 }
@@ -143,79 +168,137 @@ __device__ __forceinline__ void teardown(uint32_t tmem) {
     tc::fence_before_sync();
     __syncthreads();
     if ((threadIdx.x >> 5) == C::NW) tc::tmem_dealloc(tmem, TMEM_COLS);
+    if (C::CL > 1) tc::cluster_sync();      // no CTA leaves while a peer may still signal its barriers
 }
 
 // ------------------------------------------------------------------ producer (one thread)
 template <class C>
-__device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m) {
+__device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool dead = false) {
     uint32_t it = 0;
+    const uint32_t rank = C::CL > 1 ? tc::cluster_ctarank() : 0u;
+    constexpr uint16_t mask = (uint16_t)((1u << C::CL) - 1u);
+#ifdef KPD_WS_TRACE
+    unsigned long long tp[64];
+#endif
     for (int g = 0; g < n_gvps; ++g) {
         const GvpW& w = gv[g];
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksg = NBf >> 4;
         const uint32_t slab = C::NS * 2 * (NBf / 8) * 128;
         const int b = g & 1;
-        if (g >= 2) tc::mbar_wait(&m.wg_empty[b], ((g >> 1) - 1) & 1);      // gates MMA g-2 has consumed this buffer
-        tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
         const uint4* WfP = C::NS == 2 ? w.WfP2 : w.WfP;
-        tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
+        if (!dead) {
+            if (g >= 2) tc::mbar_wait(&m.wg_empty[b], ((g >> 1) - 1) & 1);      // gates MMA g-2 has consumed this buffer
+            tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
+            tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
+        }
         for (int j = 0; j < ksf; ++j, ++it) {
             const uint32_t st = it % C::STAGES;
             if (it >= (uint32_t)C::STAGES) tc::mbar_wait(&m.empty[st], ((it / C::STAGES) - 1) & 1);
             tc::mbar_arrive_expect_tx(&m.full[st], slab);
-            tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
+            if (C::CL == 1) {
+                tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
+            } else {
+                // this CTA fetches 1/CL of the slab and multicasts it to the whole cluster; every CTA's full[st]
+                // expects the whole slab (the CL parts arrive from the CL producers)
+                const uint32_t part = slab / C::CL;
+                tc::bulk_g2s_multicast(m.ring + (size_t)st * C::SLAB + rank * part,
+                                       reinterpret_cast<const unsigned char*>(WfP) + (size_t)j * slab + rank * part, part,
+                                       &m.full[st], mask);
+            }
+#ifdef KPD_WS_TRACE
+            if (it < 64) tp[it] = clock64();
+#endif
         }
     }
+#ifdef KPD_WS_TRACE
+    if (blockIdx.x == 1 && blockIdx.y == 1) {
+        for (uint32_t i = 0; i < it && i < 64; ++i) {
+            const int k = atomicAdd(&g_ws_trace_n, 1);
+            if (k < 2048) { g_ws_trace[3 * k] = 100 + i; g_ws_trace[3 * k + 1] = threadIdx.x >> 5; g_ws_trace[3 * k + 2] = tp[i]; }
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------ MMA issuer (one thread)
 template <class C>
 __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_t tmem) {
     uint32_t it = 0;
+#ifdef KPD_WS_TRACE
+    unsigned long long tk[64];
+#endif
     tc::mbar_wait(m.feats_ready, 0);
     tc::fence_after_sync();
+    WS_TRACE(1);
     for (int g = 0; g < n_gvps; ++g) {
         const GvpW& w = gv[g];
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksm = w.fin >> 4, ksg = NBf >> 4;
-        const uint32_t idesc = tc::make_idesc_bf16(C::R, NBf);
+        const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NBf);
         const uint32_t b_k = (NBf / 8) * 128, slab1 = 2 * b_k;
         for (int j = 0; j < ksf; ++j, ++it) {
-            if (j == ksm) { tc::mbar_wait(m.tail_ready, g & 1); tc::fence_after_sync(); }
+            if (j == ksm) { WS_TRACE(2); tc::mbar_wait(m.tail_ready, g & 1); tc::fence_after_sync(); WS_TRACE(3); }
             const uint32_t st = it % C::STAGES;
             tc::mbar_wait(&m.full[st], (it / C::STAGES) & 1);
             tc::fence_after_sync();
+#ifdef KPD_WS_TRACE
+            if (it < 64) tk[it] = clock64();
+#endif
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
             tc::mma_bf16_ss(tmem, a0, b0, idesc, j > 0 ? 1u : 0u);
-            if (C::NS == 2) {
-                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+            if (C::NS == 2) {       // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
                 const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
-                tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);
                 tc::mma_bf16_ss(tmem, a0, b1, idesc, 1u);
             }
-            tc::mma_commit(&m.empty[st]);
+            if (C::CL == 1) tc::mma_commit(&m.empty[st]);
+            else tc::mma_commit_multicast(&m.empty[st], (uint16_t)((1u << C::CL) - 1u));   // frees the slot in every CTA
         }
         tc::mma_commit(m.acc_done);
+        WS_TRACE(4);
         // epilogue 1 of this GVP done: feats_out is in A, the accumulator columns are free again
         tc::mbar_wait(m.feats_ready, (g + 1) & 1);
         tc::fence_after_sync();
+        WS_TRACE(5);
         tc::mbar_wait(&m.wg_full[g & 1], (g >> 1) & 1);
         tc::fence_after_sync();
-        const uint32_t idg = tc::make_idesc_bf16(C::R, 16);
+        const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
         const uint32_t wg = tc::smem_u32(m.Wg[0] + (g & 1) * C::WG_BYTES);
         for (int j = 0; j < ksg; ++j) {
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
             tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, j > 0 ? 1u : 0u);
             if (C::NS == 2) {
-                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
                 const uint64_t b1 = tc::make_smem_desc(wg + j * 1024 + 512, 256, 128);
-                tc::mma_bf16_ss(tmem + GATE_COL, a1, b0, idg, 1u);
                 tc::mma_bf16_ss(tmem + GATE_COL, a0, b1, idg, 1u);
             }
         }
         tc::mma_commit(m.gates_done);
         tc::mma_commit(&m.wg_empty[g & 1]);
+        WS_TRACE(6);
+    }
+#ifdef KPD_WS_TRACE
+    if (blockIdx.x == 1 && blockIdx.y == 1) {
+        for (uint32_t i = 0; i < it && i < 64; ++i) {
+            const int k = atomicAdd(&g_ws_trace_n, 1);
+            if (k < 2048) { g_ws_trace[3 * k] = 200 + i; g_ws_trace[3 * k + 1] = threadIdx.x >> 5; g_ws_trace[3 * k + 2] = tk[i]; }
+        }
+    }
+#endif
+}
+
+// A CTA of a live cluster whose own tile is empty still takes part in the shared weight stream: its producer
+// fetches its share, and this loop releases every ring slot as soon as it has filled.
+template <class C>
+__device__ __forceinline__ void drain(const GvpW* gv, int n_gvps, Sm& m) {
+    uint32_t it = 0;
+    for (int g = 0; g < n_gvps; ++g) {
+        const int ksf = (gv[g].fin + gv[g].hd + 15) >> 4;
+        for (int j = 0; j < ksf; ++j, ++it) {
+            const uint32_t st = it % C::STAGES;
+            tc::mbar_wait(&m.full[st], (it / C::STAGES) & 1);
+            for (uint32_t r = 0; r < (uint32_t)C::CL; ++r) tc::mbar_arrive_remote(tc::map_to_cta(&m.empty[st], r));
+        }
     }
 }
 
@@ -239,7 +322,7 @@ __device__ __forceinline__ float act_sigmoid(float x) { return NS == 1 ? sigmoid
 // store one value into the bf16 plane(s) at (row, col)
 template <class C>
 __device__ __forceinline__ void put_scalar(const Sm& m, int row, int col, float x) {
-    const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (row >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
+    const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (col & 7) * 2) + row_off<C>(row);
     const __nv_bfloat16 hi = __float2bfloat16(x);
     *reinterpret_cast<__nv_bfloat16*>(m.A[0] + off) = hi;
     if (C::NS == 2) *reinterpret_cast<__nv_bfloat16*>(m.A[1] + off) = __float2bfloat16(x - __bfloat162float(hi));
@@ -248,7 +331,7 @@ __device__ __forceinline__ void put_scalar(const Sm& m, int row, int col, float 
 // 8 consecutive columns (one k-chunk) of one row
 template <class C>
 __device__ __forceinline__ void put_chunk(const Sm& m, int row, int kc, const float (&f)[8]) {
-    const uint32_t off = (uint32_t)(kc * C::KCS + (row >> 3) * 128 + (row & 7) * 16);
+    const uint32_t off = (uint32_t)(kc * C::KCS) + row_off<C>(row);
     uint4 hi;
     hi.x = tc::pack_bf16x2(f[0], f[1]); hi.y = tc::pack_bf16x2(f[2], f[3]);
     hi.z = tc::pack_bf16x2(f[4], f[5]); hi.w = tc::pack_bf16x2(f[6], f[7]);
@@ -266,7 +349,7 @@ __device__ __forceinline__ void put_chunk(const Sm& m, int row, int kc, const fl
 // value of (row, col) read back from the plane(s)
 template <class C>
 __device__ __forceinline__ float get_scalar(const Sm& m, int row, int col) {
-    const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (row >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
+    const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (col & 7) * 2) + row_off<C>(row);
     float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(m.A[0] + off));
     if (C::NS == 2) x += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(m.A[1] + off));
     return x;
@@ -287,6 +370,7 @@ struct Lane {
     bool own;    // false for the 8 spare lanes (they mirror row 7 of the warp and never store)
     uint32_t rowoff;   // byte offset of the row inside a k-chunk of A
 };
+template <class C>
 __device__ __forceinline__ Lane lane_geometry() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Lane L;
@@ -295,7 +379,7 @@ __device__ __forceinline__ Lane lane_geometry() {
     L.row = 8 * warp + rr;
     L.bl = 3 * rr;
     L.own = lane < 24;
-    L.rowoff = (uint32_t)((L.row >> 3) * 128 + (L.row & 7) * 16);
+    L.rowoff = row_off<C>(L.row);
     return L;
 }
 __device__ __forceinline__ float sum3(float x, const Lane& L) {
@@ -335,7 +419,7 @@ template <class C>
 __device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
                                             const Sm& m, int row_a, int lane) {
     const int cp = 2 * (lane & 3);
-    const uint32_t ro = (uint32_t)((row_a >> 3) * 128 + (row_a & 7) * 16 + cp * 2);
+    const uint32_t ro = row_off<C>(row_a) + cp * 2;     // row_a + 8 is the next 8-row group: + 128 bytes
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int col = c0 + 8 * i;
@@ -374,6 +458,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const int NBf = (g.fout + 15) & ~15;
     // a. Vh = V^T Wh (gvp.py:96); sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
     TC_T(t0);
+    WS_TRACE(10);
     float vh[VMAX];
 #pragma unroll
     for (int h = 0; h < VMAX; ++h) vh[h] = 0.f;
@@ -411,6 +496,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     }
     publish(m.tail_ready);
     TC_T(t1);
+    WS_TRACE(11);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
     float vu[16];
 #pragma unroll
@@ -431,9 +517,11 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const bool valid_e = C::R == 128 ? true : lane < 16;
     const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
     TC_T(t2);
+    WS_TRACE(12);
     tc::mbar_wait(m.acc_done, gi & 1);
     tc::fence_after_sync();
     TC_T(t3);
+    WS_TRACE(13);
     {
         constexpr int cpw = 256 / C::NCG;
         const int row0 = C::R == 128 ? 32 * q : 16 * q;
@@ -448,7 +536,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                 epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
                 if (two) epi1_chunk<C>(v1, cb + 32, g.fout, NBf, bf_s, m, row_e);
             }
-        } else {
+        } else if constexpr (C::NS == 1) {
             for (int cb = cg * cpw; cb < cend; cb += 128) {
                 uint32_t v0[32], v1[32];
                 const bool two = cb + 64 < cend;
@@ -458,15 +546,28 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                 epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
                 if (two) epi1_frag64<C>(v1, cb + 64, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
             }
+        } else {
+            // stacked operand: lanes [32q, 32q+16) = A_hi (W_hi + W_lo), lanes [32q+16, 32q+32) = A_lo (W_hi + W_lo)
+            for (int cb = cg * cpw; cb < cend; cb += 64) {
+                uint32_t v0[32], v1[32];
+                tc::tmem_ld_16x256b_x8(taddr + cb, v0);
+                tc::tmem_ld_16x256b_x8(taddr + (16u << 16) + cb, v1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
+                epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+            }
         }
     }
     tc::fence_before_sync();
     publish(m.feats_ready);
     TC_T(t4);
+    WS_TRACE(14);
     // d. epilogue 2: vectors_out = act(gating) * Vu   (gvp.py:105-111)
     tc::mbar_wait(m.gates_done, gi & 1);
     tc::fence_after_sync();
     TC_T(t5);
+    WS_TRACE(15);
     {
         constexpr int CG = 16 / C::NCG;          // gate columns per warp
         uint32_t gv[CG];
@@ -476,7 +577,9 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
 #pragma unroll
         for (int i = 0; i < CG; ++i) {
             const int u = cg * CG + i;
-            float a = __uint_as_float(gv[i]) + bg_s[u];
+            float a = __uint_as_float(gv[i]);
+            if (C::NS == 2) a += __shfl_xor_sync(0xffffffffu, a, 16);     // hi rows (lanes 0-15) + lo rows (lanes 16-31)
+            a += bg_s[u];
             if (g.sigmoid_gate) a = act_sigmoid<C::NS>(a);
             if (valid_e) m.gate[u * C::R + row_e] = a;
         }
@@ -486,6 +589,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     for (int u = 0; u < 16; ++u) v[u] = vu[u] * m.gate[u * C::R + L.row];
     v[16] = 0.f;
     TC_T(t6);
+    WS_TRACE(16);
     WS_ACC(tb + 0, t0, t1); WS_ACC(tb + 1, t1, t2); WS_ACC(tb + 2, t2, t3); WS_ACC(tb + 3, t3, t4); WS_ACC(tb + 4, t4, t5);
     WS_ACC(tb + 5, t5, t6); WS_ACC(tb + 6, 0, 1);
 }
@@ -520,9 +624,12 @@ __device__ __forceinline__ void build_segments(const Sm& m, int n) {
 
 }  // namespace ws
 
-using WsBf16 = ws::Cfg<128, 1>;    // bf16 operands, 128-row tiles (M = 128)
-using WsSplit = ws::Cfg<64, 2>;    // bf16 hi/lo operands (three MMAs per product), 64-row tiles (M = 64)
-using WsBf16N = ws::Cfg<64, 1>;    // bf16 operands, 64-row tiles: node / head kernels (few rows per launch)
+#ifndef KPD_WS_CLUSTER
+#define KPD_WS_CLUSTER 1
+#endif
+using WsBf16 = ws::Cfg<128, 1, KPD_WS_CLUSTER>;    // bf16 operands, 128-row tiles (M = 128)
+using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER>;    // bf16 (hi, lo) rows stacked into one M = 128 operand, 64-row tiles
+using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
 
 // fp32 node scalars -> bf16 hi (and lo) planes, row-major [n][S]: what the edge kernels gather with 16-byte cp.async
 __global__ void split_planes_kernel(const float* __restrict__ s0, int n0, const float* __restrict__ s1, int n1, int S,
@@ -554,7 +661,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
     const GvpEtypeArgs& a = L.e[blockIdx.y];
     const int E = a.rowptr[a.n_dst];
     const int tile_begin = blockIdx.x * C::R;
-    if (tile_begin >= E) return;
+    if ((int)(blockIdx.x / C::CL) * C::CL * C::R >= E) return;      // the whole cluster is past the last edge
+    const bool dead = tile_begin >= E;                              // this CTA only helps to stream the weights
     const int n = min(C::R, E - tile_begin);
     extern __shared__ __align__(128) unsigned char smem_ws[];
     TC_T(e0);
@@ -563,10 +671,10 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = L.Sdim, Vd = L.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) ws::issue<C>(a.msg, L.n_msg, m, tmem);
+        if (lane == 0) { if (dead) ws::drain<C>(a.msg, L.n_msg, m); else ws::issue<C>(a.msg, L.n_msg, m, tmem); }
     } else if (warp == C::NW + 1) {
-        if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m);
-    } else {
+        if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m, dead);
+    } else if (!dead) {
         TC_T(e1);
         if (tid < C::R) {
             const int e = tile_begin + min(tid, n - 1);
@@ -582,7 +690,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             const int items = C::R * (Sd >> 3);
             for (int idx = tid; idx < items; idx += C::NT_SIMT) {
                 const int r = idx % C::R, kc = idx / C::R;
-                const uint32_t off = (uint32_t)(kc * C::KCS + (r >> 3) * 128 + (r & 7) * 16);
+                const uint32_t off = (uint32_t)(kc * C::KCS) + ws::row_off<C>(r);
                 const size_t g = (size_t)m.src_s[r] * Sd + 8 * kc;
                 cp_async16(m.A[0] + off, a.s_hi + g);
                 if (C::NS == 2) cp_async16(m.A[1] + off, a.s_lo + g);
@@ -590,7 +698,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             cp_async_commit();
         }
         // geometry + v_src -> registers (gvp.py:474-480)
-        const ws::Lane Ln = ws::lane_geometry();
+        const ws::Lane Ln = ws::lane_geometry<C>();
         float v[VMAX];
         {
             const int s = m.src_s[Ln.row], d = m.dst_s[Ln.row];
@@ -639,7 +747,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
                     float s0 = 0.f, s1 = 0.f;
                     if (scal) {
                         for (int j = ra; j < rb; ++j) {
-                            const uint32_t ro = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                            const uint32_t ro = ws::row_off<C>(j);
                             const uint32_t wv = *reinterpret_cast<const uint32_t*>(p0 + ro);
                             float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
                             if (C::NS == 2) {
@@ -733,7 +841,7 @@ __device__ __forceinline__ float vec_norm(const float (&v)[VMAX], int nv, const 
 // 8 consecutive feats of one row read back from the bf16 plane(s)
 template <class C>
 __device__ __forceinline__ void get_chunk(const Sm& m, int row, int kc, float (&f)[8]) {
-    const uint32_t off = (uint32_t)(kc * C::KCS + (row >> 3) * 128 + (row & 7) * 16);
+    const uint32_t off = (uint32_t)(kc * C::KCS) + row_off<C>(row);
     const uint4 hi = *reinterpret_cast<const uint4*>(m.A[0] + off);
     f[0] = __uint_as_float(hi.x << 16); f[1] = __uint_as_float(hi.x & 0xffff0000u);
     f[2] = __uint_as_float(hi.y << 16); f[3] = __uint_as_float(hi.y & 0xffff0000u);
@@ -773,7 +881,8 @@ template <class C>
 __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_constant__ GvpNodeLaunch L) {
     const GvpNodeArgs& a = L.nt[blockIdx.y];
     const int n0 = blockIdx.x * NODE_ROWS;
-    if (n0 >= a.n) return;
+    if ((int)(blockIdx.x / C::CL) * C::CL * NODE_ROWS >= a.n) return;
+    const bool dead = n0 >= a.n;
     const int n = min(NODE_ROWS, a.n - n0);
     constexpr int RPW = NODE_ROWS / C::NW;     // rows per warp in the scalar phases (row = warp + NW * j)
     extern __shared__ __align__(128) unsigned char smem_ws[];
@@ -783,11 +892,11 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) ws::issue<C>(a.upd, a.n_upd, m, tmem);
+        if (lane == 0) { if (dead) ws::drain<C>(a.upd, a.n_upd, m); else ws::issue<C>(a.upd, a.n_upd, m, tmem); }
     } else if (warp == C::NW + 1) {
-        if (lane == 0) ws::produce<C>(a.upd, a.n_upd, m);
-    } else {
-        const ws::Lane Ln = ws::lane_geometry();
+        if (lane == 0) ws::produce<C>(a.upd, a.n_upd, m, dead);
+    } else if (!dead) {
+        const ws::Lane Ln = ws::lane_geometry<C>();
         const bool act = 8 * lane < Sd;
         // ---- phase 0: per-row metadata -> shared memory (one round trip for the whole tile)
         int* meta = m.src_s;                                   // [R][4]: r0, r1 of both edge types
@@ -979,7 +1088,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_constant__ GvpHeadArgs a) {
     const int n0 = blockIdx.x * NODE_ROWS;
-    if (n0 >= a.n) return;
+    if ((int)(blockIdx.x / C::CL) * C::CL * NODE_ROWS >= a.n) return;
+    const bool dead = n0 >= a.n;
     const int n = min(NODE_ROWS, a.n - n0);
     extern __shared__ __align__(128) unsigned char smem_ws[];
     ws::Sm m = ws::carve<C>(smem_ws, a.kch);
@@ -987,16 +1097,16 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) ws::issue<C>(a.g, a.n_gvps, m, tmem);
+        if (lane == 0) { if (dead) ws::drain<C>(a.g, a.n_gvps, m); else ws::issue<C>(a.g, a.n_gvps, m, tmem); }
     } else if (warp == C::NW + 1) {
-        if (lane == 0) ws::produce<C>(a.g, a.n_gvps, m);
-    } else {
-        const ws::Lane Ln = ws::lane_geometry();
+        if (lane == 0) ws::produce<C>(a.g, a.n_gvps, m, dead);
+    } else if (!dead) {
+        const ws::Lane Ln = ws::lane_geometry<C>();
         {
             const int items = NODE_ROWS * (Sd >> 3);
             for (int idx = tid; idx < items; idx += C::NT_SIMT) {
                 const int r = idx % NODE_ROWS, kc = idx / NODE_ROWS;
-                const uint32_t off = (uint32_t)(kc * C::KCS + (r >> 3) * 128 + (r & 7) * 16);
+                const uint32_t off = (uint32_t)(kc * C::KCS) + ws::row_off<C>(r);
                 const size_t g = (size_t)(n0 + min(r, n - 1)) * Sd + 8 * kc;
                 cp_async16(m.A[0] + off, a.s_hi + g);
                 if (C::NS == 2) cp_async16(m.A[1] + off, a.s_lo + g);
