@@ -43,6 +43,7 @@ struct GvpW {
     const uint4* WfP2;  // bf16x3 mode: the same two weights as interleaved (hi, lo) k-step slabs
     const uint4* WgP2;
     int vin, vout, hd, fin, fout, ldf, sigmoid_gate;
+    int xfirst;         // input vector channel 0 is the edge's unit x_diff (message GVP 0)
 };
 
 // GVP.forward (models/gvp.py:89-116) on a shared-memory tile of TE rows.
@@ -466,6 +467,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         g.ldf = (fout + 3) & ~3; g.sigmoid_gate = sig;
         g.Wh = P(); g.Wu = P(); g.WfT = P(); g.bf = P(); g.WgT = P(); g.bg = P();
         g.WfP = nullptr; g.WgP = nullptr; g.WfP2 = nullptr; g.WgP2 = nullptr;
+        g.xfirst = vin > vout && sig ? 1 : 0;
         return g;
     };
     int expect = 8 + cfg->n_noise_gvps * 6 + 2;

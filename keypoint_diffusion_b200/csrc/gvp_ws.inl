@@ -36,9 +36,14 @@ __device__ int g_ws_trace_n;
 
 namespace ws {
 
-constexpr int WH_LD = 20;                                   // Wh staged as [17][20] (zero padded)
-constexpr int WSM = VMAX * WH_LD + VMAX * 16 + 256 + 16;    // floats per GVP: Wh | Wu [17][16] | bf | bg
+// small fp32 weights of one GVP in shared memory, laid out as mma.sync B fragments (see vector MMAs below):
+//   Wh pairs [12][WH_LD][2]: (our channel 2p, 2p+1; h)   Wu pairs [12][WU_LD][2]: (h = 2p, 2p+1; u)
+// leading dimensions == 4 (mod 16) in 8-byte units make the 64-bit fragment loads conflict-free
+constexpr int WH_LD = 36, WU_LD = 20;
+constexpr int WH_SZ = 12 * WH_LD * 2, WU_SZ = 12 * WU_LD * 2;
+template <int NS> constexpr int wsm_floats() { return NS * (WH_SZ + WU_SZ) + 256 + 16; }   // (hi[, lo]) Wh | Wu | bf | bg
 constexpr int VS_LD = 52;                                   // fp32 vector staging row (48 used)
+constexpr int GATE_LD = 20;                                 // gates staged as [R][20]
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t GATE_COL = 256;
 
@@ -54,6 +59,8 @@ struct Cfg {
     static constexpr int STAGES = NS == 1 ? 8 : 4;
     static constexpr int SLAB = NS * 8192;           // one ring stage: one k-step of a 256-row weight (hi [, lo])
     static constexpr int WG_BYTES = NS * 8192;       // gates weight: 16 k-steps x 512 B (hi [, lo])
+    static constexpr int WGB = NS == 1 ? 2 : 1;      // gates weight buffers
+    static constexpr int WSM = wsm_floats<NS>();
     static constexpr int NCG = NW / 4;               // column groups of the epilogues (4 TMEM lane quarters x NCG)
 };
 
@@ -62,7 +69,7 @@ struct Sm {
     unsigned char* ring;
     unsigned char* Wg[2];
     float* wsm;
-    float* gate;      // [16][R]
+    float* gate;      // [R][GATE_LD]
     int *src_s, *dst_s, *seg, *rp;
     uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done;
     uint32_t* tmem_slot;
@@ -85,8 +92,8 @@ __device__ __forceinline__ uint32_t row_off(int r) {
 
 template <class C>
 static size_t smem_bytes(int kch) {
-    return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + 2 * C::WG_BYTES + sizeof(float) * MAXG * WSM +
-           sizeof(float) * 16 * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 8) + 16 + 128;
+    return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * MAXG * C::WSM +
+           sizeof(float) * GATE_LD * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 8) + 16 + 128;
 }
 
 template <class C>
@@ -97,9 +104,9 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.ring = smem + plane_bytes<C>(kch);
     m.Wg[0] = m.ring + C::STAGES * C::SLAB;
     m.Wg[1] = m.Wg[0] + C::WG_BYTES;
-    m.wsm = reinterpret_cast<float*>(m.Wg[1] + C::WG_BYTES);
-    m.gate = m.wsm + MAXG * WSM;
-    m.src_s = reinterpret_cast<int*>(m.gate + 16 * C::R);
+    m.wsm = reinterpret_cast<float*>(m.Wg[0] + C::WGB * C::WG_BYTES);
+    m.gate = m.wsm + MAXG * C::WSM;
+    m.src_s = reinterpret_cast<int*>(m.gate + GATE_LD * C::R);
     m.dst_s = m.src_s + C::R;
     m.seg = m.dst_s + C::R;            // [R + 8]
     m.rp = m.seg + C::R + 8;           // [2R]
@@ -119,6 +126,20 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
 template <class C>
 __device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(C::NT_SIMT) : "memory"); }
 
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// warp-level tensor-core MMA, D(16x8) += A(16x8) B(8x8), tf32 operands, fp32 accumulation
+__device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float& d3, float a0, float a1, float a2, float a3,
+                                         float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                 : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
 // barriers + TMEM + zeroed A planes + the small fp32 weights of the chain; ends with a __syncthreads()
 template <class C>
 __device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_gvps) {
@@ -136,22 +157,34 @@ __device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     const int nz = (int)(plane_bytes<C>(kch) / 16);
     for (int i = tid; i < nz; i += C::NT) reinterpret_cast<uint4*>(m.A[0])[i] = z;
-    for (int idx = tid; idx < n_gvps * WSM; idx += C::NT) {
-        const int gi = idx / WSM, o = idx - gi * WSM;
+    for (int idx = tid; idx < n_gvps * C::WSM; idx += C::NT) {
+        const int gi = idx / C::WSM;
+        int o = idx - gi * C::WSM;
         const GvpW& g = gv[gi];
         float val = 0.f;
-        if (o < VMAX * WH_LD) {
-            const int k = o / WH_LD, hh = o - k * WH_LD;
-            if (k < g.vin && hh < g.hd) val = g.Wh[k * g.hd + hh];
-        } else if (o < VMAX * WH_LD + VMAX * 16) {
-            const int q = o - VMAX * WH_LD, h = q >> 4, u = q & 15;
+        bool lo = false, wt = false;
+        if (o < C::NS * WH_SZ) {             // Wh: our input channel k (x_diff last for message GVP 0) x h
+            wt = true;
+            if (o >= WH_SZ) { lo = true; o -= WH_SZ; }
+            const int pr = o / (WH_LD * 2), rem = o - pr * (WH_LD * 2), h = rem >> 1, k = 2 * pr + (rem & 1);
+            const int rk = g.xfirst ? (k == g.vin - 1 ? 0 : k + 1) : k;       // reference row of our channel k
+            if (k < g.vin && h < g.hd) val = g.Wh[rk * g.hd + h];
+        } else if (o < C::NS * (WH_SZ + WU_SZ)) {
+            wt = true;
+            o -= C::NS * WH_SZ;
+            if (o >= WU_SZ) { lo = true; o -= WU_SZ; }
+            const int pr = o / (WU_LD * 2), rem = o - pr * (WU_LD * 2), u = rem >> 1, h = 2 * pr + (rem & 1);
             if (h < g.hd && u < g.vout) val = g.Wu[h * g.vout + u];
-        } else if (o < VMAX * WH_LD + VMAX * 16 + 256) {
-            const int f = o - (VMAX * WH_LD + VMAX * 16);
+        } else if (o < C::NS * (WH_SZ + WU_SZ) + 256) {
+            const int f = o - C::NS * (WH_SZ + WU_SZ);
             if (f < g.fout) val = g.bf[f];
         } else {
-            const int u = o - (VMAX * WH_LD + VMAX * 16 + 256);
+            const int u = o - (C::NS * (WH_SZ + WU_SZ) + 256);
             if (u < g.vout) val = g.bg[u];
+        }
+        if (wt) {                             // tf32 operands of the vector MMAs: hi = rna(w), lo = rna(w - hi)
+            const float hi = tf32_rna(val);
+            val = lo ? tf32_rna(val - hi) : hi;
         }
         m.wsm[idx] = val;
     }
@@ -184,13 +217,8 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
         const GvpW& w = gv[g];
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksg = NBf >> 4;
         const uint32_t slab = C::NS * 2 * (NBf / 8) * 128;
-        const int b = g & 1;
+        const int b = g % C::WGB;
         const uint4* WfP = C::NS == 2 ? w.WfP2 : w.WfP;
-        if (!dead) {
-            if (g >= 2) tc::mbar_wait(&m.wg_empty[b], ((g >> 1) - 1) & 1);      // gates MMA g-2 has consumed this buffer
-            tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
-            tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
-        }
         for (int j = 0; j < ksf; ++j, ++it) {
             const uint32_t st = it % C::STAGES;
             if (it >= (uint32_t)C::STAGES) tc::mbar_wait(&m.empty[st], ((it / C::STAGES) - 1) & 1);
@@ -208,6 +236,12 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
 #ifdef KPD_WS_TRACE
             if (it < 64) tp[it] = clock64();
 #endif
+        }
+        // the gates weight is needed only after this GVP's feats GEMM: queue it behind the slabs
+        if (!dead) {
+            if (g >= C::WGB) tc::mbar_wait(&m.wg_empty[b], ((g / C::WGB) - 1) & 1);   // gates MMA g-WGB has consumed the buffer
+            tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
+            tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
         }
     }
 #ifdef KPD_WS_TRACE
@@ -260,10 +294,10 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         tc::mbar_wait(m.feats_ready, (g + 1) & 1);
         tc::fence_after_sync();
         WS_TRACE(5);
-        tc::mbar_wait(&m.wg_full[g & 1], (g >> 1) & 1);
+        tc::mbar_wait(&m.wg_full[g % C::WGB], (g / C::WGB) & 1);
         tc::fence_after_sync();
         const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
-        const uint32_t wg = tc::smem_u32(m.Wg[0] + (g & 1) * C::WG_BYTES);
+        const uint32_t wg = tc::smem_u32(m.Wg[0] + (g % C::WGB) * C::WG_BYTES);
         for (int j = 0; j < ksg; ++j) {
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
@@ -274,7 +308,7 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
             }
         }
         tc::mma_commit(m.gates_done);
-        tc::mma_commit(&m.wg_empty[g & 1]);
+        tc::mma_commit(&m.wg_empty[g % C::WGB]);
         WS_TRACE(6);
     }
 #ifdef KPD_WS_TRACE
@@ -362,30 +396,97 @@ __device__ __forceinline__ void publish(uint64_t* bar) {
     if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
 }
 
-// lane geometry of the register-resident vectors
+// Register-resident vectors.  The 8 tile rows of a SIMT warp x 3 components form the 24 (of 32) rows of two
+// m16n8k8 MMA tiles, ordered component-major: tile 0 rows 0-7 = x, rows 8-15 = y; tile 1 rows 0-7 = z.  Lane
+// (g = lane / 4, t = lane % 4) therefore holds, for tile row 8 * warp + g and ALL THREE components, the vector
+// channels 8 s + 2 t + e (s = k-step / n-tile, e = 0, 1): exactly the accumulator fragment of one GEMM and, with the
+// K index permuted the same way in the staged weights, the A fragment of the next (no shuffles, no shared memory).
+struct VF { float x[3][3][2]; };     // [component][s][e]
 struct Lane {
-    int row;     // tile row owned by this lane
-    int c;       // xyz component
-    int bl;      // first lane of this row's triple
-    bool own;    // false for the 8 spare lanes (they mirror row 7 of the warp and never store)
+    int row;           // tile row of this lane
+    int t;             // lane % 4
     uint32_t rowoff;   // byte offset of the row inside a k-chunk of A
 };
 template <class C>
 __device__ __forceinline__ Lane lane_geometry() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Lane L;
-    const int rr = lane < 24 ? lane / 3 : 7;
-    L.c = lane < 24 ? lane - 3 * rr : (lane - 24) % 3;
-    L.row = 8 * warp + rr;
-    L.bl = 3 * rr;
-    L.own = lane < 24;
+    L.row = 8 * warp + (lane >> 2);
+    L.t = lane & 3;
     L.rowoff = row_off<C>(L.row);
     return L;
 }
-__device__ __forceinline__ float sum3(float x, const Lane& L) {
-    const float t1 = __shfl_sync(0xffffffffu, x, L.bl + (L.c + 1) % 3);
-    const float t2 = __shfl_sync(0xffffffffu, x, L.bl + (L.c + 2) % 3);
-    return x + t1 + t2;
+__device__ __forceinline__ void vf_zero(VF& v) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) v.x[c][s][0] = v.x[c][s][1] = 0.f;
+}
+// channels of this lane from / to a [nv][3] row in global or shared memory (channels >= nv read as 0)
+__device__ __forceinline__ void vf_load(VF& v, const float* __restrict__ p, int nv, int t) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int u = 8 * s + 2 * t + e;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v.x[c][s][e] = u < nv ? p[3 * u + c] : 0.f;
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.x[c][2][0] = v.x[c][2][1] = 0.f;
+}
+__device__ __forceinline__ void vf_store(const VF& v, float* p, int nv, int t) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int u = 8 * s + 2 * t + e;
+            if (u < nv) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p[3 * u + c] = v.x[c][s][e];
+            }
+        }
+}
+// D[c][j][e] += sum_k A[c][k-step][.] W[k][8 j + 2 t + e]: one GEMM of the vector path on the warp-level tensor cores.
+// W: staged B fragments (hi at W, lo at W + lo_off for the 3xTF32 mode); nks k-steps, NT n-tiles (the last only if nt3).
+template <int NS, int LD, int NT>
+__device__ __forceinline__ void vec_gemm(const float (&A)[3][3][2], float (&D)[3][NT][2], const float* __restrict__ W, int lo_off,
+                                         int nks, bool nt_last, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) D[c][j][0] = D[c][j][1] = 0.f;
+    float junk0 = 0.f, junk1 = 0.f;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        if (s < nks) {
+            float ah[3][2], al[3][2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (NS == 2) { ah[c][e] = tf32_rna(A[c][s][e]); al[c][e] = tf32_rna(A[c][s][e] - ah[c][e]); }
+                    else ah[c][e] = A[c][s][e];          // plain tf32: the tensor core ignores the low mantissa bits
+                }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                if (j + 1 < NT || nt_last) {
+                    const float2 b = *reinterpret_cast<const float2*>(W + ((4 * s + t) * LD + 8 * j + g) * 2);
+                    // tile 0: rows 0-7 = component 0, rows 8-15 = component 1; tile 1: rows 0-7 = component 2
+                    mma_tf32(D[0][j][0], D[0][j][1], D[1][j][0], D[1][j][1], ah[0][0], ah[1][0], ah[0][1], ah[1][1], b.x, b.y);
+                    mma_tf32(D[2][j][0], D[2][j][1], junk0, junk1, ah[2][0], 0.f, ah[2][1], 0.f, b.x, b.y);
+                    if (NS == 2) {
+                        const float2 bl = *reinterpret_cast<const float2*>(W + lo_off + ((4 * s + t) * LD + 8 * j + g) * 2);
+                        mma_tf32(D[0][j][0], D[0][j][1], D[1][j][0], D[1][j][1], al[0][0], al[1][0], al[0][1], al[1][1], b.x, b.y);
+                        mma_tf32(D[2][j][0], D[2][j][1], junk0, junk1, al[2][0], 0.f, al[2][1], 0.f, b.x, b.y);
+                        mma_tf32(D[0][j][0], D[0][j][1], D[1][j][0], D[1][j][1], ah[0][0], ah[1][0], ah[0][1], ah[1][1], bl.x, bl.y);
+                        mma_tf32(D[2][j][0], D[2][j][1], junk0, junk1, ah[2][0], 0.f, ah[2][1], 0.f, bl.x, bl.y);
+                    }
+                }
+            }
+        }
+    }
 }
 
 // one 32-column chunk of epilogue 1: bias + SiLU -> bf16 plane(s) of A (static register indexing only)
@@ -448,69 +549,41 @@ __device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[32], int c0, int
 // In: v[0..vin) (registers), feats in A[:, 0:fin) already published.  Out: v[0..vout), feats_out in A[:, 0:fout)
 // published through feats_ready.
 template <class C>
-__device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uint32_t tmem, float (&v)[VMAX], const Lane& L,
+__device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uint32_t tmem, VF& v, const Lane& L,
                                          int rows_valid, int tb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* Wh_s = m.wsm + gi * WSM;
-    const float* Wu_s = Wh_s + VMAX * WH_LD;
-    const float* bf_s = Wu_s + VMAX * 16;
+    const float* Wh_s = m.wsm + gi * C::WSM;
+    const float* Wu_s = Wh_s + C::NS * WH_SZ;
+    const float* bf_s = Wu_s + C::NS * WU_SZ;
     const float* bg_s = bf_s + 256;
     const int NBf = (g.fout + 15) & ~15;
-    // a. Vh = V^T Wh (gvp.py:96); sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
+    // a. Vh = V^T Wh (gvp.py:96) on the warp-level tensor cores; sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
     TC_T(t0);
     WS_TRACE(10);
-    float vh[VMAX];
+    float vh[3][3][2];
+    vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
 #pragma unroll
-    for (int h = 0; h < VMAX; ++h) vh[h] = 0.f;
-#pragma unroll
-    for (int k = 0; k < VMAX; ++k) {
-        const float4* w4 = reinterpret_cast<const float4*>(Wh_s + k * WH_LD);
-        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-        const float w16 = Wh_s[k * WH_LD + 16];
-        const float x = v[k];
-        vh[0] = fmaf(x, w0.x, vh[0]); vh[1] = fmaf(x, w0.y, vh[1]); vh[2] = fmaf(x, w0.z, vh[2]); vh[3] = fmaf(x, w0.w, vh[3]);
-        vh[4] = fmaf(x, w1.x, vh[4]); vh[5] = fmaf(x, w1.y, vh[5]); vh[6] = fmaf(x, w1.z, vh[6]); vh[7] = fmaf(x, w1.w, vh[7]);
-        vh[8] = fmaf(x, w2.x, vh[8]); vh[9] = fmaf(x, w2.y, vh[9]); vh[10] = fmaf(x, w2.z, vh[10]); vh[11] = fmaf(x, w2.w, vh[11]);
-        vh[12] = fmaf(x, w3.x, vh[12]); vh[13] = fmaf(x, w3.y, vh[13]); vh[14] = fmaf(x, w3.z, vh[14]); vh[15] = fmaf(x, w3.w, vh[15]);
-        vh[16] = fmaf(x, w16, vh[16]);
-    }
-    {
-        float sq[18];
-#pragma unroll
-        for (int h = 0; h < VMAX; ++h) sq[h] = sum3(vh[h] * vh[h], L);
-        sq[17] = 0.f;
-        // lane c of the row's triple stores h = c, c + 3, ...  (sqrt.approx: 2^-23 relative, far inside both modes' bars)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const int h = 3 * j + L.c;
-            const float val = L.c == 0 ? sq[3 * j] : (L.c == 1 ? sq[3 * j + 1] : sq[3 * j + 2]);
-            if (L.own && h < g.hd) {
-                const int col = g.fin + h;
-                const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (col & 7) * 2) + L.rowoff;
-                const float x = sqrt_fast(fmaxf(val, 1e-8f));
-                const __nv_bfloat16 hi = __float2bfloat16(x);
-                *reinterpret_cast<__nv_bfloat16*>(m.A[0] + off) = hi;
-                if (C::NS == 2) *reinterpret_cast<__nv_bfloat16*>(m.A[1] + off) = __float2bfloat16(x - __bfloat162float(hi));
-            }
+    for (int j = 0; j < 3; ++j) {
+        const int h = 8 * j + 2 * L.t;
+        if (h < g.hd) {       // both columns of the pair are written; a column >= hd meets zero weight rows
+            const float s0 = vh[0][j][0] * vh[0][j][0] + vh[1][j][0] * vh[1][j][0] + vh[2][j][0] * vh[2][j][0];
+            const float s1 = vh[0][j][1] * vh[0][j][1] + vh[1][j][1] * vh[1][j][1] + vh[2][j][1] * vh[2][j][1];
+            const float x0 = sqrt_fast(fmaxf(s0, 1e-8f)), x1 = sqrt_fast(fmaxf(s1, 1e-8f));
+            const int col = g.fin + h;
+            const uint32_t off = (uint32_t)((col >> 3) * C::KCS + (col & 7) * 2) + L.rowoff;
+            const uint32_t hi = tc::pack_bf16x2(x0, x1);
+            *reinterpret_cast<uint32_t*>(m.A[0] + off) = hi;
+            if (C::NS == 2)
+                *reinterpret_cast<uint32_t*>(m.A[1] + off) =
+                    tc::pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
         }
     }
     publish(m.tail_ready);
     TC_T(t1);
     WS_TRACE(11);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
-    float vu[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) vu[u] = 0.f;
-#pragma unroll
-    for (int h = 0; h < VMAX; ++h) {
-        const float4* w4 = reinterpret_cast<const float4*>(Wu_s + h * 16);
-        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-        const float x = vh[h];
-        vu[0] = fmaf(x, w0.x, vu[0]); vu[1] = fmaf(x, w0.y, vu[1]); vu[2] = fmaf(x, w0.z, vu[2]); vu[3] = fmaf(x, w0.w, vu[3]);
-        vu[4] = fmaf(x, w1.x, vu[4]); vu[5] = fmaf(x, w1.y, vu[5]); vu[6] = fmaf(x, w1.z, vu[6]); vu[7] = fmaf(x, w1.w, vu[7]);
-        vu[8] = fmaf(x, w2.x, vu[8]); vu[9] = fmaf(x, w2.y, vu[9]); vu[10] = fmaf(x, w2.z, vu[10]); vu[11] = fmaf(x, w2.w, vu[11]);
-        vu[12] = fmaf(x, w3.x, vu[12]); vu[13] = fmaf(x, w3.y, vu[13]); vu[14] = fmaf(x, w3.z, vu[14]); vu[15] = fmaf(x, w3.w, vu[15]);
-    }
+    float vu[3][2][2];
+    vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
     // c. epilogue 1: feats_out = SiLU(acc + b) -> A[:, 0:fout)   (gvp.py:101-103)
     const int q = warp & 3, cg = warp >> 2;
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
@@ -581,13 +654,18 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
             if (C::NS == 2) a += __shfl_xor_sync(0xffffffffu, a, 16);     // hi rows (lanes 0-15) + lo rows (lanes 16-31)
             a += bg_s[u];
             if (g.sigmoid_gate) a = act_sigmoid<C::NS>(a);
-            if (valid_e) m.gate[u * C::R + row_e] = a;
+            if (valid_e) m.gate[row_e * GATE_LD + u] = a;
         }
     }
     simt_bar<C>();
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = vu[u] * m.gate[u * C::R + L.row];
-    v[16] = 0.f;
+    for (int j = 0; j < 2; ++j) {
+        const float2 gt = *reinterpret_cast<const float2*>(m.gate + L.row * GATE_LD + 8 * j + 2 * L.t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * gt.x; v.x[c][j][1] = vu[c][j][1] * gt.y; }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.x[c][2][0] = v.x[c][2][1] = 0.f;
     TC_T(t6);
     WS_TRACE(16);
     WS_ACC(tb + 0, t0, t1); WS_ACC(tb + 1, t1, t2); WS_ACC(tb + 2, t2, t3); WS_ACC(tb + 3, t3, t4); WS_ACC(tb + 4, t4, t5);
@@ -699,20 +777,26 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         }
         // geometry + v_src -> registers (gvp.py:474-480)
         const ws::Lane Ln = ws::lane_geometry<C>();
-        float v[VMAX];
+        ws::VF v;
         {
             const int s = m.src_s[Ln.row], d = m.dst_s[Ln.row];
-            const float dxc = a.xs[3 * s + Ln.c] - a.xd[3 * d + Ln.c];
-            const float d2 = ws::sum3(dxc * dxc, Ln);
-            const float dij = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
-            v[0] = dxc / dij;
-            const float* vp = a.v_src + (size_t)s * (Vd * 3) + Ln.c;
+            const float dx = a.xs[3 * s] - a.xd[3 * d], dy = a.xs[3 * s + 1] - a.xd[3 * d + 1], dz = a.xs[3 * s + 2] - a.xd[3 * d + 2];
+            const float dij = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-8f)) + 1e-8f;
+            ws::vf_load(v, a.v_src + (size_t)s * (Vd * 3), Vd, Ln.t);
+            // the unit x_diff is the LAST input channel here (channel Vd; Wh is staged with its rows permuted to match)
+            {
+                const int sx = Vd >> 3, tx = (Vd & 7) >> 1, ex = Vd & 1;
+                if (Ln.t == tx) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[1 + k] = k < Vd ? vp[3 * k] : 0.f;
-            for (int k = Ln.c; k < L.rbf_dim; k += 3) {
+                    for (int ss = 0; ss < 3; ++ss)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            if (ss == sx && e == ex) { v.x[0][ss][e] = dx / dij; v.x[1][ss][e] = dy / dij; v.x[2][ss][e] = dz / dij; }
+                }
+            }
+            for (int k = Ln.t; k < L.rbf_dim; k += 4) {
                 const float z = (dij - (float)k * L.rbf_step) / L.rbf_sigma;
-                const float val = expf(-(z * z));
-                if (Ln.own) ws::put_scalar<C>(m, Ln.row, Sd + k, val);
+                ws::put_scalar<C>(m, Ln.row, Sd + k, expf(-(z * z)));
             }
         }
         ws::build_segments<C>(m, n);
@@ -723,10 +807,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         TC_T(e3);
         // ---- deterministic segmented reduction by destination (all MMAs and bulk copies have completed)
         float* VS = reinterpret_cast<float*>(m.ring);
-        if (Ln.own) {
-#pragma unroll
-            for (int u = 0; u < 16; ++u) if (u < Vd) VS[Ln.row * ws::VS_LD + 3 * u + Ln.c] = v[u];
-        }
+        ws::vf_store(v, VS + Ln.row * ws::VS_LD, Vd, Ln.t);
         ws::simt_bar<C>();
         {
             constexpr int GRP = 160;
@@ -828,13 +909,17 @@ __device__ __forceinline__ void warp_layernorm8(float (&x)[8], bool act, int Sdi
 
 // vector part of GVPLayerNorm (gvp.py:163-165) on the register-resident vectors of one row:
 // vn = sqrt(mean_u clamp(|v_u|^2, 1e-8) + eps) + eps
-__device__ __forceinline__ float vec_norm(const float (&v)[VMAX], int nv, const Lane& L) {
+__device__ __forceinline__ float vec_norm(const VF& v, int nv, const Lane& L) {
     float q = 0.f;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const float n2 = sum3(v[u] * v[u], L);
-        if (u < nv) q += fmaxf(n2, 1e-8f);
-    }
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float n2 = v.x[0][s][e] * v.x[0][s][e] + v.x[1][s][e] * v.x[1][s][e] + v.x[2][s][e] * v.x[2][s][e];
+            if (8 * s + 2 * L.t + e < nv) q += fmaxf(n2, 1e-8f);
+        }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);      // the four lanes of a row hold disjoint channels
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
     return sqrtf(q / (float)nv + 1e-5f) + 1e-5f;
 }
 
@@ -985,50 +1070,55 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         }
         // ---- phase 1b: vectors of lane (row, c) -> registers; residual stash in global
         TC_T(n2t);
-        float v[VMAX];
+        ws::VF v;
         {
             const int nd = n0 + min(Ln.row, n - 1);
             const float nv = nvs[Ln.row];
-#pragma unroll
-            for (int u = 0; u < VMAX; ++u) v[u] = 0.f;
+            ws::VF msg;
+            ws::vf_zero(msg);
             for (int e = 0; e < a.n_et; ++e) {
                 const int r0 = meta[4 * Ln.row + 2 * e], r1 = meta[4 * Ln.row + 2 * e + 1];
                 const float cnt = a.norm_mode == 1 ? (float)max(r1 - r0, 1) : 1.0f;
                 if (r1 > r0) {
                     const int t0 = r0 / a.edge_tile, t1 = (r1 - 1) / a.edge_tile;
-                    float g[16];
-                    if (t0 == t1) {            // the common case: one tile holds the whole CSR row -> 16 independent loads
-                        const float* p = a.vm[e] + (size_t)nd * (3 * Vd) + Ln.c;
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) g[u] = u < Vd ? __ldg(p + 3 * u) : 0.f;
+                    ws::VF gsum;
+                    if (t0 == t1) {            // the common case: one tile holds the whole CSR row
+                        ws::vf_load(gsum, a.vm[e] + (size_t)nd * (3 * Vd), Vd, Ln.t);
                     } else {
-                        const float* p = a.part[e] + ((size_t)t0 * 2 + 1) * a.pw + Sd + Ln.c;
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) g[u] = u < Vd ? p[3 * u] : 0.f;
+                        ws::vf_load(gsum, a.part[e] + ((size_t)t0 * 2 + 1) * a.pw + Sd, Vd, Ln.t);
                         for (int t = t0 + 1; t <= t1; ++t) {
-                            const float* q = a.part[e] + ((size_t)t * 2 + 0) * a.pw + Sd + Ln.c;
+                            ws::VF q;
+                            ws::vf_load(q, a.part[e] + ((size_t)t * 2 + 0) * a.pw + Sd, Vd, Ln.t);
 #pragma unroll
-                            for (int u = 0; u < 16; ++u) if (u < Vd) g[u] += q[3 * u];
+                            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                                for (int ss = 0; ss < 2; ++ss) { gsum.x[c][ss][0] += q.x[c][ss][0]; gsum.x[c][ss][1] += q.x[c][ss][1]; }
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) v[u] += a.norm_mode == 1 ? g[u] / cnt : g[u];
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+                            for (int ee = 0; ee < 2; ++ee)
+                                msg.x[c][ss][ee] += a.norm_mode == 1 ? gsum.x[c][ss][ee] / cnt : gsum.x[c][ss][ee];
                 }
             }
-            const float* vp = a.v + (size_t)nd * (3 * Vd) + Ln.c;
-            float vr[16];
+            ws::vf_load(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) vr[u] = u < Vd ? __ldg(vp + 3 * u) : 0.f;
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = vr[u] + v[u] / nv;
+                for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] += msg.x[c][ss][ee] / nv;
             const float vn = ws::vec_norm(v, Vd, Ln);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = v[u] / vn;
-            if (Ln.own && Ln.row < n) {
-                float* vo = a.v + (size_t)nd * (3 * Vd) + Ln.c;
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int u = 0; u < 16; ++u) if (u < Vd) vo[3 * u] = v[u];
-            }
+                for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] = v.x[c][ss][ee] / vn;
+            if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
         ws::publish(m.feats_ready);
         TC_T(n3t);
@@ -1068,15 +1158,22 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         }
         {
             const int nd = n0 + min(Ln.row, n - 1);
-            const float* vp = a.v + (size_t)nd * (3 * Vd) + Ln.c;
+            ws::VF res;
+            ws::vf_load(res, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = u < Vd ? v[u] + vp[3 * u] : 0.f;
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] += res.x[c][ss][ee];
             const float vn = ws::vec_norm(v, Vd, Ln);
-            if (Ln.own && Ln.row < n) {
-                float* vo = a.v + (size_t)nd * (3 * Vd) + Ln.c;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) if (u < Vd) vo[3 * u] = v[u] / vn;
-            }
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] = v.x[c][ss][ee] / vn;
+            if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
         TC_T(n5t);
         WS_ACC(24, n0t, n1t); WS_ACC(25, n1t, n2t); WS_ACC(26, n2t, n3t); WS_ACC(27, n3t, n4t); WS_ACC(28, n4t, n5t); WS_ACC(29, 0, 1);
@@ -1113,13 +1210,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
             }
             cp_async_commit();
         }
-        float v[VMAX];
-        {
-            const float* vp = a.v + (size_t)(n0 + min(Ln.row, n - 1)) * (3 * Vd) + Ln.c;
-#pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = u < Vd ? vp[3 * u] : 0.f;
-            v[16] = 0.f;
-        }
+        ws::VF v;
+        ws::vf_load(v, a.v + (size_t)(n0 + min(Ln.row, n - 1)) * (3 * Vd), Vd, Ln.t);
         cp_async_wait<0>();
         ws::publish(m.feats_ready);
         for (int i = 0; i < a.n_gvps; ++i) ws::gvp_simt<C>(a.g[i], i, m, tmem, v, Ln, n, 32);
@@ -1130,7 +1222,10 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
             for (int k = 0; k < a.hid_out; ++k) s = fmaf(ws::get_scalar<C>(m, r, k), a.WoT[k * a.Fp + c], s);
             a.eps_h[(size_t)(n0 + r) * a.F + c] = s;
         }
-        if (Ln.own && Ln.row < n) a.eps_x[(size_t)(n0 + Ln.row) * 3 + Ln.c] = v[0];
+        if (Ln.t == 0 && Ln.row < n) {
+            float* ex = a.eps_x + (size_t)(n0 + Ln.row) * 3;
+            ex[0] = v.x[0][0][0]; ex[1] = v.x[1][0][0]; ex[2] = v.x[2][0][0];
+        }
     }
     ws::teardown<C>(tmem);
 }
