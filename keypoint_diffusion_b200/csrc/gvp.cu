@@ -42,6 +42,8 @@ struct GvpW {
     const uint4* WgP;   // bf16 mode: gates weight, rows padded to 16
     const uint4* WfP2;  // bf16x3 mode: the same two weights as interleaved (hi, lo) k-step slabs
     const uint4* WgP2;
+    const float* wsmP;  // tensor-core modes: shared-memory image of Wh, Wu, bf, bg (pack.pack_gvp_small)
+    const float* wsmP2;
     int vin, vout, hd, fin, fout, ldf, sigmoid_gate;
     int xfirst;         // input vector channel 0 is the edge's unit x_diff (message GVP 0)
 };
@@ -178,7 +180,7 @@ constexpr int RM_NODE = 2;         // 32-node tiles: node counts are small, more
 constexpr int TN = 16 * RM_NODE;
 
 struct GvpEtypeArgs {
-    const int* rowptr; const int* src; const int* dst; int n_dst;
+    const int* rowptr; const int* src; const int* dst; int n_dst; int cap;
     const float* s_src; const float* v_src; const float* xs; const float* xd;
     const __nv_bfloat16* s_hi; const __nv_bfloat16* s_lo;   // tensor-core modes: bf16 planes of s_src
     GvpW msg[MAXG];
@@ -466,7 +468,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         g.vin = vin; g.vout = vout; g.hd = vin > vout ? vin : vout; g.fin = fin; g.fout = fout;
         g.ldf = (fout + 3) & ~3; g.sigmoid_gate = sig;
         g.Wh = P(); g.Wu = P(); g.WfT = P(); g.bf = P(); g.WgT = P(); g.bg = P();
-        g.WfP = nullptr; g.WgP = nullptr; g.WfP2 = nullptr; g.WgP2 = nullptr;
+        g.WfP = nullptr; g.WgP = nullptr; g.WfP2 = nullptr; g.WgP2 = nullptr; g.wsmP = nullptr; g.wsmP2 = nullptr;
         g.xfirst = vin > vout && sig ? 1 : 0;
         return g;
     };
@@ -538,18 +540,21 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
                                  int32_t nsplit) {
     KPD_REQUIRE(m && tc_blob && byte_offsets, "kpd_gvp_attach_tc: null argument");
     KPD_REQUIRE(nsplit == 1 || nsplit == 2, "kpd_gvp_attach_tc: nsplit must be 1 (bf16) or 2 (bf16 hi/lo)");
-    KPD_REQUIRE(n == 2 * (int)m->all_gvps.size(), "kpd_gvp_attach_tc: expected %d offsets, got %d", 2 * (int)m->all_gvps.size(), n);
+    KPD_REQUIRE(n == 3 * (int)m->all_gvps.size(), "kpd_gvp_attach_tc: expected %d offsets, got %d", 3 * (int)m->all_gvps.size(), n);
     KPD_REQUIRE((reinterpret_cast<uintptr_t>(tc_blob) & 127) == 0, "kpd_gvp_attach_tc: blob must be 128-byte aligned");
     KPD_REQUIRE(m->S % 16 == 0, "kpd_gvp_attach_tc: n_hidden_scalars must be a multiple of 16 for the tensor-core mode");
     KPD_REQUIRE(m->smem_tc <= 227 * 1024 && m->smem_ws1 <= 227 * 1024 && m->smem_ws2 <= 227 * 1024,
                 "kpd_gvp_attach_tc: tile needs %zu / %zu / %zu B of shared memory", m->smem_tc, m->smem_ws1, m->smem_ws2);
     const char* base = static_cast<const char*>(tc_blob);
     for (size_t i = 0; i < m->all_gvps.size(); ++i) {
-        KPD_REQUIRE(byte_offsets[2 * i] % 16 == 0 && byte_offsets[2 * i + 1] % 16 == 0, "kpd_gvp_attach_tc: unaligned offset");
-        const uint4* wf = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i]);
-        const uint4* wg = reinterpret_cast<const uint4*>(base + byte_offsets[2 * i + 1]);
-        if (nsplit == 1) { m->all_gvps[i]->WfP = wf; m->all_gvps[i]->WgP = wg; }
-        else { m->all_gvps[i]->WfP2 = wf; m->all_gvps[i]->WgP2 = wg; }
+        KPD_REQUIRE(byte_offsets[3 * i] % 16 == 0 && byte_offsets[3 * i + 1] % 16 == 0 && byte_offsets[3 * i + 2] % 16 == 0,
+                    "kpd_gvp_attach_tc: unaligned offset");
+        KPD_REQUIRE(m->all_gvps[i]->fout % 8 == 0, "kpd_gvp_attach_tc: GVP output widths must be multiples of 8");
+        const uint4* wf = reinterpret_cast<const uint4*>(base + byte_offsets[3 * i]);
+        const uint4* wg = reinterpret_cast<const uint4*>(base + byte_offsets[3 * i + 1]);
+        const float* ws_img = reinterpret_cast<const float*>(base + byte_offsets[3 * i + 2]);
+        if (nsplit == 1) { m->all_gvps[i]->WfP = wf; m->all_gvps[i]->WgP = wg; m->all_gvps[i]->wsmP = ws_img; }
+        else { m->all_gvps[i]->WfP2 = wf; m->all_gvps[i]->WgP2 = wg; m->all_gvps[i]->wsmP2 = ws_img; }
     }
     if (nsplit == 2) {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
@@ -690,7 +695,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         int max_tiles = 1;
         for (int e = 0; e < W.n_et; ++e) {
             GvpEtypeArgs& a = L.e[e];
-            a.rowptr = G[e]->rowptr; a.src = G[e]->src; a.dst = G[e]->dst; a.n_dst = G[e]->n_dst;
+            a.rowptr = G[e]->rowptr; a.src = G[e]->src; a.dst = G[e]->dst; a.n_dst = G[e]->n_dst; a.cap = caps[e] > 0 ? caps[e] : 1;
             a.s_src = w.s[src_nt[e]]; a.v_src = w.v[src_nt[e]];
             a.s_hi = w.s_hi[src_nt[e]]; a.s_lo = w.s_lo[src_nt[e]];
             a.xs = X[src_nt[e]]; a.xd = X[dst_nt[e]];

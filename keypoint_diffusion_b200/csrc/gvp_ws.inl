@@ -71,7 +71,7 @@ struct Sm {
     float* wsm;
     float* gate;      // [R][GATE_LD]
     int *src_s, *dst_s, *seg, *rp;
-    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done;
+    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full;
     uint32_t* tmem_slot;
     int* warp_cnt;
 };
@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t row_off(int r) {
 template <class C>
 static size_t smem_bytes(int kch) {
     return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * MAXG * C::WSM +
-           sizeof(float) * GATE_LD * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 8) + 16 + 128;
+           sizeof(float) * GATE_LD * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 9) + 16 + 128;
 }
 
 template <class C>
@@ -119,7 +119,8 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.tail_ready = m.feats_ready + 1;
     m.acc_done = m.tail_ready + 1;
     m.gates_done = m.acc_done + 1;
-    m.tmem_slot = reinterpret_cast<uint32_t*>(m.gates_done + 1);
+    m.wsm_full = m.gates_done + 1;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.wsm_full + 1);
     return m;
 }
 
@@ -140,58 +141,55 @@ __device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float&
                    "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
-// barriers + TMEM + zeroed A planes + the small fp32 weights of the chain; ends with a __syncthreads()
 template <class C>
-__device__ __forceinline__ uint32_t setup(Sm& m, int kch, const GvpW* gv, int n_gvps) {
+__device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
+    for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], 1); }
+    tc::mbar_init(m.feats_ready, C::NW);
+    tc::mbar_init(m.tail_ready, C::NW);
+    tc::mbar_init(m.acc_done, 1);
+    tc::mbar_init(m.gates_done, 1);
+    tc::mbar_init(m.wsm_full, 1);
+    tc::fence_barrier_init();
+}
+
+// barriers + TMEM + zeroed A planes; ends with a __syncthreads() (the small fp32 weights arrive as one bulk copy
+// per GVP issued by the producer, see produce())
+template <class C>
+__device__ __forceinline__ uint32_t setup(Sm& m, int kch) {
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) {
-        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], 1); }
-        tc::mbar_init(m.feats_ready, C::NW);
-        tc::mbar_init(m.tail_ready, C::NW);
-        tc::mbar_init(m.acc_done, 1);
-        tc::mbar_init(m.gates_done, 1);
-        tc::fence_barrier_init();
-    }
+    if (tid == 0) init_barriers<C>(m);
     if (warp == C::NW) { tc::tmem_alloc(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish(); }
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     const int nz = (int)(plane_bytes<C>(kch) / 16);
     for (int i = tid; i < nz; i += C::NT) reinterpret_cast<uint4*>(m.A[0])[i] = z;
-    for (int idx = tid; idx < n_gvps * C::WSM; idx += C::NT) {
-        const int gi = idx / C::WSM;
-        int o = idx - gi * C::WSM;
-        const GvpW& g = gv[gi];
-        float val = 0.f;
-        bool lo = false, wt = false;
-        if (o < C::NS * WH_SZ) {             // Wh: our input channel k (x_diff last for message GVP 0) x h
-            wt = true;
-            if (o >= WH_SZ) { lo = true; o -= WH_SZ; }
-            const int pr = o / (WH_LD * 2), rem = o - pr * (WH_LD * 2), h = rem >> 1, k = 2 * pr + (rem & 1);
-            const int rk = g.xfirst ? (k == g.vin - 1 ? 0 : k + 1) : k;       // reference row of our channel k
-            if (k < g.vin && h < g.hd) val = g.Wh[rk * g.hd + h];
-        } else if (o < C::NS * (WH_SZ + WU_SZ)) {
-            wt = true;
-            o -= C::NS * WH_SZ;
-            if (o >= WU_SZ) { lo = true; o -= WU_SZ; }
-            const int pr = o / (WU_LD * 2), rem = o - pr * (WU_LD * 2), u = rem >> 1, h = 2 * pr + (rem & 1);
-            if (h < g.hd && u < g.vout) val = g.Wu[h * g.vout + u];
-        } else if (o < C::NS * (WH_SZ + WU_SZ) + 256) {
-            const int f = o - C::NS * (WH_SZ + WU_SZ);
-            if (f < g.fout) val = g.bf[f];
-        } else {
-            const int u = o - (C::NS * (WH_SZ + WU_SZ) + 256);
-            if (u < g.vout) val = g.bg[u];
-        }
-        if (wt) {                             // tf32 operands of the vector MMAs: hi = rna(w), lo = rna(w - hi)
-            const float hi = tf32_rna(val);
-            val = lo ? tf32_rna(val - hi) : hi;
-        }
-        m.wsm[idx] = val;
-    }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     if (C::CL > 1) tc::cluster_sync();      // every CTA's barriers exist before a peer multicasts into it
+    tc::fence_after_sync();
+    return *m.tmem_slot;
+}
+
+// Asynchronous set-up (edge kernel, no clusters): the control warps initialise the barriers and TMEM and start
+// streaming weights at once; the SIMT warps meet them at named barrier 3 only after their gathers are in flight.
+template <class C>
+__device__ __forceinline__ void control_setup(Sm& m) {      // the two control warps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == C::NW) {
+        if (lane == 0) init_barriers<C>(m);
+        __syncwarp();
+        tc::tmem_alloc(m.tmem_slot, TMEM_COLS);
+        tc::tmem_relinquish();
+        tc::fence_before_sync();
+    }
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+    asm volatile("bar.arrive 3, %0;" ::"n"(C::NT) : "memory");
+    tc::fence_after_sync();
+}
+template <class C>
+__device__ __forceinline__ uint32_t simt_join(Sm& m) {       // the SIMT warps, before their first mbarrier / TMEM use
+    asm volatile("bar.sync 3, %0;" ::"n"(C::NT) : "memory");
     tc::fence_after_sync();
     return *m.tmem_slot;
 }
@@ -210,6 +208,11 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
     uint32_t it = 0;
     const uint32_t rank = C::CL > 1 ? tc::cluster_ctarank() : 0u;
     constexpr uint16_t mask = (uint16_t)((1u << C::CL) - 1u);
+    if (!dead) {                // shared-memory images of the small fp32 weights of the whole chain
+        tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)(n_gvps * C::WSM * sizeof(float)));
+        for (int g = 0; g < n_gvps; ++g)
+            tc::bulk_g2s(m.wsm + g * C::WSM, C::NS == 2 ? gv[g].wsmP2 : gv[g].wsmP, C::WSM * sizeof(float), m.wsm_full);
+    }
 #ifdef KPD_WS_TRACE
     unsigned long long tp[64];
 #endif
@@ -467,7 +470,7 @@ __device__ __forceinline__ void vec_gemm(const float (&A)[3][3][2], float (&D)[3
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     if (NS == 2) { ah[c][e] = tf32_rna(A[c][s][e]); al[c][e] = tf32_rna(A[c][s][e] - ah[c][e]); }
-                    else ah[c][e] = A[c][s][e];          // plain tf32: the tensor core ignores the low mantissa bits
+                    else ah[c][e] = tf32_rna(A[c][s][e]);   // round (the tensor core would truncate the low mantissa bits)
                 }
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
@@ -560,6 +563,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     // a. Vh = V^T Wh (gvp.py:96) on the warp-level tensor cores; sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
     TC_T(t0);
     WS_TRACE(10);
+    if (gi == 0) tc::mbar_wait(m.wsm_full, 0);
     float vh[3][3][2];
     vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
 #pragma unroll
@@ -737,30 +741,43 @@ __global__ void split_planes_kernel(const float* __restrict__ s0, int n0, const 
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_constant__ GvpEdgeLaunch L) {
     const GvpEtypeArgs& a = L.e[blockIdx.y];
-    const int E = a.rowptr[a.n_dst];
     const int tile_begin = blockIdx.x * C::R;
+    // this thread's edge, fetched together with the edge count (the arrays are sized at capacity, so the speculative
+    // read is in bounds; rows past the end are mapped to the tile's last edge below)
+    int my_s = 0, my_d = 0;
+    if (threadIdx.x < C::R) {
+        const int e = min(tile_begin + (int)threadIdx.x, a.cap - 1);
+        my_s = __ldg(a.src + e); my_d = __ldg(a.dst + e);
+    }
+    const int E = a.rowptr[a.n_dst];
     if ((int)(blockIdx.x / C::CL) * C::CL * C::R >= E) return;      // the whole cluster is past the last edge
     const bool dead = tile_begin >= E;                              // this CTA only helps to stream the weights
     const int n = min(C::R, E - tile_begin);
     extern __shared__ __align__(128) unsigned char smem_ws[];
     TC_T(e0);
     ws::Sm m = ws::carve<C>(smem_ws, L.kch);
-    const uint32_t tmem = ws::setup<C>(m, L.kch, a.msg, L.n_msg);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = L.Sdim, Vd = L.Vdim;
-    if (warp == C::NW) {
-        if (lane == 0) { if (dead) ws::drain<C>(a.msg, L.n_msg, m); else ws::issue<C>(a.msg, L.n_msg, m, tmem); }
-    } else if (warp == C::NW + 1) {
-        if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m, dead);
+    constexpr bool ASYNC = C::CL == 1;        // clusters need every CTA's barriers before any multicast: common set-up
+    uint32_t tmem = 0;
+    if (!ASYNC) tmem = ws::setup<C>(m, L.kch);
+    if (warp >= C::NW) {
+        if (ASYNC) { ws::control_setup<C>(m); tmem = *m.tmem_slot; }
+        if (warp == C::NW) {
+            if (lane == 0) { if (dead) ws::drain<C>(a.msg, L.n_msg, m); else ws::issue<C>(a.msg, L.n_msg, m, tmem); }
+        } else {
+            if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m, dead);
+        }
     } else if (!dead) {
         TC_T(e1);
-        if (tid < C::R) {
-            const int e = tile_begin + min(tid, n - 1);
-            const int s = a.src[e], d = a.dst[e];
-            m.src_s[tid] = s;
-            m.dst_s[tid] = d;
-            m.rp[2 * tid] = a.rowptr[d];
-            m.rp[2 * tid + 1] = a.rowptr[d + 1];
+        if (tid < C::R) { m.src_s[tid] = my_s; m.dst_s[tid] = my_d; }
+        ws::simt_bar<C>();
+        if (tid >= n && tid < C::R) { my_s = m.src_s[n - 1]; my_d = m.dst_s[n - 1]; }     // rows past the end mirror the last edge
+        ws::simt_bar<C>();
+        if (tid >= n && tid < C::R) { m.src_s[tid] = my_s; m.dst_s[tid] = my_d; }
+        if (tid < C::R) {           // needed only by the segmented reduction at the end
+            m.rp[2 * tid] = __ldg(a.rowptr + my_d);
+            m.rp[2 * tid + 1] = __ldg(a.rowptr + my_d + 1);
         }
         ws::simt_bar<C>();
         // s_src: 16-byte cp.async straight into the canonical bf16 plane(s); consecutive lanes = consecutive rows
@@ -775,31 +792,35 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             }
             cp_async_commit();
         }
-        // geometry + v_src -> registers (gvp.py:474-480)
+        // geometry + v_src -> registers (gvp.py:474-480), in flight together with the gather
         const ws::Lane Ln = ws::lane_geometry<C>();
         ws::VF v;
+        const int sI = m.src_s[Ln.row], dI = m.dst_s[Ln.row];
+        const float dx = a.xs[3 * sI] - a.xd[3 * dI], dy = a.xs[3 * sI + 1] - a.xd[3 * dI + 1], dz = a.xs[3 * sI + 2] - a.xd[3 * dI + 2];
+        ws::vf_load(v, a.v_src + (size_t)sI * (Vd * 3), Vd, Ln.t);
+        if (ASYNC) {        // only the k-chunks behind the gathered scalars need zeros (rbf / |Vh| columns and K padding)
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const int c0 = Sd >> 3, per = C::KCS / 16;
+            for (int i = tid; i < (L.kch - c0) * per; i += C::NT_SIMT) reinterpret_cast<uint4*>(m.A[0] + (size_t)c0 * C::KCS)[i] = z;
+        }
+        ws::build_segments<C>(m, n);             // (its barriers also order the zero fill before the rbf stores)
         {
-            const int s = m.src_s[Ln.row], d = m.dst_s[Ln.row];
-            const float dx = a.xs[3 * s] - a.xd[3 * d], dy = a.xs[3 * s + 1] - a.xd[3 * d + 1], dz = a.xs[3 * s + 2] - a.xd[3 * d + 2];
             const float dij = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-8f)) + 1e-8f;
-            ws::vf_load(v, a.v_src + (size_t)s * (Vd * 3), Vd, Ln.t);
             // the unit x_diff is the LAST input channel here (channel Vd; Wh is staged with its rows permuted to match)
-            {
-                const int sx = Vd >> 3, tx = (Vd & 7) >> 1, ex = Vd & 1;
-                if (Ln.t == tx) {
+            const int sx = Vd >> 3, tx = (Vd & 7) >> 1, ex = Vd & 1;
+            if (Ln.t == tx) {
 #pragma unroll
-                    for (int ss = 0; ss < 3; ++ss)
+                for (int ss = 0; ss < 3; ++ss)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                            if (ss == sx && e == ex) { v.x[0][ss][e] = dx / dij; v.x[1][ss][e] = dy / dij; v.x[2][ss][e] = dz / dij; }
-                }
+                    for (int e = 0; e < 2; ++e)
+                        if (ss == sx && e == ex) { v.x[0][ss][e] = dx / dij; v.x[1][ss][e] = dy / dij; v.x[2][ss][e] = dz / dij; }
             }
             for (int k = Ln.t; k < L.rbf_dim; k += 4) {
                 const float z = (dij - (float)k * L.rbf_step) / L.rbf_sigma;
                 ws::put_scalar<C>(m, Ln.row, Sd + k, expf(-(z * z)));
             }
         }
-        ws::build_segments<C>(m, n);
+        if (ASYNC) tmem = ws::simt_join<C>(m);
         cp_async_wait<0>();
         ws::publish(m.feats_ready);
         TC_T(e2);
@@ -857,6 +878,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         TC_T(e4);
         WS_ACC(8, e0, e1); WS_ACC(9, e1, e2); WS_ACC(10, e2, e3); WS_ACC(11, e3, e4); WS_ACC(13, 0, 1);
     }
+    if (ASYNC && warp < C::NW && dead) tmem = ws::simt_join<C>(m);     // (unreachable without clusters; keeps barrier 3 balanced)
     ws::teardown<C>(tmem);
 }
 
@@ -973,7 +995,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
     extern __shared__ __align__(128) unsigned char smem_ws[];
     TC_T(n0t);
     ws::Sm m = ws::carve<C>(smem_ws, a.kch);
-    const uint32_t tmem = ws::setup<C>(m, a.kch, a.upd, a.n_upd);
+    const uint32_t tmem = ws::setup<C>(m, a.kch);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
@@ -1190,7 +1212,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
     const int n = min(NODE_ROWS, a.n - n0);
     extern __shared__ __align__(128) unsigned char smem_ws[];
     ws::Sm m = ws::carve<C>(smem_ws, a.kch);
-    const uint32_t tmem = ws::setup<C>(m, a.kch, a.g, a.n_gvps);
+    const uint32_t tmem = ws::setup<C>(m, a.kch);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {

@@ -217,7 +217,8 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
                 device, split: bool = False) -> Tuple[torch.Tensor, List[int]]:
     """bf16 tensor-core weights of every GVP, in the library's creation order (csrc/gvp.cu kpd_gvp_attach_tc):
     per conv the message GVPs per edge type, then the update GVPs per node type; then the noise head.
-    Two entries per GVP: to_feats_out (rows padded to 16) and scalar_to_vector_gates (rows padded to 16).
+    Three entries per GVP: to_feats_out (rows padded to 16), scalar_to_vector_gates (rows padded to 16) and the
+    shared-memory image of its small fp32 weights (pack_gvp_small).
     split=True packs (hi, lo) slab pairs for the bf16x3 mode.
     Returns one bf16 device blob (every entry 128-byte aligned) and byte offsets."""
     names = []
@@ -230,13 +231,67 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
             names += [f"{q}node_update_fns.{nt}.{i}" for i in range(n_update_gvps)]
     names += [f"noise_predictor.noise_predictor.gvps.{i}" for i in range(n_noise_gvps)]
     parts, offs, n = [], [], 0
+
+    def add(t):
+        nonlocal n
+        pad = (-t.numel()) % 64                      # 64 bf16 = 128 bytes
+        offs.append(2 * n)
+        parts.append(t)
+        if pad:
+            parts.append(torch.zeros(pad, dtype=torch.bfloat16))
+        n += t.numel() + pad
+
     for name in names:
         for key in (".to_feats_out.0.weight", ".scalar_to_vector_gates.weight"):
-            t = pack_tc_weight(sd[name + key], split)
-            pad = (-t.numel()) % 64                      # 64 bf16 = 128 bytes
-            offs.append(2 * n)
-            parts.append(t)
-            if pad:
-                parts.append(torch.zeros(pad, dtype=torch.bfloat16))
-            n += t.numel() + pad
+            add(pack_tc_weight(sd[name + key], split))
+        # message GVP 0 of every edge type takes the unit x_diff as its first input vector channel
+        xfirst = ".edge_message_fns." in name and name.endswith(".0")
+        img = pack_gvp_small(sd[name + ".Wh"], sd[name + ".Wu"], sd[name + ".to_feats_out.0.bias"],
+                             sd[name + ".scalar_to_vector_gates.bias"], xfirst, split)
+        add(img.view(torch.bfloat16))                # fp32 image carried in the bf16 blob (two bf16 per float)
     return torch.cat(parts).to(device), offs
+
+
+# shared-memory image of the small fp32 weights of one GVP (csrc/gvp_ws.inl: ws::WH_LD, WU_LD, wsm_floats)
+_WH_LD, _WU_LD = 36, 20
+_WH_SZ, _WU_SZ = 12 * _WH_LD * 2, 12 * _WU_LD * 2
+
+
+def _tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32: round to nearest, ties away, keeping 10 mantissa bits."""
+    b = x.contiguous().view(torch.int32)
+    mag = (b & 0x7FFFFFFF) + 0x1000
+    return ((mag & ~0x1FFF) | (b & -0x80000000)).view(torch.float32)
+
+
+def pack_gvp_small(Wh, Wu, bf, bg, xfirst: bool, split: bool) -> torch.Tensor:
+    """Wh [vin, h] and Wu [h, vout] as mma.sync B fragments (pairs of consecutive K rows interleaved, tf32-rounded;
+    with split=True followed by the tf32 residuals for the 3xTF32 mode), then the to_feats_out bias padded to 256 and
+    the gates bias padded to 16.  xfirst: the kernel keeps the x_diff channel LAST, so Wh's rows are rotated."""
+    Wh, Wu = Wh.detach().float().cpu(), Wu.detach().float().cpu()
+    vin, hd = Wh.shape
+    vout = Wu.shape[1]
+    if xfirst:
+        Wh = torch.cat([Wh[1:], Wh[:1]])
+    ns = 2 if split else 1
+
+    def frag(W, ld):
+        K, N = W.shape
+        full = torch.zeros(24, ld)
+        full[:K, :N] = W
+        return full.view(12, 2, ld).permute(0, 2, 1).contiguous().reshape(-1)     # [pair][n][2]
+
+    out = []
+    for W, ld in ((Wh, _WH_LD), (Wu, _WU_LD)):
+        f = frag(W, ld)
+        hi = _tf32_rna(f)
+        out.append(hi)
+        if split:
+            out.append(_tf32_rna(f - hi))
+    b1 = torch.zeros(256)
+    b1[:bf.numel()] = bf.detach().float().cpu()
+    b2 = torch.zeros(16)
+    b2[:bg.numel()] = bg.detach().float().cpu()
+    img = torch.cat(out + [b1, b2])
+    assert img.numel() == ns * (_WH_SZ + _WU_SZ) + 272
+    return img
