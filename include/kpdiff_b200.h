@@ -104,13 +104,15 @@ int kpd_linear(const float* X, int32_t ldx, const float* WT, int32_t ldw, const 
                const float* R, int32_t ldr, float* Y, int32_t ldy, int32_t M, int32_t K, int32_t N,
                int32_t act, void* stream);
 
-/* Same operation on the 5th-generation tensor cores (bf16 operands, fp32 accumulation in TMEM):
- * tcgen05.mma with the weight pre-packed into K-major k-step slabs by pack.pack_tc_weight and fetched
- * with cp.async.bulk; X is converted to bf16 while it is staged.  N <= 256.  This is the "bf16 GEMM
- * mode" of the north star: results differ from fp32 at the 1e-3 level and are reported separately. */
+/* Same operation on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulation in TMEM): W_packed from
+ * pack.pack_tc_weight (k-step slabs streamed with cp.async.bulk); X is converted while it is staged.
+ *   nsplit = 1: bf16 operands (the "bf16 GEMM mode");
+ *   nsplit = 2: bf16 (hi, lo) operand pairs, all four products -> fp32-grade results ("bf16x3", the parity mode;
+ *               W_packed from pack_tc_weight(w, split=True)).
+ * X rows must be 16-byte aligned. */
 int kpd_tc_linear(const float* X, int32_t ldx, const void* W_packed, const float* bias, const float* R,
                   int32_t ldr, float* Y, int32_t ldy, int32_t M, int32_t K, int32_t N, int32_t act,
-                  void* stream);
+                  int32_t nsplit, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (b)+(d) EGNN denoiser.  Replaces LigRecDynamics.forward (models/dynamics.py:342-385),
@@ -139,6 +141,13 @@ typedef struct kpd_egnn_model kpd_egnn_model;
 int kpd_egnn_create(const kpd_egnn_config* cfg, const float* blob, const int64_t* offsets,
                     int32_t n_offsets, kpd_egnn_model** out);
 void kpd_egnn_destroy(kpd_egnn_model* m);
+/* Tensor-core mode of the EGNN ("bf16x3": split (hi, lo) bf16 operands on tcgen05, all four products, fp32
+ * accumulation in TMEM -- inside the 1e-4 parity bar): the per-node first-layer products and the node MLPs run
+ * through kpd_tc_linear(nsplit = 2), the edge stage through the warp-specialised kernel of csrc/egnn_ws.inl.
+ * tc_blob / byte_offsets from pack.pack_egnn_tc.  mode: 0 = fp32 SIMT (default), 2 = bf16x3. */
+int kpd_egnn_attach_tc(kpd_egnn_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n,
+                       int32_t nsplit);
+int kpd_egnn_set_mode(kpd_egnn_model* m, int32_t mode);
 int kpd_egnn_dims(const kpd_egnn_model* m, int* rec_nf, int* hidden_nf);
 int64_t kpd_egnn_workspace_bytes(const kpd_egnn_model* m, const kpd_batch* batch,
                                  int32_t cap_ll, int32_t cap_kl, int32_t cap_kk);

@@ -68,9 +68,11 @@ def _load():
         "kpd_build_graph": (I, [C.POINTER(KpdBatch), P, P, C.POINTER(KpdGraphParams), C.POINTER(KpdCsr),
                                 C.POINTER(KpdCsr), C.POINTER(KpdCsr), P, P, P, P]),
         "kpd_linear": (I, [P, I, P, I, P, P, I, P, I, I, I, I, I, P]),
-        "kpd_tc_linear": (I, [P, I, P, P, P, I, P, I, I, I, I, I, P]),
+        "kpd_tc_linear": (I, [P, I, P, P, P, I, P, I, I, I, I, I, I, P]),
         "kpd_egnn_create": (I, [C.POINTER(KpdEgnnConfig), P, C.POINTER(L), I, C.POINTER(P)]),
         "kpd_egnn_destroy": (None, [P]),
+        "kpd_egnn_attach_tc": (I, [P, P, C.POINTER(L), I, I]),
+        "kpd_egnn_set_mode": (I, [P, I]),
         "kpd_egnn_dims": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "kpd_egnn_workspace_bytes": (L, [P, C.POINTER(KpdBatch), I, I, I]),
         "kpd_egnn_forward": (I, [P, C.POINTER(KpdBatch), P, P, P, P, P, P, I, C.POINTER(KpdCsr),

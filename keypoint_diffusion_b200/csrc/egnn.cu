@@ -27,6 +27,7 @@
 //   Roles (slot = 2*role + branch) inside P: lig: ll.s, ll.d, lk.s, kl.d  | ll.s, ll.d, kl.d
 //                                            kp : kl.s, kk.s, kk.d, lk.d  | kl.s
 #include "common.cuh"
+#include "ws_common.cuh"
 #include <string.h>
 #include <vector>
 
@@ -234,6 +235,11 @@ __global__ void __launch_bounds__(128) egnn_node_prep_kernel(const EgnnNodePrep 
     }
 }
 
+#include "egnn_ws.inl"
+
+int launch_tc_linear(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y,
+                     int ldy, int M, int K, int N, int act, int nsplit, cudaStream_t st);
+
 }  // namespace kpd
 
 using namespace kpd;
@@ -244,6 +250,8 @@ struct EgnnLayerW {
     const float* watt[4]; const float* batt[4]; const float* w3c[4];
     const float* Wn1T[2]; const float* bn1[2]; const float* Wn2T[2]; const float* bn2[2];
     const float* lnw[2]; const float* lnb[2];
+    // tensor-core mode (kpd_egnn_attach_tc): packed k-step slabs
+    const void* WpreP[2]; const uint4* W2P[4][2]; const void* Wn1P[2]; const void* Wn2P[2];
 };
 
 struct kpd_egnn_model {
@@ -252,7 +260,9 @@ struct kpd_egnn_model {
     int n_et, n_upd, nslot[2];
     const float* lig_enc[4]; const float* rec_enc[4]; const float* dec[4];
     std::vector<EgnnLayerW> layers;
-    size_t edge_smem;
+    size_t edge_smem, edge_smem_ws;
+    int mode;          // 0 = fp32 SIMT, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
+    bool tc2_ready;
 };
 
 struct EgnnWs {
@@ -332,11 +342,49 @@ extern "C" int kpd_egnn_create(const kpd_egnn_config* cfg, const float* blob, co
     m->edge_smem = sizeof(float) * ((size_t)TE * m->lda + BS_FLOATS + TE * 4 + TE * 3 + TE * 3 + TE) + sizeof(int) * 2 * TE;
     cudaError_t e = cudaFuncSetAttribute(egnn_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->edge_smem);
     if (e != cudaSuccess) { const size_t sm = m->edge_smem; delete m; KPD_REQUIRE(false, "kpd_egnn_create: cannot set %zu B shared memory: %s", sm, cudaGetErrorString(e)); }
+    m->mode = 0;
+    m->tc2_ready = false;
+    m->edge_smem_ws = egws::smem_bytes(2 * cdiv(m->H, 16));
     *out = m;
     return 0;
 }
 
 extern "C" void kpd_egnn_destroy(kpd_egnn_model* m) { delete m; }
+
+// Tensor-core mode ("bf16x3": split (hi, lo) bf16 operands, fp32-grade): tc_blob holds, per layer, the packed
+// (pack.pack_tc_weight(split=True)) weights  Wpre[lig], Wpre[kp]; per edge type W2 of edge_mlp and coord_mlp (rows
+// [0, nmain)); per updated node type node_mlp.0 and node_mlp.2 -- pack.pack_egnn_tc.
+extern "C" int kpd_egnn_attach_tc(kpd_egnn_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n, int32_t nsplit) {
+    KPD_REQUIRE(m && tc_blob && byte_offsets, "kpd_egnn_attach_tc: null argument");
+    KPD_REQUIRE(nsplit == 2, "kpd_egnn_attach_tc: only nsplit = 2 (bf16x3) is implemented for the EGNN");
+    const int per_layer = 2 + m->n_et * 2 + m->n_upd * 2;
+    KPD_REQUIRE(n == m->cfg.n_layers * per_layer, "kpd_egnn_attach_tc: expected %d offsets, got %d", m->cfg.n_layers * per_layer, n);
+    KPD_REQUIRE((reinterpret_cast<uintptr_t>(tc_blob) & 127) == 0, "kpd_egnn_attach_tc: blob must be 128-byte aligned");
+    KPD_REQUIRE(m->nmain % 8 == 0 && m->H <= 257, "kpd_egnn_attach_tc: hidden width %d unsupported by the tensor-core tiles", m->H);
+    KPD_REQUIRE(m->edge_smem_ws <= 227 * 1024, "kpd_egnn_attach_tc: tile needs %zu B of shared memory", m->edge_smem_ws);
+    const char* base = static_cast<const char*>(tc_blob);
+    int i = 0;
+    auto P = [&](void) -> const void* { return base + byte_offsets[i++]; };
+    for (int l = 0; l < m->cfg.n_layers; ++l) {
+        EgnnLayerW& L = m->layers[l];
+        for (int nt = 0; nt < 2; ++nt) L.WpreP[nt] = P();
+        for (int e = 0; e < m->n_et; ++e)
+            for (int br = 0; br < 2; ++br) L.W2P[e][br] = static_cast<const uint4*>(P());
+        for (int nt = 0; nt < m->n_upd; ++nt) { L.Wn1P[nt] = P(); L.Wn2P[nt] = P(); }
+    }
+    cudaError_t e = cudaFuncSetAttribute(egnn_edge_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->edge_smem_ws);
+    KPD_REQUIRE(e == cudaSuccess, "kpd_egnn_attach_tc: cannot set %zu B shared memory: %s", m->edge_smem_ws, cudaGetErrorString(e));
+    m->tc2_ready = true;
+    return 0;
+}
+
+extern "C" int kpd_egnn_set_mode(kpd_egnn_model* m, int32_t mode) {
+    KPD_REQUIRE(m, "kpd_egnn_set_mode: null model");
+    KPD_REQUIRE(mode == 0 || mode == 2, "kpd_egnn_set_mode: mode must be 0 (fp32 SIMT) or 2 (bf16x3 tensor cores)");
+    KPD_REQUIRE(mode != 2 || m->tc2_ready, "kpd_egnn_set_mode: call kpd_egnn_attach_tc first");
+    m->mode = mode;
+    return 0;
+}
 
 extern "C" int kpd_egnn_dims(const kpd_egnn_model* m, int* rec_nf, int* hidden_nf) {
     KPD_REQUIRE(m, "kpd_egnn_dims: null model");
@@ -411,7 +459,8 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
         prof_begin(PROF_EGNN_PRE, st);
         for (int nt = 0; nt < 2; ++nt) {
             const int ncol = m->nslot[nt] * Hp;
-            KPD_TRY(launch_linear(w.h[nt], Hp, W.WpreT[nt], ncol, W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, st));
+            if (m->mode == 2) KPD_TRY(launch_tc_linear(w.h[nt], Hp, W.WpreP[nt], W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, 2, st));
+            else KPD_TRY(launch_linear(w.h[nt], Hp, W.WpreT[nt], ncol, W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, st));
         }
         prof_end(PROF_EGNN_PRE, st);
         EgnnEdgeLaunch L;
@@ -429,8 +478,19 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             a.hn = w.hn[e]; a.xn = w.xn[e]; a.part = w.part[e];
         }
         prof_begin(PROF_EGNN_EDGE, st);
-        egnn_edge_kernel<<<dim3(max_tiles, m->n_et), NT, m->edge_smem, st>>>(L);
-        KPD_TRY(check_launch("egnn_edge_kernel"));
+        if (m->mode == 2) {
+            EgnnWsLaunch WL;
+            memset(&WL, 0, sizeof(WL));
+            WL.L = L;
+            WL.kch = 2 * cdiv(H, 16);
+            for (int e = 0; e < m->n_et; ++e)
+                for (int br = 0; br < 2; ++br) WL.t[e].W2P[br] = W.W2P[e][br];
+            egnn_edge_ws_kernel<<<dim3(max_tiles, m->n_et), egws::NT, m->edge_smem_ws, st>>>(WL);
+            KPD_TRY(check_launch("egnn_edge_ws_kernel"));
+        } else {
+            egnn_edge_kernel<<<dim3(max_tiles, m->n_et), NT, m->edge_smem, st>>>(L);
+            KPD_TRY(check_launch("egnn_edge_kernel"));
+        }
         prof_end(PROF_EGNN_EDGE, st);
         prof_begin(PROF_EGNN_NODE, st);
 
@@ -454,8 +514,13 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
                 KPD_TRY(check_launch("egnn_node_prep_kernel"));
             }
             // node_mlp = Linear(2H,H), SiLU, Linear(H,H); residual; LayerNorm  (:202-205)
-            KPD_TRY(launch_linear(w.cat, a.ldcat, W.Wn1T[nt], Hp, W.bn1[nt], nullptr, 0, w.tmp1, Hp, N[nt], 2 * H, H, 1, st));
-            KPD_TRY(launch_linear(w.tmp1, Hp, W.Wn2T[nt], Hp, W.bn2[nt], w.h[nt], Hp, w.y, Hp, N[nt], H, H, 0, st));
+            if (m->mode == 2) {
+                KPD_TRY(launch_tc_linear(w.cat, a.ldcat, W.Wn1P[nt], W.bn1[nt], nullptr, 0, w.tmp1, Hp, N[nt], 2 * H, H, 1, 2, st));
+                KPD_TRY(launch_tc_linear(w.tmp1, Hp, W.Wn2P[nt], W.bn2[nt], w.h[nt], Hp, w.y, Hp, N[nt], H, H, 0, 2, st));
+            } else {
+                KPD_TRY(launch_linear(w.cat, a.ldcat, W.Wn1T[nt], Hp, W.bn1[nt], nullptr, 0, w.tmp1, Hp, N[nt], 2 * H, H, 1, st));
+                KPD_TRY(launch_linear(w.tmp1, Hp, W.Wn2T[nt], Hp, W.bn2[nt], w.h[nt], Hp, w.y, Hp, N[nt], H, H, 0, st));
+            }
             if (m->cfg.norm) KPD_TRY(launch_layernorm(w.y, Hp, w.h[nt], Hp, N[nt], H, W.lnw[nt], W.lnb[nt], st));
             else KPD_TRY(launch_copy_rows(w.y, Hp, w.h[nt], Hp, N[nt], H, st));
         }

@@ -1,0 +1,363 @@
+// Warp-specialised tensor-core EGNN edge kernel (included inside namespace kpd by egnn.cu).
+//
+// LigRecConv.message + aggregation (models/dynamics.py:89-122, :159-185) for all edge types in one launch, on
+// tiles of 64 dst-sorted edges.  Per branch (edge_mlp, coord_mlp):
+//   SIMT:   A = SiLU(P_src[src] + P_dst[dst] + w1c * dij)  -> bf16 (hi, lo) rows stacked into ONE 128-row UMMA
+//           operand (ws_common.cuh); the few output columns beyond a multiple of 8 (H = 257 -> column 256) as
+//           fp32 dot products on the way;
+//   MMA:    acc[64 x 256] (+)= A W2^T, two tcgen05.mma per k-step (W_hi, W_lo) = all four hi/lo products, fp32 in
+//           TMEM; weights streamed as packed k-step slabs through a cp.async.bulk ring;
+//   SIMT:   m2 = SiLU(acc + b2) straight out of TMEM; the row dot products with the attention / coordinate vector;
+//           edge branch: m2 -> shared memory, att = sigmoid(.), messages m2 * att summed per destination;
+//           coord branch: cw = tanh(.) * range, x messages cw * x_diff / (dij + 1) summed per destination.
+// Both branches have their own A buffer and TMEM columns, so the tensor core works on one while the SIMT warps
+// build / drain the other.  Deterministic segmented reduction and output layout as in egnn_edge_kernel.
+namespace egws {
+
+using C = ws::Cfg<64, 2, 1>;              // 64-edge tiles, (hi, lo) stacked: M = 128
+constexpr int R = C::R, NW = C::NW, NT_SIMT = C::NT_SIMT, NT = C::NT;
+constexpr int VEC_LD = 264;                   // per-etype vectors staged in shared memory (floats; even, >= Hp)
+static_assert(VEC_LD >= KPD_MAX_HIDDEN + 3 && VEC_LD % 2 == 0, "VEC_LD");
+
+struct Sm {
+    unsigned char* A[2];
+    unsigned char* ring;
+    float *w1c[2], *b2[2], *wv[2], *w2lo[2];     // [VEC_LD] each; w2lo: [3][VEC_LD]
+    float *dij, *xsc, *lo, *dotp, *att, *xm;     // [R], [R][3], [2][R][4], [2][R], [R], [R][3]
+    int *src_s, *dst_s, *seg, *rp, *warp_cnt;
+    uint64_t *full, *empty, *a_ready, *acc_done;
+    uint32_t* tmem_slot;
+};
+
+__host__ __device__ inline size_t a_bytes(int kch) { return ((size_t)kch * C::KCS + 127) & ~(size_t)127; }
+
+static size_t smem_bytes(int kch) {
+    return 2 * a_bytes(kch) + (size_t)C::STAGES * C::SLAB + sizeof(float) * (2 * 3 * VEC_LD + 2 * 3 * VEC_LD) +
+           sizeof(float) * (R + 3 * R + 8 * R + 2 * R + R + 3 * R) + sizeof(int) * (5 * R + 16) +
+           sizeof(uint64_t) * (2 * C::STAGES + 4) + 16 + 128;
+}
+
+__device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
+    Sm m;
+    m.A[0] = smem;
+    m.A[1] = smem + a_bytes(kch);
+    m.ring = smem + 2 * a_bytes(kch);
+    float* f = reinterpret_cast<float*>(m.ring + C::STAGES * C::SLAB);
+    for (int br = 0; br < 2; ++br) { m.w1c[br] = f; f += VEC_LD; m.b2[br] = f; f += VEC_LD; m.wv[br] = f; f += VEC_LD; }
+    for (int br = 0; br < 2; ++br) { m.w2lo[br] = f; f += 3 * VEC_LD; }
+    m.dij = f; f += R;
+    m.xsc = f; f += 3 * R;
+    m.lo = f; f += 8 * R;
+    m.dotp = f; f += 2 * R;
+    m.att = f; f += R;
+    m.xm = f; f += 3 * R;
+    m.src_s = reinterpret_cast<int*>(f);
+    m.dst_s = m.src_s + R;
+    m.seg = m.dst_s + R;
+    m.rp = m.seg + R + 8;
+    m.warp_cnt = m.rp + 2 * R;
+    m.full = reinterpret_cast<uint64_t*>(m.warp_cnt + 8);
+    m.empty = m.full + C::STAGES;
+    m.a_ready = m.empty + C::STAGES;
+    m.acc_done = m.a_ready + 2;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.acc_done + 2);
+    return m;
+}
+
+__device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT_SIMT) : "memory"); }
+
+__device__ __forceinline__ void publish(uint64_t* bar) {
+    tc::fence_proxy_async();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
+}
+
+}  // namespace egws
+
+struct EgnnWsEtype {
+    const uint4* W2P[2];        // packed (hi, lo) k-step slabs of W2[:nmain, :H] per branch (pack.pack_egnn_tc)
+};
+struct EgnnWsLaunch {
+    EgnnEdgeLaunch L;
+    EgnnWsEtype t[4];
+    int kch;
+};
+
+__global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_constant__ EgnnWsLaunch W) {
+    using namespace egws;
+    const EgnnEdgeLaunch& L = W.L;
+    const EgnnEtypeArgs& a = L.e[blockIdx.y];
+    const int tile_begin = blockIdx.x * R;
+    const int E = a.rowptr[a.n_dst];
+    if (tile_begin >= E) return;
+    const int n = min(R, E - tile_begin);
+    extern __shared__ __align__(128) unsigned char smem_eg[];
+    Sm m = carve(smem_eg, W.kch);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = L.H, Hp = L.Hp, nmain = L.nmain, nlo = L.nlo;
+    const int ksteps = W.kch >> 1;
+    const int NB = (nmain + 15) & ~15;
+
+    if (tid == 0) {
+        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.a_ready[i], NW); tc::mbar_init(&m.acc_done[i], 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == NW) { tc::tmem_alloc(m.tmem_slot, 512); tc::tmem_relinquish(); }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *m.tmem_slot;
+
+    if (warp == NW + 1) {
+        // ---- producer: W2 slabs of the edge branch, then of the coord branch
+        if (lane == 0) {
+            const uint32_t slab = C::NS * 2 * (NB / 8) * 128;
+            uint32_t it = 0;
+            for (int br = 0; br < 2; ++br)
+                for (int j = 0; j < ksteps; ++j, ++it) {
+                    const uint32_t st = it % C::STAGES;
+                    if (it >= (uint32_t)C::STAGES) tc::mbar_wait(&m.empty[st], ((it / C::STAGES) - 1) & 1);
+                    tc::mbar_arrive_expect_tx(&m.full[st], slab);
+                    tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, W.t[blockIdx.y].W2P[br] + (size_t)j * (slab / 16), slab, &m.full[st]);
+                }
+        }
+    } else if (warp == NW) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NB);
+            const uint32_t b_k = (NB / 8) * 128, slab1 = 2 * b_k;
+            uint32_t it = 0;
+            for (int br = 0; br < 2; ++br) {
+                tc::mbar_wait(&m.a_ready[br], 0);
+                tc::fence_after_sync();
+                for (int j = 0; j < ksteps; ++j, ++it) {
+                    const uint32_t st = it % C::STAGES;
+                    tc::mbar_wait(&m.full[st], (it / C::STAGES) & 1);
+                    tc::fence_after_sync();
+                    const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
+                    const uint64_t ad = tc::make_smem_desc(tc::smem_u32(m.A[br] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                    tc::mma_bf16_ss(tmem + 256 * br, ad, tc::make_smem_desc(bs, b_k, 128), idesc, j > 0 ? 1u : 0u);
+                    tc::mma_bf16_ss(tmem + 256 * br, ad, tc::make_smem_desc(bs + slab1, b_k, 128), idesc, 1u);
+                    tc::mma_commit(&m.empty[st]);
+                }
+                tc::mma_commit(&m.acc_done[br]);
+            }
+        }
+    } else {
+        // ---- SIMT warps
+        // per-etype vectors -> shared memory; indices + geometry (models/dynamics.py:160, :211, :169)
+        for (int i = tid; i < 2 * Hp; i += NT_SIMT) {
+            const int br = i / Hp, k = i - br * Hp;
+            m.w1c[br][k] = a.w1c[br][k];
+            m.b2[br][k] = a.b2[br][k];
+            m.wv[br][k] = br == 0 ? a.watt[k] : a.w3c[k];
+            for (int c = 0; c < 3; ++c) m.w2lo[br][c * VEC_LD + k] = c < nlo ? a.W2lo[br][c * Hp + k] : 0.f;
+        }
+        if (tid < R) {
+            const int e = tile_begin + min(tid, n - 1);     // rows >= n replicate the last valid edge
+            const int s = a.src[e], d = a.dst[e];
+            m.src_s[tid] = s;
+            m.dst_s[tid] = d;
+            m.rp[2 * tid] = a.rowptr[d];
+            m.rp[2 * tid + 1] = a.rowptr[d + 1];
+            const float dx = a.xs[3 * s] - a.xd[3 * d], dy = a.xs[3 * s + 1] - a.xd[3 * d + 1], dz = a.xs[3 * s + 2] - a.xd[3 * d + 2];
+            const float dij = sqrtf(dx * dx + dy * dy + dz * dz);
+            m.dij[tid] = dij;
+            const float inv = 1.0f / (dij + 1.0f);
+            m.xsc[3 * tid] = dx * inv; m.xsc[3 * tid + 1] = dy * inv; m.xsc[3 * tid + 2] = dz * inv;
+        }
+        simt_bar();
+        // segment table of the dst-sorted tile (as ws::build_segments)
+        {
+            bool start = false;
+            unsigned bal = 0;
+            if (tid < R) {
+                start = tid < n && (tid == 0 || m.dst_s[tid] != m.dst_s[tid - 1]);
+                bal = __ballot_sync(0xffffffffu, start);
+                if (lane == 0) m.warp_cnt[warp] = __popc(bal);
+            }
+            simt_bar();
+            if (tid < R) {
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += m.warp_cnt[w];
+                if (start) m.seg[base + __popc(bal & ((1u << lane) - 1u))] = tid;
+                if (tid == 0) {
+                    int tot = 0;
+                    for (int w = 0; w < R / 32; ++w) tot += m.warp_cnt[w];
+                    m.seg[tot] = n;
+                    m.seg[R + 1] = tot;
+                }
+            }
+        }
+        // ---- 1. both branches: first Linear (factorised) + SiLU -> A[br]; leftover output columns as fp32 dots
+        for (int br = 0; br < 2; ++br) {
+            for (int rb = 0; rb < R / NW; rb += 4) {
+                float v[4][2][8];          // [row of the batch][chunk slot: lane, lane + 32][8]
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = warp * (R / NW) + rb + j;
+                    const float* ps = a.Ps + (size_t)m.src_s[r] * a.ldps + (a.slot_s + br) * Hp;
+                    const float* pd = a.Pd + (size_t)m.dst_s[r] * a.ldpd + (a.slot_d + br) * Hp;
+#pragma unroll
+                    for (int cs = 0; cs < 2; ++cs) {
+                        const int c = lane + 32 * cs;
+                        if (8 * c + 8 <= H) {
+                            const float4 u0 = __ldg(reinterpret_cast<const float4*>(ps + 8 * c)), u1 = __ldg(reinterpret_cast<const float4*>(ps + 8 * c + 4));
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pd + 8 * c)), w1 = __ldg(reinterpret_cast<const float4*>(pd + 8 * c + 4));
+                            v[j][cs][0] = u0.x + w0.x; v[j][cs][1] = u0.y + w0.y; v[j][cs][2] = u0.z + w0.z; v[j][cs][3] = u0.w + w0.w;
+                            v[j][cs][4] = u1.x + w1.x; v[j][cs][5] = u1.y + w1.y; v[j][cs][6] = u1.z + w1.z; v[j][cs][7] = u1.w + w1.w;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[j][cs][q] = 8 * c + q < H ? __ldg(ps + 8 * c + q) + __ldg(pd + 8 * c + q) : 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = warp * (R / NW) + rb + j;
+                    const float d = m.dij[r];
+                    float dots[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int cs = 0; cs < 2; ++cs) {
+                        const int c = lane + 32 * cs;
+                        if (c < W.kch) {
+                            float f[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int k = 8 * c + q;
+                                f[q] = k < H ? ws::silu_acc(v[j][cs][q] + m.w1c[br][k] * d) : 0.f;
+                            }
+                            for (int cc = 0; cc < nlo; ++cc)
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    if (8 * c + q < H) dots[cc] = fmaf(f[q], m.w2lo[br][cc * VEC_LD + 8 * c + q], dots[cc]);
+                            uint4 hi, lo;
+                            ws::split8(f, hi, lo);
+                            const uint32_t off = (uint32_t)(c * C::KCS) + ws::row_off<C>(r);
+                            *reinterpret_cast<uint4*>(m.A[br] + off) = hi;
+                            *reinterpret_cast<uint4*>(m.A[br] + off + 256) = lo;
+                        }
+                    }
+                    for (int cc = 0; cc < nlo; ++cc) {
+                        float s = dots[cc];
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(s + m.b2[br][nmain + cc]);
+                    }
+                }
+            }
+            publish(&m.a_ready[br]);
+        }
+        // ---- 2. per branch: epilogue straight out of TMEM, then the deterministic segmented reduction
+        const int q4 = warp & 3, cg = warp >> 2;
+        const int ra = 16 * q4 + (lane >> 2), cp = 2 * (lane & 3);
+        const uint32_t ro = ws::row_off<C>(ra) + cp * 2;
+        for (int br = 0; br < 2; ++br) {
+            tc::mbar_wait(&m.acc_done[br], 0);
+            tc::fence_after_sync();
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + 256 * br;
+            float dota = 0.f, dotb = 0.f;
+            const int cend = min(nmain, cg * 128 + 128);
+            for (int cb = cg * 128; cb < cend; cb += 64) {
+                uint32_t v0[32], v1[32];
+                tc::tmem_ld_16x256b_x8(taddr + cb, v0);
+                tc::tmem_ld_16x256b_x8(taddr + (16u << 16) + cb, v1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int col = cb + 8 * i + cp;
+                    if (cb + 8 * i < nmain) {
+                        const float2 b = *reinterpret_cast<const float2*>(m.b2[br] + col);
+                        const float2 wv = *reinterpret_cast<const float2*>(m.wv[br] + col);
+                        const float fa0 = ws::silu_acc(__uint_as_float(v0[4 * i + 0]) + __uint_as_float(v1[4 * i + 0]) + b.x);
+                        const float fa1 = ws::silu_acc(__uint_as_float(v0[4 * i + 1]) + __uint_as_float(v1[4 * i + 1]) + b.y);
+                        const float fb0 = ws::silu_acc(__uint_as_float(v0[4 * i + 2]) + __uint_as_float(v1[4 * i + 2]) + b.x);
+                        const float fb1 = ws::silu_acc(__uint_as_float(v0[4 * i + 3]) + __uint_as_float(v1[4 * i + 3]) + b.y);
+                        dota = fmaf(fa0, wv.x, fmaf(fa1, wv.y, dota));
+                        dotb = fmaf(fb0, wv.x, fmaf(fb1, wv.y, dotb));
+                        if (br == 0) {          // m2 of the edge branch -> A[0] (its MMAs have completed), as (hi, lo) bf16
+                            const uint32_t off = (uint32_t)((col >> 3) * C::KCS) + ro;
+                            const uint32_t ha = tc::pack_bf16x2(fa0, fa1), hb = tc::pack_bf16x2(fb0, fb1);
+                            *reinterpret_cast<uint32_t*>(m.A[0] + off) = ha;
+                            *reinterpret_cast<uint32_t*>(m.A[0] + off + 128) = hb;
+                            *reinterpret_cast<uint32_t*>(m.A[0] + off + 256) =
+                                tc::pack_bf16x2(fa0 - __uint_as_float(ha << 16), fa1 - __uint_as_float(ha & 0xffff0000u));
+                            *reinterpret_cast<uint32_t*>(m.A[0] + off + 384) =
+                                tc::pack_bf16x2(fb0 - __uint_as_float(hb << 16), fb1 - __uint_as_float(hb & 0xffff0000u));
+                        }
+                    }
+                }
+            }
+            dota += __shfl_xor_sync(0xffffffffu, dota, 1); dota += __shfl_xor_sync(0xffffffffu, dota, 2);
+            dotb += __shfl_xor_sync(0xffffffffu, dotb, 1); dotb += __shfl_xor_sync(0xffffffffu, dotb, 2);
+            if ((lane & 3) == 0) { m.dotp[cg * R + ra] = dota; m.dotp[cg * R + ra + 8] = dotb; }
+            simt_bar();
+            if (tid < R) {
+                float dot = m.dotp[tid] + m.dotp[R + tid];
+                for (int cc = 0; cc < nlo; ++cc) dot = fmaf(m.lo[(br * R + tid) * 4 + cc], m.wv[br][nmain + cc], dot);
+                if (br == 0) {
+                    m.att[tid] = ws::sigmoid_acc(dot + a.batt[0]);          // msg_h = m2 * sigmoid(Linear(m2))  (:111-112)
+                } else {
+                    // msg_x = tanh(coord_mlp(f)) * x_diff * coords_range | coord_mlp(f) * x_diff  (:117-120)
+                    const float cw = L.use_tanh ? tanhf(dot) * L.coords_range : dot;
+                    m.xm[3 * tid] = cw * m.xsc[3 * tid]; m.xm[3 * tid + 1] = cw * m.xsc[3 * tid + 1]; m.xm[3 * tid + 2] = cw * m.xsc[3 * tid + 2];
+                }
+            }
+            simt_bar();
+            // segmented reduction by destination (copy_e + sum, :177-185)
+            const int nseg = m.seg[R + 1];
+            float* part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
+            float* part1 = a.part + ((size_t)blockIdx.x * 2 + 1) * L.pw;
+            if (br == 0) {
+                const int npair = nmain >> 1;
+                const int grp = tid / 128, p = tid & 127;           // two groups of 128 threads split the segments
+                if (p < npair) {
+                    const int col = 2 * p;
+                    const unsigned char* p0 = m.A[0] + (size_t)(col >> 3) * C::KCS + (col & 7) * 2;
+                    for (int sg = grp; sg < nseg; sg += NT_SIMT / 128) {
+                        const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
+                        float s0 = 0.f, s1 = 0.f;
+                        for (int j = r0; j < r1; ++j) {
+                            const uint32_t o2 = ws::row_off<C>(j);
+                            const uint32_t wh = *reinterpret_cast<const uint32_t*>(p0 + o2), wl = *reinterpret_cast<const uint32_t*>(p0 + o2 + 256);
+                            const float at = m.att[j];
+                            s0 = fmaf(__uint_as_float(wh << 16) + __uint_as_float(wl << 16), at, s0);
+                            s1 = fmaf(__uint_as_float(wh & 0xffff0000u) + __uint_as_float(wl & 0xffff0000u), at, s1);
+                        }
+                        const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
+                        const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
+                        float* t = from_prev ? part0 + col : into_next ? part1 + col : a.hn + (size_t)m.dst_s[r0] * Hp + col;
+                        t[0] = s0; t[1] = s1;
+                    }
+                }
+                if (tid < nlo) {                                    // the leftover feature columns
+                    const int col = nmain + tid;
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
+                        float s = 0.f;
+                        for (int j = r0; j < r1; ++j) s = fmaf(m.lo[j * 4 + tid], m.att[j], s);
+                        const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
+                        const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
+                        float* t = from_prev ? part0 + col : into_next ? part1 + col : a.hn + (size_t)m.dst_s[r0] * Hp + col;
+                        t[0] = s;
+                    }
+                }
+            } else if (tid < 3) {                                   // x messages; their partial slots follow the Hp feature columns
+                for (int sg = 0; sg < nseg; ++sg) {
+                    const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
+                    float s = 0.f;
+                    for (int j = r0; j < r1; ++j) s += m.xm[3 * j + tid];
+                    const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
+                    const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
+                    float* t = from_prev ? part0 + Hp + tid : into_next ? part1 + Hp + tid : a.xn + (size_t)m.dst_s[r0] * 4 + tid;
+                    t[0] = s;
+                }
+            }
+            // (the next branch's epilogue touches neither A[0] nor att/xm before its own barriers)
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == egws::NW) tc::tmem_dealloc(tmem, 512);
+}

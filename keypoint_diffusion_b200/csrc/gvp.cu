@@ -23,6 +23,7 @@
 //   etypes(l) = (ll, kl, lk, kk) if update_kp and l != n_convs-1 else (ll, kl)
 #include "common.cuh"
 #include "tc.cuh"
+#include "ws_common.cuh"
 #include <string.h>
 #include <vector>
 
@@ -360,7 +361,6 @@ __global__ void __launch_bounds__(NT, 1) gvp_head_kernel(const GvpHeadArgs a) {
     }
 }
 
-#include "gvp_tc.inl"
 #include "gvp_ws.inl"
 
 }  // namespace kpd
@@ -401,7 +401,7 @@ struct kpd_gvp_model {
     std::vector<GvpLayerW> layers;
     GvpW head[MAXG];
     const float* WoT; const float* bo;
-    size_t smem, smem_node, smem_tc, smem_ws1, smem_ws2, smem_ws1n;
+    size_t smem, smem_node, smem_ws1, smem_ws2, smem_ws1n;
     int kch;           // k-chunks of the bf16 tile (tensor-core mode)
     int mode;          // 0 = fp32 SIMT, 1 = bf16 tcgen05, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
     bool tc_ready, tc2_ready;
@@ -510,7 +510,6 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         int wmax = m->S + cfg->rbf_dim + m->V + 1;
         if (wmax < 64 + m->V) wmax = 64 + m->V;
         m->kch = 2 * ((wmax + 15) / 16);
-        m->smem_tc = gvp_tc_smem_bytes(m->kch);
         m->smem_ws1 = ws::smem_bytes<WsBf16>(m->kch);
         m->smem_ws2 = ws::smem_bytes<WsSplit>(m->kch);
         m->smem_ws1n = ws::smem_bytes<WsBf16N>(m->kch);
@@ -543,8 +542,8 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
     KPD_REQUIRE(n == 3 * (int)m->all_gvps.size(), "kpd_gvp_attach_tc: expected %d offsets, got %d", 3 * (int)m->all_gvps.size(), n);
     KPD_REQUIRE((reinterpret_cast<uintptr_t>(tc_blob) & 127) == 0, "kpd_gvp_attach_tc: blob must be 128-byte aligned");
     KPD_REQUIRE(m->S % 16 == 0, "kpd_gvp_attach_tc: n_hidden_scalars must be a multiple of 16 for the tensor-core mode");
-    KPD_REQUIRE(m->smem_tc <= 227 * 1024 && m->smem_ws1 <= 227 * 1024 && m->smem_ws2 <= 227 * 1024,
-                "kpd_gvp_attach_tc: tile needs %zu / %zu / %zu B of shared memory", m->smem_tc, m->smem_ws1, m->smem_ws2);
+    KPD_REQUIRE(m->smem_ws1 <= 227 * 1024 && m->smem_ws2 <= 227 * 1024 && m->smem_ws1n <= 227 * 1024,
+                "kpd_gvp_attach_tc: tile needs %zu / %zu / %zu B of shared memory", m->smem_ws1, m->smem_ws2, m->smem_ws1n);
     const char* base = static_cast<const char*>(tc_blob);
     for (size_t i = 0; i < m->all_gvps.size(); ++i) {
         KPD_REQUIRE(byte_offsets[3 * i] % 16 == 0 && byte_offsets[3 * i + 1] % 16 == 0 && byte_offsets[3 * i + 2] % 16 == 0,
@@ -570,22 +569,7 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsBf16N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws1);
     }
-    cudaError_t e1 = cudaFuncSetAttribute(gvp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
-    cudaError_t e2 = cudaFuncSetAttribute(gvp_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
-    cudaError_t e3 = cudaFuncSetAttribute(gvp_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_tc);
-    KPD_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_tc);
     m->tc_ready = true;
-    return 0;
-}
-
-// debug: read (and reset) the phase timers of the tensor-core kernels (cycles summed over CTAs)
-extern "C" int kpd_debug_tc_times(unsigned long long* out16) {
-    KPD_REQUIRE(out16, "kpd_debug_tc_times: null argument");
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, g_tc_times, sizeof(unsigned long long) * 16);
-    unsigned long long z[16] = {0};
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_times, z, sizeof(z));
-    KPD_REQUIRE(e == cudaSuccess, "kpd_debug_tc_times: %s", cudaGetErrorString(e));
     return 0;
 }
 

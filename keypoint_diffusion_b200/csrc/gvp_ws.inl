@@ -36,33 +36,11 @@ __device__ int g_ws_trace_n;
 
 namespace ws {
 
-// small fp32 weights of one GVP in shared memory, laid out as mma.sync B fragments (see vector MMAs below):
-//   Wh pairs [12][WH_LD][2]: (our channel 2p, 2p+1; h)   Wu pairs [12][WU_LD][2]: (h = 2p, 2p+1; u)
-// leading dimensions == 4 (mod 16) in 8-byte units make the 64-bit fragment loads conflict-free
-constexpr int WH_LD = 36, WU_LD = 20;
-constexpr int WH_SZ = 12 * WH_LD * 2, WU_SZ = 12 * WU_LD * 2;
-template <int NS> constexpr int wsm_floats() { return NS * (WH_SZ + WU_SZ) + 256 + 16; }   // (hi[, lo]) Wh | Wu | bf | bg
 constexpr int VS_LD = 52;                                   // fp32 vector staging row (48 used)
 constexpr int GATE_LD = 20;                                 // gates staged as [R][20]
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t GATE_COL = 256;
 
-template <int R_, int NS_, int CL_>
-struct Cfg {
-    static constexpr int R = R_, NS = NS_;
-    static constexpr int CL = CL_;                   // CTAs per cluster: neighbouring tiles share ONE weight stream (multicast)
-    static constexpr int NW = R / 8;                 // SIMT warps: 8 rows each, lanes = (row, xyz component)
-    static constexpr int NT_SIMT = 32 * NW;
-    static constexpr int NT = NT_SIMT + 64;
-    static constexpr int MMA_M = R * NS;             // NS = 2 stacks the hi and lo rows of a tile into ONE 128-row A operand
-    static constexpr int KCS = (MMA_M / 8) * 128 + 16;   // bytes between k-chunks of A (+16: bank rotation for column walks)
-    static constexpr int STAGES = NS == 1 ? 8 : 4;
-    static constexpr int SLAB = NS * 8192;           // one ring stage: one k-step of a 256-row weight (hi [, lo])
-    static constexpr int WG_BYTES = NS * 8192;       // gates weight: 16 k-steps x 512 B (hi [, lo])
-    static constexpr int WGB = NS == 1 ? 2 : 1;      // gates weight buffers
-    static constexpr int WSM = wsm_floats<NS>();
-    static constexpr int NCG = NW / 4;               // column groups of the epilogues (4 TMEM lane quarters x NCG)
-};
 
 struct Sm {
     unsigned char* A[2];
@@ -80,15 +58,6 @@ struct Sm {
 template <class C>
 __host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C::KCS + 127) & ~(size_t)127; }
 
-// Byte offset of tile row r inside a k-chunk of A.  NS = 1: plain canonical rows.  NS = 2: MMA rows are ordered
-// (16-row group q, plane, row % 16): TMEM lanes [32q, 32q+16) hold the hi rows and [32q+16, 32q+32) the lo rows of
-// tile rows [16q, 16q+16), so one warp reads both halves of a row's accumulator (16x256b loads) and adds them.
-// The lo row of r sits 256 bytes after its hi row.
-template <class C>
-__device__ __forceinline__ uint32_t row_off(int r) {
-    if (C::NS == 2) return (uint32_t)((4 * (r >> 4) + ((r >> 3) & 1)) * 128 + (r & 7) * 16);
-    return (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
-}
 
 template <class C>
 static size_t smem_bytes(int kch) {
@@ -126,20 +95,6 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
 
 template <class C>
 __device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(C::NT_SIMT) : "memory"); }
-
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-// warp-level tensor-core MMA, D(16x8) += A(16x8) B(8x8), tf32 operands, fp32 accumulation
-__device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float& d3, float a0, float a1, float a2, float a3,
-                                         float b0, float b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
-                 : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
-                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
-}
 
 template <class C>
 __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
@@ -340,22 +295,6 @@ __device__ __forceinline__ void drain(const GvpW* gv, int n_gvps, Sm& m) {
 }
 
 // ------------------------------------------------------------------ SIMT helpers
-__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// fp32-grade logistic on two MUFU ops (ex2 and rcp are good to ~2^-22; no range fix-ups: 1 + 2^t never overflows
-// to a value rcp cannot take, and a huge argument gives rcp(inf) = 0, the right limit)
-__device__ __forceinline__ float sigmoid_acc(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return r;
-}
-__device__ __forceinline__ float silu_acc(float x) { return x * sigmoid_acc(x); }
-
-template <int NS>
-__device__ __forceinline__ float act_silu(float x) { return NS == 1 ? silu_fast(x) : silu_acc(x); }
-template <int NS>
-__device__ __forceinline__ float act_sigmoid(float x) { return NS == 1 ? sigmoid_fast(x) : sigmoid_acc(x); }
-
 // store one value into the bf16 plane(s) at (row, col)
 template <class C>
 __device__ __forceinline__ void put_scalar(const Sm& m, int row, int col, float x) {

@@ -89,6 +89,16 @@ class LigRecDynamics(_DynamicsBase):
         self.update_kp_feat, self.norm, self.ll_k, self.kl_k = update_kp_feat, norm, ll_k, kl_k
         # the reference's division by z never reaches the graph; False reproduces that
         self.message_norm_effective = message_norm_effective
+        # 'fp32': SIMT kernels in the reference's own arithmetic; 'bf16x3': tcgen05 tensor cores with split (hi, lo)
+        # bf16 operands and fp32 accumulation, inside the 1e-4 parity bar
+        self.precision = "fp32"
+
+    def set_precision(self, precision: str):
+        if precision not in ops.EgnnModel.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(ops.EgnnModel.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+        if self._st.model is not None:
+            self._st.model.set_precision(precision)
 
     def device_model(self, device) -> ops.EgnnModel:
         st = self._st
@@ -100,6 +110,8 @@ class LigRecDynamics(_DynamicsBase):
                                      message_norm=self.message_norm, device=device,
                                      z_effective=self.message_norm_effective)
             st.model_key = key
+        if st.model.precision != self.precision:
+            st.model.set_precision(self.precision)
         return st.model
 
     @torch.no_grad()

@@ -154,15 +154,20 @@ def linear(x, wt, bias=None, residual=None, act=0, n_out=None):
     return y
 
 
-def tc_linear(x, w_packed, n_out, bias=None, residual=None, act=0):
-    """Y = act(X @ W^T + b) (+R) on tcgen05 tensor cores (bf16 operands, fp32 accumulate); w_packed from
-    pack.pack_tc_weight."""
+def tc_linear(x, w_packed, n_out, bias=None, residual=None, act=0, nsplit=1):
+    """Y = act(X @ W^T + b) (+R) on tcgen05 tensor cores, fp32 accumulate.  nsplit=1: bf16 operands, w_packed from
+    pack.pack_tc_weight(w); nsplit=2: split (hi, lo) bf16 operands ("bf16x3", fp32-grade), w_packed from
+    pack.pack_tc_weight(w, split=True).  Rows of x must be 16-byte aligned."""
     _require_cuda(x, w_packed)
     M, K = x.shape
+    if x.stride(0) % 4:
+        xp = torch.zeros(M, (K + 3) // 4 * 4, dtype=torch.float32, device=x.device)
+        xp[:, :K] = x
+        x = xp
     y = torch.empty(M, n_out, dtype=torch.float32, device=x.device)
     check(lib.kpd_tc_linear(ptr(x), x.stride(0), ptr(w_packed), ptr(bias), ptr(residual),
                             residual.stride(0) if residual is not None else 0, ptr(y), y.stride(0), M, K, n_out, act,
-                            _stream()), "kpd_tc_linear")
+                            int(nsplit), _stream()), "kpd_tc_linear")
     return y
 
 
@@ -204,6 +209,24 @@ class EgnnModel(_Model):
                             int(bool(z_effective)))
         arr = (C.c_int64 * len(offs))(*offs)
         check(lib.kpd_egnn_create(C.byref(cfg), ptr(self.blob), arr, len(offs), C.byref(self.handle)), "kpd_egnn_create")
+        self.precision = "fp32"
+        self.tc_blob2 = None
+        H = hidden_nf + 1
+        if (min(H, 256) // 4 * 4) % 8 == 0 and H <= 257:
+            self.tc_blob2, toffs = pack.pack_egnn_tc(sd, hidden_nf=hidden_nf, n_layers=n_layers,
+                                                     update_kp_feat=update_kp_feat, device=self.device, split=True)
+            tarr = (C.c_int64 * len(toffs))(*toffs)
+            check(lib.kpd_egnn_attach_tc(self.handle, ptr(self.tc_blob2), tarr, len(toffs), 2), "kpd_egnn_attach_tc")
+
+    PRECISIONS = {"fp32": 0, "bf16x3": 2}
+
+    def set_precision(self, precision: str):
+        """'fp32' (SIMT, the reference's arithmetic) or 'bf16x3' (tcgen05 tensor cores with split bf16 operands:
+        fp32-grade, inside the 1e-4 parity bar)."""
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}, got {precision!r}")
+        check(lib.kpd_egnn_set_mode(self.handle, self.PRECISIONS[precision]), "kpd_egnn_set_mode")
+        self.precision = precision
 
     def __del__(self):
         if getattr(self, "handle", None) and self.handle.value and lib is not None:

@@ -178,6 +178,49 @@ def pack_gvp(sd: Dict[str, torch.Tensor], *, n_lig_scalars, n_kp_scalars, vector
     return blob.finish(device), offs
 
 
+def pack_egnn_tc(sd: Dict[str, torch.Tensor], *, hidden_nf, n_layers, update_kp_feat, device,
+                 split: bool = True) -> Tuple[torch.Tensor, List[int]]:
+    """Tensor-core weights of the EGNN (csrc/egnn.cu kpd_egnn_attach_tc), packed with pack_tc_weight: per layer the
+    per-node first-layer weight of lig and kp ([slots * Hp, H], same column order as pack_egnn's WpreT), per edge type
+    the second Linear of edge_mlp and coord_mlp (output rows [0, nmain)), per updated node type node_mlp.0 / .2."""
+    H = hidden_nf + 1
+    Hp = _r4(H)
+    nmain = min(H, 256) // 4 * 4
+    etypes = ["ll", "kl", "lk", "kk"] if update_kp_feat else ["ll", "kl"]
+    upd = ["lig", "kp"] if update_kp_feat else ["lig"]
+    roles = EGNN_ROLES[bool(update_kp_feat)]
+    parts, offs, n = [], [], 0
+
+    def add(w):
+        nonlocal n
+        t = pack_tc_weight(w, split)
+        pad = (-t.numel()) % 64
+        offs.append(2 * n)
+        parts.append(t)
+        if pad:
+            parts.append(torch.zeros(pad, dtype=torch.bfloat16))
+        n += t.numel() + pad
+
+    for l in range(n_layers):
+        q = f"egnn.conv_layers.{l}."
+        for nt in ("lig", "kp"):
+            rows = []
+            for et, sdir in roles[nt]:
+                for mlp in ("edge_mlp", "coord_mlp"):
+                    W1 = sd[f"{q}{mlp}.{et}.0.weight"].detach().float().cpu()     # [H, 2H+1]
+                    blk = torch.zeros(Hp, H)
+                    blk[:H] = W1[:, :H] if sdir == "s" else W1[:, H:2 * H]
+                    rows.append(blk)                                               # one slot: Hp output rows
+            add(torch.cat(rows, dim=0))
+        for et in etypes:
+            for mlp in ("edge_mlp", "coord_mlp"):
+                add(sd[f"{q}{mlp}.{et}.2.weight"].detach().float().cpu()[:nmain, :])
+        for nt in upd:
+            add(sd[f"{q}node_mlp.{nt}.0.weight"].detach().float().cpu())
+            add(sd[f"{q}node_mlp.{nt}.2.weight"].detach().float().cpu())
+    return torch.cat(parts).to(device), offs
+
+
 def _tc_block(wp: torch.Tensor, split: bool) -> torch.Tensor:
     """[NB, ks*16] fp32 -> k-step slabs [ks][hi(, lo)][2 k-chunks][NB/8][8 rows][8] bf16."""
     NB, K16 = wp.shape
