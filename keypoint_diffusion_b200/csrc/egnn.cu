@@ -28,6 +28,7 @@
 //                                            kp : kl.s, kk.s, kk.d, lk.d  | kl.s
 #include "common.cuh"
 #include "ws_common.cuh"
+#include "tc_gemm.cuh"
 #include <string.h>
 #include <vector>
 
@@ -237,9 +238,6 @@ __global__ void __launch_bounds__(128) egnn_node_prep_kernel(const EgnnNodePrep 
 
 #include "egnn_ws.inl"
 
-int launch_tc_linear(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y,
-                     int ldy, int M, int K, int N, int act, int nsplit, cudaStream_t st);
-
 }  // namespace kpd
 
 using namespace kpd;
@@ -266,7 +264,7 @@ struct kpd_egnn_model {
 };
 
 struct EgnnWs {
-    float *h[2], *xc[2], *P[2], *hn[4], *xn[4], *part[4], *cat, *tmp1, *y, *t1, *t2;
+    float *h[2], *xc[2], *P[2], *hn[4], *xn[4], *part[4], *cat[2], *tmp1[2], *y[2], *t1, *t2;
 };
 
 static int egnn_ntiles(int cap) { return cdiv(cap > 0 ? cap : 1, TE) + 1; }
@@ -287,9 +285,11 @@ static EgnnWs egnn_carve(const kpd_egnn_model* m, const kpd_batch* b, const int 
         w.xn[e] = c.take<float>((int64_t)dstN[e] * 4);
         w.part[e] = c.take<float>((int64_t)egnn_ntiles(caps[e]) * 2 * m->pw);
     }
-    w.cat = c.take<float>((int64_t)maxN * (2 * m->H + 4));
-    w.tmp1 = c.take<float>((int64_t)maxN * m->Hp);
-    w.y = c.take<float>((int64_t)maxN * m->Hp);
+    for (int nt = 0; nt < 2; ++nt) {
+        w.cat[nt] = c.take<float>((int64_t)N[nt] * (2 * m->H + 4));
+        w.tmp1[nt] = c.take<float>((int64_t)N[nt] * m->Hp);
+        w.y[nt] = c.take<float>((int64_t)N[nt] * m->Hp);
+    }
     const int t1w = 64 > m->C2p ? 64 : m->C2p;
     w.t1 = c.take<float>((int64_t)maxN * t1w);
     w.t2 = c.take<float>((int64_t)N[0] * m->F2p);
@@ -378,6 +378,17 @@ extern "C" int kpd_egnn_attach_tc(kpd_egnn_model* m, const void* tc_blob, const 
     return 0;
 }
 
+// debug: read (and reset) the phase timers of the warp-specialised edge kernel (cycles summed over CTAs)
+extern "C" int kpd_debug_eg_times(unsigned long long* out16) {
+    KPD_REQUIRE(out16, "kpd_debug_eg_times: null argument");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, g_eg_times, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_eg_times, z, sizeof(z));
+    KPD_REQUIRE(e == cudaSuccess, "kpd_debug_eg_times: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int kpd_egnn_set_mode(kpd_egnn_model* m, int32_t mode) {
     KPD_REQUIRE(m, "kpd_egnn_set_mode: null model");
     KPD_REQUIRE(mode == 0 || mode == 2, "kpd_egnn_set_mode: mode must be 0 (fp32 SIMT) or 2 (bf16x3 tensor cores)");
@@ -457,10 +468,19 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
     for (int l = 0; l < m->cfg.n_layers; ++l) {
         const EgnnLayerW& W = m->layers[l];
         prof_begin(PROF_EGNN_PRE, st);
-        for (int nt = 0; nt < 2; ++nt) {
-            const int ncol = m->nslot[nt] * Hp;
-            if (m->mode == 2) KPD_TRY(launch_tc_linear(w.h[nt], Hp, W.WpreP[nt], W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, 2, st));
-            else KPD_TRY(launch_linear(w.h[nt], Hp, W.WpreT[nt], ncol, W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, st));
+        if (m->mode == 2) {       // both node types in one launch
+            TcLinBatch TB;
+            memset(&TB, 0, sizeof(TB));
+            for (int nt = 0; nt < 2; ++nt) {
+                const int ncol = m->nslot[nt] * Hp;
+                TB.p[nt] = tc_problem(w.h[nt], Hp, W.WpreP[nt], W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0);
+            }
+            KPD_TRY(launch_tc_batch(TB, 2, 2, st));
+        } else {
+            for (int nt = 0; nt < 2; ++nt) {
+                const int ncol = m->nslot[nt] * Hp;
+                KPD_TRY(launch_linear(w.h[nt], Hp, W.WpreT[nt], ncol, W.bpre[nt], nullptr, 0, w.P[nt], ncol, N[nt], H, ncol, 0, st));
+            }
         }
         prof_end(PROF_EGNN_PRE, st);
         EgnnEdgeLaunch L;
@@ -494,12 +514,13 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
         prof_end(PROF_EGNN_EDGE, st);
         prof_begin(PROF_EGNN_NODE, st);
 
+        const int ldcat = (2 * H + 3) & ~3;
         for (int nt = 0; nt < m->n_upd; ++nt) {
             EgnnNodePrep a;
             memset(&a, 0, sizeof(a));
             a.n = N[nt]; a.H = H; a.Hp = Hp; a.pw = m->pw;
-            a.ldcat = (2 * H + 3) & ~3;
-            a.h = w.h[nt]; a.cat = w.cat; a.x = w.xc[nt];
+            a.ldcat = ldcat;
+            a.h = w.h[nt]; a.cat = w.cat[nt]; a.x = w.xc[nt];
             a.n_et = 2;
             for (int k = 0; k < 2; ++k) {
                 const int e = nt * 2 + k;   // lig <- (ll, kl); kp <- (lk, kk)
@@ -513,16 +534,26 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
                 egnn_node_prep_kernel<<<a.n, 128, 0, st>>>(a);
                 KPD_TRY(check_launch("egnn_node_prep_kernel"));
             }
-            // node_mlp = Linear(2H,H), SiLU, Linear(H,H); residual; LayerNorm  (:202-205)
-            if (m->mode == 2) {
-                KPD_TRY(launch_tc_linear(w.cat, a.ldcat, W.Wn1P[nt], W.bn1[nt], nullptr, 0, w.tmp1, Hp, N[nt], 2 * H, H, 1, 2, st));
-                KPD_TRY(launch_tc_linear(w.tmp1, Hp, W.Wn2P[nt], W.bn2[nt], w.h[nt], Hp, w.y, Hp, N[nt], H, H, 0, 2, st));
-            } else {
-                KPD_TRY(launch_linear(w.cat, a.ldcat, W.Wn1T[nt], Hp, W.bn1[nt], nullptr, 0, w.tmp1, Hp, N[nt], 2 * H, H, 1, st));
-                KPD_TRY(launch_linear(w.tmp1, Hp, W.Wn2T[nt], Hp, W.bn2[nt], w.h[nt], Hp, w.y, Hp, N[nt], H, H, 0, st));
+        }
+        // node_mlp = Linear(2H,H), SiLU, Linear(H,H); residual; LayerNorm  (:202-205)
+        if (m->mode == 2) {       // all updated node types in one launch per Linear
+            TcLinBatch T1, T2;
+            memset(&T1, 0, sizeof(T1));
+            memset(&T2, 0, sizeof(T2));
+            for (int nt = 0; nt < m->n_upd; ++nt) {
+                T1.p[nt] = tc_problem(w.cat[nt], ldcat, W.Wn1P[nt], W.bn1[nt], nullptr, 0, w.tmp1[nt], Hp, N[nt], 2 * H, H, 1);
+                T2.p[nt] = tc_problem(w.tmp1[nt], Hp, W.Wn2P[nt], W.bn2[nt], w.h[nt], Hp, w.y[nt], Hp, N[nt], H, H, 0);
             }
-            if (m->cfg.norm) KPD_TRY(launch_layernorm(w.y, Hp, w.h[nt], Hp, N[nt], H, W.lnw[nt], W.lnb[nt], st));
-            else KPD_TRY(launch_copy_rows(w.y, Hp, w.h[nt], Hp, N[nt], H, st));
+            KPD_TRY(launch_tc_batch(T1, m->n_upd, 2, st));
+            KPD_TRY(launch_tc_batch(T2, m->n_upd, 2, st));
+        }
+        for (int nt = 0; nt < m->n_upd; ++nt) {
+            if (m->mode != 2) {
+                KPD_TRY(launch_linear(w.cat[nt], ldcat, W.Wn1T[nt], Hp, W.bn1[nt], nullptr, 0, w.tmp1[nt], Hp, N[nt], 2 * H, H, 1, st));
+                KPD_TRY(launch_linear(w.tmp1[nt], Hp, W.Wn2T[nt], Hp, W.bn2[nt], w.h[nt], Hp, w.y[nt], Hp, N[nt], H, H, 0, st));
+            }
+            if (m->cfg.norm) KPD_TRY(launch_layernorm(w.y[nt], Hp, w.h[nt], Hp, N[nt], H, W.lnw[nt], W.lnb[nt], st));
+            else KPD_TRY(launch_copy_rows(w.y[nt], Hp, w.h[nt], Hp, N[nt], H, st));
         }
         prof_end(PROF_EGNN_NODE, st);
     }

@@ -12,6 +12,11 @@
 //           coord branch: cw = tanh(.) * range, x messages cw * x_diff / (dij + 1) summed per destination.
 // Both branches have their own A buffer and TMEM columns, so the tensor core works on one while the SIMT warps
 // build / drain the other.  Deterministic segmented reduction and output layout as in egnn_edge_kernel.
+// phase timers (cycles, SIMT thread 0, summed over CTAs): set-up, indices + geometry, build A (edge), build A (coord),
+// wait + epilogue (edge), reduce (edge), wait + epilogue (coord), reduce (coord), [8] = CTAs
+__device__ unsigned long long g_eg_times[16];
+#define EG_ACC(slot, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_eg_times[slot], (unsigned long long)((b) - (a))); } while (0)
+
 namespace egws {
 
 using C = ws::Cfg<64, 2, 1>;              // 64-edge tiles, (hi, lo) stacked: M = 128
@@ -92,6 +97,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
     if (tile_begin >= E) return;
     const int n = min(R, E - tile_begin);
     extern __shared__ __align__(128) unsigned char smem_eg[];
+    TC_T(g0);
     Sm m = carve(smem_eg, W.kch);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = L.H, Hp = L.Hp, nmain = L.nmain, nlo = L.nlo;
@@ -146,6 +152,8 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         }
     } else {
         // ---- SIMT warps
+        TC_T(g1);
+        long long gt[8];
         // per-etype vectors -> shared memory; indices + geometry (models/dynamics.py:160, :211, :169)
         for (int i = tid; i < 2 * Hp; i += NT_SIMT) {
             const int br = i / Hp, k = i - br * Hp;
@@ -191,63 +199,87 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             }
         }
         // ---- 1. both branches: first Linear (factorised) + SiLU -> A[br]; leftover output columns as fp32 dots
+        TC_T(g2);
+        const int nfull = H >> 3, ntail = H & 7;       // full 8-feature chunks (one per lane: H <= 263) and leftover features
         for (int br = 0; br < 2; ++br) {
-            for (int rb = 0; rb < R / NW; rb += 4) {
-                float v[4][2][8];          // [row of the batch][chunk slot: lane, lane + 32][8]
+            // all 8 rows of the warp in one batch: every load of the batch is in flight together
+            constexpr int RPW = R / NW;
+            float v[RPW][8], vt[RPW];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = warp * (R / NW) + rb + j;
-                    const float* ps = a.Ps + (size_t)m.src_s[r] * a.ldps + (a.slot_s + br) * Hp;
-                    const float* pd = a.Pd + (size_t)m.dst_s[r] * a.ldpd + (a.slot_d + br) * Hp;
+            for (int j = 0; j < RPW; ++j) {
+                const int r = warp * RPW + j;
+                const float* ps = a.Ps + (size_t)m.src_s[r] * a.ldps + (a.slot_s + br) * Hp;
+                const float* pd = a.Pd + (size_t)m.dst_s[r] * a.ldpd + (a.slot_d + br) * Hp;
+                if (lane < nfull) {
+                    const float4 u0 = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane)), u1 = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane + 4));
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane)), w1 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane + 4));
+                    v[j][0] = u0.x + w0.x; v[j][1] = u0.y + w0.y; v[j][2] = u0.z + w0.z; v[j][3] = u0.w + w0.w;
+                    v[j][4] = u1.x + w1.x; v[j][5] = u1.y + w1.y; v[j][6] = u1.z + w1.z; v[j][7] = u1.w + w1.w;
+                }
+                vt[j] = lane < ntail ? __ldg(ps + 8 * nfull + lane) + __ldg(pd + 8 * nfull + lane) : 0.f;
+            }
+            const float* w1c = m.w1c[br];
+            const float* w2lo = m.w2lo[br];
+            unsigned char* Ab = m.A[br];
 #pragma unroll
-                    for (int cs = 0; cs < 2; ++cs) {
-                        const int c = lane + 32 * cs;
-                        if (8 * c + 8 <= H) {
-                            const float4 u0 = __ldg(reinterpret_cast<const float4*>(ps + 8 * c)), u1 = __ldg(reinterpret_cast<const float4*>(ps + 8 * c + 4));
-                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pd + 8 * c)), w1 = __ldg(reinterpret_cast<const float4*>(pd + 8 * c + 4));
-                            v[j][cs][0] = u0.x + w0.x; v[j][cs][1] = u0.y + w0.y; v[j][cs][2] = u0.z + w0.z; v[j][cs][3] = u0.w + w0.w;
-                            v[j][cs][4] = u1.x + w1.x; v[j][cs][5] = u1.y + w1.y; v[j][cs][6] = u1.z + w1.z; v[j][cs][7] = u1.w + w1.w;
-                        } else {
+            for (int j = 0; j < RPW; ++j) {
+                const int r = warp * RPW + j;
+                const float d = m.dij[r];
+                const uint32_t rof = ws::row_off<C>(r);
+                float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
+                if (lane < nfull) {
+                    const float4 wa = *reinterpret_cast<const float4*>(w1c + 8 * lane), wb = *reinterpret_cast<const float4*>(w1c + 8 * lane + 4);
+                    float f[8];
+                    f[0] = ws::silu_acc(fmaf(wa.x, d, v[j][0])); f[1] = ws::silu_acc(fmaf(wa.y, d, v[j][1]));
+                    f[2] = ws::silu_acc(fmaf(wa.z, d, v[j][2])); f[3] = ws::silu_acc(fmaf(wa.w, d, v[j][3]));
+                    f[4] = ws::silu_acc(fmaf(wb.x, d, v[j][4])); f[5] = ws::silu_acc(fmaf(wb.y, d, v[j][5]));
+                    f[6] = ws::silu_acc(fmaf(wb.z, d, v[j][6])); f[7] = ws::silu_acc(fmaf(wb.w, d, v[j][7]));
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) v[j][cs][q] = 8 * c + q < H ? __ldg(ps + 8 * c + q) + __ldg(pd + 8 * c + q) : 0.f;
+                    for (int cc = 0; cc < 3; ++cc) {
+                        if (cc < nlo) {
+                            const float4 la = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane);
+                            const float4 lb = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane + 4);
+                            const float t = f[0] * la.x + f[1] * la.y + f[2] * la.z + f[3] * la.w + f[4] * lb.x + f[5] * lb.y + f[6] * lb.z + f[7] * lb.w;
+                            if (cc == 0) dot0 = t; else if (cc == 1) dot1 = t; else dot2 = t;
                         }
                     }
+                    uint4 hi, lo;
+                    ws::split8(f, hi, lo);
+                    const uint32_t off = (uint32_t)(lane * C::KCS) + rof;
+                    *reinterpret_cast<uint4*>(Ab + off) = hi;
+                    *reinterpret_cast<uint4*>(Ab + off + 256) = lo;
+                }
+                // leftover features (H = 257: feature 256) and the K padding: zero the chunks, then 2-byte stores
+                if (lane < W.kch - nfull) {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t off = (uint32_t)((nfull + lane) * C::KCS) + rof;
+                    *reinterpret_cast<uint4*>(Ab + off) = z;
+                    *reinterpret_cast<uint4*>(Ab + off + 256) = z;
+                }
+                __syncwarp();
+                if (lane < ntail) {
+                    const int k = 8 * nfull + lane;
+                    const float f = ws::silu_acc(fmaf(w1c[k], d, vt[j]));
+                    const uint32_t off = (uint32_t)((k >> 3) * C::KCS + (k & 7) * 2) + rof;
+                    const __nv_bfloat16 hi = __float2bfloat16(f);
+                    *reinterpret_cast<__nv_bfloat16*>(Ab + off) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(Ab + off + 256) = __float2bfloat16(f - __bfloat162float(hi));
+                    if (nlo > 0) dot0 = fmaf(f, w2lo[k], dot0);
+                    if (nlo > 1) dot1 = fmaf(f, w2lo[VEC_LD + k], dot1);
+                    if (nlo > 2) dot2 = fmaf(f, w2lo[2 * VEC_LD + k], dot2);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = warp * (R / NW) + rb + j;
-                    const float d = m.dij[r];
-                    float dots[3] = {0.f, 0.f, 0.f};
+                for (int cc = 0; cc < 3; ++cc) {
+                    if (cc < nlo) {
+                        float sdot = cc == 0 ? dot0 : cc == 1 ? dot1 : dot2;
 #pragma unroll
-                    for (int cs = 0; cs < 2; ++cs) {
-                        const int c = lane + 32 * cs;
-                        if (c < W.kch) {
-                            float f[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int k = 8 * c + q;
-                                f[q] = k < H ? ws::silu_acc(v[j][cs][q] + m.w1c[br][k] * d) : 0.f;
-                            }
-                            for (int cc = 0; cc < nlo; ++cc)
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    if (8 * c + q < H) dots[cc] = fmaf(f[q], m.w2lo[br][cc * VEC_LD + 8 * c + q], dots[cc]);
-                            uint4 hi, lo;
-                            ws::split8(f, hi, lo);
-                            const uint32_t off = (uint32_t)(c * C::KCS) + ws::row_off<C>(r);
-                            *reinterpret_cast<uint4*>(m.A[br] + off) = hi;
-                            *reinterpret_cast<uint4*>(m.A[br] + off + 256) = lo;
-                        }
-                    }
-                    for (int cc = 0; cc < nlo; ++cc) {
-                        float s = dots[cc];
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                        if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(s + m.b2[br][nmain + cc]);
+                        for (int o = 16; o; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+                        if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(sdot + m.b2[br][nmain + cc]);
                     }
                 }
             }
             publish(&m.a_ready[br]);
+            gt[br] = clock64();
         }
         // ---- 2. per branch: epilogue straight out of TMEM, then the deterministic segmented reduction
         const int q4 = warp & 3, cg = warp >> 2;
@@ -305,6 +337,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                 }
             }
             simt_bar();
+            gt[2 + 2 * br] = clock64();
             // segmented reduction by destination (copy_e + sum, :177-185)
             const int nseg = m.seg[R + 1];
             float* part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
@@ -355,7 +388,10 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                 }
             }
             // (the next branch's epilogue touches neither A[0] nor att/xm before its own barriers)
+            gt[3 + 2 * br] = clock64();
         }
+        EG_ACC(0, g0, g1); EG_ACC(1, g1, g2); EG_ACC(2, g2, gt[0]); EG_ACC(3, gt[0], gt[1]); EG_ACC(4, gt[1], gt[2]);
+        EG_ACC(5, gt[2], gt[3]); EG_ACC(6, gt[3], gt[4]); EG_ACC(7, gt[4], gt[5]); EG_ACC(8, 0, 1);
     }
     tc::fence_before_sync();
     __syncthreads();

@@ -8,202 +8,288 @@
 // blockIdx.y selects a 256-column block of the output (UMMA N <= 256).
 #include "common.cuh"
 #include "ws_common.cuh"
+#include "tc_gemm.cuh"
+#include <string.h>
 
 namespace kpd {
 
 constexpr int TCG_STAGES = 4;
+constexpr int TCG_THREADS = 192;      // warps 0-3: stage A + epilogues | warp 4: MMA issuer | warp 5: weight producer
 
 template <int NS>
-__global__ void __launch_bounds__(128, 1)
-tc_linear_kernel(const float* __restrict__ X, int ldx, const uint4* __restrict__ Wp, const float* __restrict__ bias,
-                 const float* __restrict__ R, int ldr, float* __restrict__ Y, int ldy, int M, int K, int N, int NBmax,
-                 int act) {
+__global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinBatch B) {
     using C = ws::Cfg<128 / NS, NS, 1>;
+    const TcLinProblem& P = B.p[blockIdx.z];
+    const int M = P.M, K = P.K, N = P.N;
+    const int m0 = blockIdx.x * C::R;
+    const int nblocks = (N + 255) / 256;
+    const int blk0 = blockIdx.y * B.bpc;
+    if (m0 >= M || blk0 >= nblocks) return;
+    const int nb_cta = min(B.bpc, nblocks - blk0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    int NB = N - 256 * (int)blockIdx.y;                // rows of this output block, padded to 16
-    NB = NB > 256 ? 256 : (NB + 15) & ~15;
     const int ksteps = (K + 15) / 16;
-    unsigned char* a_s = smem_raw;                     // [2*ksteps] k-chunks of C::KCS bytes
-    unsigned char* b_s = a_s + (((size_t)2 * ksteps * C::KCS + 127) & ~(size_t)127);   // [STAGES][NS][2][NBmax/8][128 B]
-    const int b_kstride = (NB / 8) * 128;
-    const int slab1 = 2 * b_kstride;                   // one k-step of this block (hi or lo)
-    const int slab_bytes = NS * slab1;
-    const int slab_stride = NS * 2 * (NBmax / 8) * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)TCG_STAGES * slab_stride);   // full[S], empty[S], done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TCG_STAGES + 1);
+    unsigned char* a_s = smem_raw;                     // [2 * ksteps] k-chunks of C::KCS bytes
+    unsigned char* b_s = a_s + (((size_t)2 * ((B.kmax + 15) / 16) * C::KCS + 127) & ~(size_t)127);   // [STAGES] ring
+    const int slab_stride = NS * 2 * (B.NBmax / 8) * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)TCG_STAGES * slab_stride);
     uint64_t* full = bars;
     uint64_t* empty = bars + TCG_STAGES;
-    uint64_t* done = bars + 2 * TCG_STAGES;
-
+    uint64_t* a_ready = bars + 2 * TCG_STAGES;
+    uint64_t* acc_done = a_ready + 1;                  // [2]
+    uint64_t* acc_free = acc_done + 2;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * C::R;
-    const int nblk = blockIdx.y;                       // 256-column block of the output
-    // all blocks before this one are full (256 rows): their slabs are NS * 2 * 32 * 128 B per k-step
-    const uint4* Wblk = Wp + (size_t)nblk * ksteps * (NS * 2 * 32 * 128 / 16);
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < NB) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int i = 0; i < TCG_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(done, 1);
+        tc::mbar_init(a_ready, 4);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], 4); }
         tc::fence_barrier_init();
     }
-    if (warp == 0) { tc::tmem_alloc(tmem_slot, tmem_cols); tc::tmem_relinquish(); }
-    __syncthreads();
-    // ---- the producer starts streaming weights while everybody stages A
-    if (tid == 32) {
-        for (int j = 0; j < ksteps && j < TCG_STAGES; ++j) {
-            tc::mbar_arrive_expect_tx(&full[j], slab_bytes);
-            tc::bulk_g2s(b_s + (size_t)j * slab_stride, Wblk + (size_t)j * (slab_bytes / 16), slab_bytes, &full[j]);
-        }
-    }
-    // ---- stage the A tile: one warp per row, a lane per 8-element k-chunk (coalesced 32-byte reads)
-    {
-        const int nch = 2 * ksteps;
-        for (int r = warp; r < C::R; r += 4) {
-            const int gm = m0 + r;
-            const float* xr = X + (size_t)min(gm, M - 1) * ldx;
-            for (int c = lane; c < nch; c += 32) {
-                float v[8];
-                if (gm < M && 8 * c + 8 <= K) {
-                    const float4 u0 = *reinterpret_cast<const float4*>(xr + 8 * c), u1 = *reinterpret_cast<const float4*>(xr + 8 * c + 4);
-                    v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = (gm < M && 8 * c + q < K) ? xr[8 * c + q] : 0.0f;
-                }
-                uint4 hi, lo;
-                ws::split8(v, hi, lo);
-                const uint32_t off = (uint32_t)(c * C::KCS) + ws::row_off<C>(r);
-                *reinterpret_cast<uint4*>(a_s + off) = hi;
-                if (NS == 2) *reinterpret_cast<uint4*>(a_s + off + 256) = lo;
-            }
-        }
-    }
-    tc::fence_proxy_async();
+    if (warp == 4) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }     // two 256-column accumulators
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- warp 1 lane 0 keeps feeding the weight ring (cp.async.bulk), thread 0 issues the MMAs into TMEM
-    if (tid == 32) {
-        for (int j = TCG_STAGES; j < ksteps; ++j) {
-            const int st = j % TCG_STAGES;
-            tc::mbar_wait(&empty[st], ((j / TCG_STAGES) - 1) & 1);
-            tc::mbar_arrive_expect_tx(&full[st], slab_bytes);
-            tc::bulk_g2s(b_s + (size_t)st * slab_stride, Wblk + (size_t)j * (slab_bytes / 16), slab_bytes, &full[st]);
-        }
-    }
-    if (tid == 0) {
-        const uint32_t idesc = tc::make_idesc_bf16(128, NB);
-        for (int j = 0; j < ksteps; ++j) {
-            const int st = j % TCG_STAGES;
-            tc::mbar_wait(&full[st], (j / TCG_STAGES) & 1);
-            tc::fence_after_sync();
-            const uint64_t adesc = tc::make_smem_desc(tc::smem_u32(a_s + (size_t)2 * j * C::KCS), C::KCS, 128);
-            const uint32_t bs = tc::smem_u32(b_s + (size_t)st * slab_stride);
-            tc::mma_bf16_ss(tmem_base, adesc, tc::make_smem_desc(bs, b_kstride, 128), idesc, j > 0 ? 1u : 0u);
-            if (NS == 2) tc::mma_bf16_ss(tmem_base, adesc, tc::make_smem_desc(bs + slab1, b_kstride, 128), idesc, 1u);
-            tc::mma_commit(&empty[st]);
-        }
-        tc::mma_commit(done);
-    }
-    __syncwarp();
-    tc::mbar_wait(done, 0);
-    tc::fence_after_sync();
+    auto block_NB = [&](int blk) { const int r = N - 256 * blk; return r > 256 ? 256 : (r + 15) & ~15; };
+    // all blocks before the last one are full (256 rows): their slabs are NS * 2 * 32 * 128 B per k-step
+    auto block_W = [&](int blk) { return P.Wp + (size_t)blk * ksteps * (NS * 2 * 32 * 128 / 16); };
 
-    // ---- epilogue
-    if (NS == 1) {          // thread r reads its accumulator row from TMEM
-        const int r = tid, gm = m0 + r;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < NB; c0 += 32) {
-            uint32_t v[32];
-            tc::tmem_ld_x32(lane_addr + c0, v);
-            tc::tmem_ld_wait();
-            if (gm < M) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int gn = nblk * 256 + c0 + q;
-                    if (c0 + q < NB && gn < N) {
-                        float f = __uint_as_float(v[q]) + (bias ? bias[gn] : 0.0f);
-                        if (act == 1) f = silu_f(f);
-                        if (R) f += R[(size_t)gm * ldr + gn];
-                        Y[(size_t)gm * ldy + gn] = f;
-                    }
+    if (warp == 5) {
+        // ---- weight producer: the k-step slabs of this CTA's column blocks through the ring
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int bi = 0; bi < nb_cta; ++bi) {
+                const int NB = block_NB(blk0 + bi);
+                const uint32_t slab_bytes = NS * 2 * (NB / 8) * 128;
+                const uint4* Wb = block_W(blk0 + bi);
+                for (int j = 0; j < ksteps; ++j, ++it) {
+                    const uint32_t st = it % TCG_STAGES;
+                    if (it >= (uint32_t)TCG_STAGES) tc::mbar_wait(&empty[st], ((it / TCG_STAGES) - 1) & 1);
+                    tc::mbar_arrive_expect_tx(&full[st], slab_bytes);
+                    tc::bulk_g2s(b_s + (size_t)st * slab_stride, Wb + (size_t)j * (slab_bytes / 16), slab_bytes, &full[st]);
                 }
             }
         }
-    } else {                // lanes [32w, 32w+16) = hi rows, [32w+16, 32w+32) = lo rows of tile rows [16w, 16w+16)
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int ra = 16 * warp + (lane >> 2), cp = 2 * (lane & 3);
-        for (int c0 = 0; c0 < NB; c0 += 64) {
-            uint32_t v0[32], v1[32];
-            tc::tmem_ld_16x256b_x8(lane_addr + c0, v0);
-            tc::tmem_ld_16x256b_x8(lane_addr + (16u << 16) + c0, v1);
-            tc::tmem_ld_wait();
+    } else if (warp == 4) {
+        // ---- MMA issuer: accumulator bi % 2, so that the epilogue of one block overlaps the MMAs of the next
+        if (lane == 0) {
+            tc::mbar_wait(a_ready, 0);
+            tc::fence_after_sync();
+            uint32_t it = 0;
+            for (int bi = 0; bi < nb_cta; ++bi) {
+                const int buf = bi & 1, NB = block_NB(blk0 + bi);
+                const uint32_t idesc = tc::make_idesc_bf16(128, NB);
+                const uint32_t b_k = (NB / 8) * 128, slab1 = 2 * b_k;
+                if (bi >= 2) { tc::mbar_wait(&acc_free[buf], ((bi >> 1) - 1) & 1); tc::fence_after_sync(); }
+                for (int j = 0; j < ksteps; ++j, ++it) {
+                    const uint32_t st = it % TCG_STAGES;
+                    tc::mbar_wait(&full[st], (it / TCG_STAGES) & 1);
+                    tc::fence_after_sync();
+                    const uint64_t adesc = tc::make_smem_desc(tc::smem_u32(a_s + (size_t)2 * j * C::KCS), C::KCS, 128);
+                    const uint32_t bs = tc::smem_u32(b_s + (size_t)st * slab_stride);
+                    tc::mma_bf16_ss(tmem_base + 256 * buf, adesc, tc::make_smem_desc(bs, b_k, 128), idesc, j > 0 ? 1u : 0u);
+                    if (NS == 2) tc::mma_bf16_ss(tmem_base + 256 * buf, adesc, tc::make_smem_desc(bs + slab1, b_k, 128), idesc, 1u);
+                    tc::mma_commit(&empty[st]);
+                }
+                tc::mma_commit(&acc_done[buf]);
+            }
+        }
+    } else {
+        // ---- stage the A tile once: each warp owns R/4 consecutive rows; (row, 8-element k-chunk) items are dealt to
+        //      the lanes in order (coalesced 32-byte reads), four items per lane in flight
+        {
+            const int nch = 2 * ksteps;
+            constexpr int RPW = C::R / 4;
+            const int items = RPW * nch;
+            for (int base = 0; base < items; base += 128) {
+                float v[4][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int gn = nblk * 256 + c0 + 8 * i + cp;
-                if (c0 + 8 * i < NB) {
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + 32 * u + lane;
+                    const int ri = i / nch, c = i - ri * nch;
+                    const int gm = m0 + warp * RPW + ri;
+                    if (i < items && gm < M && 8 * c + 8 <= K) {
+                        const float* xr = P.X + (size_t)gm * P.ldx + 8 * c;
+                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(xr)), u1 = __ldg(reinterpret_cast<const float4*>(xr + 4));
+                        v[u][0] = u0.x; v[u][1] = u0.y; v[u][2] = u0.z; v[u][3] = u0.w;
+                        v[u][4] = u1.x; v[u][5] = u1.y; v[u][6] = u1.z; v[u][7] = u1.w;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            v[u][q] = (i < items && gm < M && 8 * c + q < K) ? __ldg(P.X + (size_t)gm * P.ldx + 8 * c + q) : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + 32 * u + lane;
+                    if (i < items) {
+                        const int ri = i / nch, c = i - ri * nch;
+                        uint4 hi, lo;
+                        ws::split8(v[u], hi, lo);
+                        const uint32_t off = (uint32_t)(c * C::KCS) + ws::row_off<C>(warp * RPW + ri);
+                        *reinterpret_cast<uint4*>(a_s + off) = hi;
+                        if (NS == 2) *reinterpret_cast<uint4*>(a_s + off + 256) = lo;
+                    }
+                }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(a_ready);
+        }
+        // ---- epilogues
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int bi = 0; bi < nb_cta; ++bi) {
+            const int buf = bi & 1, blk = blk0 + bi, NB = block_NB(blk);
+            tc::mbar_wait(&acc_done[buf], (bi >> 1) & 1);
+            tc::fence_after_sync();
+            if (NS == 1) {          // thread r reads its accumulator row from TMEM
+                const int gm = m0 + tid;
+                for (int c0 = 0; c0 < NB; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld_x32(lane_addr + 256 * buf + c0, v);
+                    tc::tmem_ld_wait();
+                    if (gm < M) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const int gn = blk * 256 + c0 + q;
+                            if (c0 + q < NB && gn < N) {
+                                float f = __uint_as_float(v[q]) + (P.bias ? P.bias[gn] : 0.0f);
+                                if (P.act == 1) f = silu_f(f);
+                                if (P.R) f += P.R[(size_t)gm * P.ldr + gn];
+                                P.Y[(size_t)gm * P.ldy + gn] = f;
+                            }
+                        }
+                    }
+                }
+            } else {                // lanes [32w, 32w+16) = hi rows, [32w+16, 32w+32) = lo rows of tile rows [16w, 16w+16)
+                const int ra = 16 * warp + (lane >> 2), cp = 2 * (lane & 3);
+                const bool vec2 = (P.ldy & 1) == 0 && (!P.R || (P.ldr & 1) == 0);      // 8-byte accesses possible
+                for (int c0 = 0; c0 < NB; c0 += 64) {
+                    uint32_t v0[32], v1[32];
+                    tc::tmem_ld_16x256b_x8(lane_addr + 256 * buf + c0, v0);
+                    tc::tmem_ld_16x256b_x8(lane_addr + (16u << 16) + 256 * buf + c0, v1);
+                    // bias of this lane's column pairs: independent loads, in flight with the TMEM reads
+                    float2 bz[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int gn = blk * 256 + c0 + 8 * i + cp;
+                        bz[i] = make_float2(0.f, 0.f);
+                        if (P.bias && c0 + 8 * i < NB) {
+                            if (gn < N) bz[i].x = __ldg(P.bias + gn);
+                            if (gn + 1 < N) bz[i].y = __ldg(P.bias + gn + 1);
+                        }
+                    }
+                    tc::tmem_ld_wait();
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int gm = m0 + ra + 8 * h;
+                        if (gm < M) {
+                            float2 f[8], rz[8];
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            if (gm < M && gn + e < N) {
-                                float f = __uint_as_float(v0[4 * i + 2 * h + e]) + __uint_as_float(v1[4 * i + 2 * h + e]) +
-                                          (bias ? bias[gn + e] : 0.0f);
-                                if (act == 1) f = silu_f(f);
-                                if (R) f += R[(size_t)gm * ldr + gn + e];
-                                Y[(size_t)gm * ldy + gn + e] = f;
+                            for (int i = 0; i < 8; ++i) {
+                                const int gn = blk * 256 + c0 + 8 * i + cp;
+                                rz[i] = make_float2(0.f, 0.f);
+                                if (P.R && c0 + 8 * i < NB) {
+                                    const float* rp = P.R + (size_t)gm * P.ldr + gn;
+                                    if (vec2 && gn + 1 < N) rz[i] = *reinterpret_cast<const float2*>(rp);
+                                    else { if (gn < N) rz[i].x = rp[0]; if (gn + 1 < N) rz[i].y = rp[1]; }
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                f[i].x = __uint_as_float(v0[4 * i + 2 * h]) + __uint_as_float(v1[4 * i + 2 * h]) + bz[i].x;
+                                f[i].y = __uint_as_float(v0[4 * i + 2 * h + 1]) + __uint_as_float(v1[4 * i + 2 * h + 1]) + bz[i].y;
+                                if (P.act == 1) { f[i].x = ws::silu_acc(f[i].x); f[i].y = ws::silu_acc(f[i].y); }
+                                f[i].x += rz[i].x; f[i].y += rz[i].y;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int gn = blk * 256 + c0 + 8 * i + cp;
+                                if (c0 + 8 * i < NB) {
+                                    float* yp = P.Y + (size_t)gm * P.ldy + gn;
+                                    if (vec2 && gn + 1 < N) *reinterpret_cast<float2*>(yp) = f[i];
+                                    else { if (gn < N) yp[0] = f[i].x; if (gn + 1 < N) yp[1] = f[i].y; }
+                                }
                             }
                         }
                     }
                 }
             }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_free[buf]);
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
 }
 
 template <int NS>
 static size_t tc_linear_smem(int K, int NB) {
     using C = ws::Cfg<128 / NS, NS, 1>;
     const int ksteps = (K + 15) / 16;
-    return (((size_t)2 * ksteps * C::KCS + 127) & ~(size_t)127) + (size_t)TCG_STAGES * NS * 2 * (NB / 8) * 128 + (2 * TCG_STAGES + 1) * 8 + 16;
+    return (((size_t)2 * ksteps * C::KCS + 127) & ~(size_t)127) + (size_t)TCG_STAGES * NS * 2 * (NB / 8) * 128 + (2 * TCG_STAGES + 5) * 8 + 16;
 }
 
 // Wp: packed by pack_tc_weight(W[N,K], split = (nsplit == 2)) -> for each 256-row block nb: [ksteps][hi(, lo)][2][NB/8][8][8]
 // bf16, NB = rows of the block rounded up to 16 (all blocks but the last have NB = 256).
-// X rows must be 16-byte aligned (ldx % 4 == 0).
+// X rows must be 16-byte aligned (ldx % 4 == 0).  Up to two problems per launch (blockIdx.z).
 template <int NS>
-static int launch_tc_linear_ns(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y,
-                               int ldy, int M, int K, int N, int act, cudaStream_t st) {
-    const int NB = N >= 256 ? 256 : (N + 15) / 16 * 16;
-    const int nblocks = cdiv(N, 256);
-    const size_t smem = tc_linear_smem<NS>(K, NB);
-    KPD_REQUIRE(smem <= 227 * 1024, "tc_linear: K=%d needs %zu B of shared memory", K, smem);
-    KPD_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "tc_linear: X rows must be 16-byte aligned (ldx=%d)", ldx);
+static int launch_tc_batch_ns(TcLinBatch& B, int nprob, cudaStream_t st) {
+    int maxM = 0, maxBlocks = 0;
+    B.NBmax = 16; B.kmax = 16;
+    for (int i = 0; i < nprob; ++i) {
+        const TcLinProblem& p = B.p[i];
+        KPD_REQUIRE(p.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0, "tc_linear: X rows must be 16-byte aligned (ldx=%d)", p.ldx);
+        const int NB = p.N >= 256 ? 256 : (p.N + 15) / 16 * 16;
+        if (NB > B.NBmax) B.NBmax = NB;
+        if (p.K > B.kmax) B.kmax = p.K;
+        if (p.M > maxM) maxM = p.M;
+        if (cdiv(p.N, 256) > maxBlocks) maxBlocks = cdiv(p.N, 256);
+    }
+    if (maxM <= 0) return 0;
+    const size_t smem = tc_linear_smem<NS>(B.kmax, B.NBmax);
+    KPD_REQUIRE(smem <= 227 * 1024, "tc_linear: K=%d needs %zu B of shared memory", B.kmax, smem);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         KPD_REQUIRE(e == cudaSuccess, "tc_linear: cannot set %zu B shared memory: %s", smem, cudaGetErrorString(e));
         configured = smem;
     }
-    tc_linear_kernel<NS><<<dim3(cdiv(M, 128 / NS), nblocks), 128, smem, st>>>(X, ldx, static_cast<const uint4*>(Wp), bias, R, ldr,
-                                                                             Y, ldy, M, K, N, NB, act);
+    // column blocks per CTA: keep the launch near one wave of 148 CTAs while re-using each staged A tile
+    const int row_tiles = cdiv(maxM, 128 / NS) * nprob;
+    int groups = 148 / (row_tiles > 0 ? row_tiles : 1);
+    if (groups < 1) groups = 1;
+    if (groups > maxBlocks) groups = maxBlocks;
+    B.bpc = cdiv(maxBlocks, groups);
+    tc_linear_kernel<NS><<<dim3(cdiv(maxM, 128 / NS), cdiv(maxBlocks, B.bpc), nprob), TCG_THREADS, smem, st>>>(B);
     return check_launch("tc_linear_kernel");
+}
+
+int launch_tc_batch(TcLinBatch& B, int nprob, int nsplit, cudaStream_t st) {
+    KPD_REQUIRE(nsplit == 1 || nsplit == 2, "tc_linear: nsplit must be 1 (bf16) or 2 (bf16x3)");
+    KPD_REQUIRE(nprob >= 1 && nprob <= 2, "tc_linear: 1 or 2 problems per launch");
+    return nsplit == 1 ? launch_tc_batch_ns<1>(B, nprob, st) : launch_tc_batch_ns<2>(B, nprob, st);
+}
+
+TcLinProblem tc_problem(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y, int ldy,
+                        int M, int K, int N, int act) {
+    TcLinProblem p;
+    p.X = X; p.Wp = static_cast<const uint4*>(Wp); p.bias = bias; p.R = R; p.Y = Y;
+    p.ldx = ldx; p.ldr = ldr; p.ldy = ldy; p.M = M; p.K = K; p.N = N; p.act = act;
+    return p;
 }
 
 int launch_tc_linear(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y,
                      int ldy, int M, int K, int N, int act, int nsplit, cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
-    KPD_REQUIRE(nsplit == 1 || nsplit == 2, "tc_linear: nsplit must be 1 (bf16) or 2 (bf16x3)");
-    return nsplit == 1 ? launch_tc_linear_ns<1>(X, ldx, Wp, bias, R, ldr, Y, ldy, M, K, N, act, st)
-                       : launch_tc_linear_ns<2>(X, ldx, Wp, bias, R, ldr, Y, ldy, M, K, N, act, st);
+    TcLinBatch B;
+    memset(&B, 0, sizeof(B));
+    B.p[0] = tc_problem(X, ldx, Wp, bias, R, ldr, Y, ldy, M, K, N, act);
+    return launch_tc_batch(B, 1, nsplit, st);
 }
 
 }  // namespace kpd
