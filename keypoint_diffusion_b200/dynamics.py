@@ -89,9 +89,10 @@ class LigRecDynamics(_DynamicsBase):
         self.update_kp_feat, self.norm, self.ll_k, self.kl_k = update_kp_feat, norm, ll_k, kl_k
         # the reference's division by z never reaches the graph; False reproduces that
         self.message_norm_effective = message_norm_effective
-        # 'fp32': SIMT kernels in the reference's own arithmetic; 'bf16x3': tcgen05 tensor cores with split (hi, lo)
-        # bf16 operands and fp32 accumulation, inside the 1e-4 parity bar
-        self.precision = "fp32"
+        # 'bf16x3' (default): tcgen05 tensor cores with split (hi, lo) bf16 operands and fp32 accumulation, inside the
+        # 1e-4 parity bar; 'fp32': SIMT kernels in the reference's own arithmetic (also what a hidden width the
+        # tensor-core tiles do not support falls back to -- still CUDA, never the CPU)
+        self.precision = "bf16x3"
 
     def set_precision(self, precision: str):
         if precision not in ops.EgnnModel.PRECISIONS:
@@ -110,8 +111,9 @@ class LigRecDynamics(_DynamicsBase):
                                      message_norm=self.message_norm, device=device,
                                      z_effective=self.message_norm_effective)
             st.model_key = key
-        if st.model.precision != self.precision:
-            st.model.set_precision(self.precision)
+        want = self.precision if st.model.tc_blob2 is not None else "fp32"
+        if st.model.precision != want:
+            st.model.set_precision(want)
         return st.model
 
     @torch.no_grad()
@@ -145,10 +147,11 @@ class LigRecDynamicsGVP(_DynamicsBase):
         self.ll_k, self.kl_k = ll_k, kl_k
         self.n_message_gvps, self.n_update_gvps, self.n_noise_gvps = n_message_gvps, n_update_gvps, n_noise_gvps
         self.dropout = dropout   # eval-time no-op (models/gvp.py:133-134); sampling never trains
-        # 'fp32': SIMT kernels in the reference's own arithmetic; 'bf16x3': tcgen05 tensor cores with split
-        # (hi, lo) bf16 operands and fp32 accumulation, inside the 1e-4 parity bar; 'bf16': tcgen05 with plain
-        # bf16 operands (the north star's separately-reported bf16 GEMM mode)
-        self.precision = "fp32"
+        # 'bf16x3' (default): tcgen05 tensor cores with split (hi, lo) bf16 operands and fp32 accumulation, inside the
+        # 1e-4 parity bar; 'fp32': SIMT kernels in the reference's own arithmetic (also the fallback for scalar widths
+        # the tensor-core tiles do not support); 'bf16': tcgen05 with plain bf16 operands (the north star's
+        # separately-reported bf16 GEMM mode)
+        self.precision = "bf16x3"
 
     def set_precision(self, precision: str):
         if precision not in ops.GvpModel.PRECISIONS:
@@ -166,10 +169,11 @@ class LigRecDynamicsGVP(_DynamicsBase):
                                     n_convs=self.n_convs, n_hidden_scalars=self.n_hidden_scalars,
                                     update_kp=self.update_kp, n_message_gvps=self.n_message_gvps,
                                     n_update_gvps=self.n_update_gvps, n_noise_gvps=self.n_noise_gvps,
-                                    message_norm=self.message_norm, device=device, precision=self.precision)
+                                    message_norm=self.message_norm, device=device)
             st.model_key = key
-        if st.model.precision != self.precision:
-            st.model.set_precision(self.precision)
+        want = self.precision if st.model.tc_blob2 is not None else "fp32"
+        if st.model.precision != want:
+            st.model.set_precision(want)
         return st.model
 
     @torch.no_grad()
