@@ -343,47 +343,57 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             float* part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
             float* part1 = a.part + ((size_t)blockIdx.x * 2 + 1) * L.pw;
             if (br == 0) {
-                const int npair = nmain >> 1;
-                const int grp = tid / 128, p = tid & 127;           // two groups of 128 threads split the segments
-                if (p < npair) {
-                    const int col = 2 * p;
-                    const unsigned char* p0 = m.A[0] + (size_t)(col >> 3) * C::KCS + (col & 7) * 2;
-                    for (int sg = grp; sg < nseg; sg += NT_SIMT / 128) {
+                // one warp per group of segments, one lane per 8-column chunk: 16-byte reads of the hi and lo planes
+                // (bank-conflict free thanks to the +16 B chunk stride), 32-byte coalesced stores
+                const int nchunk = nmain >> 3;
+                if (lane < nchunk) {
+                    const unsigned char* p0 = m.A[0] + (size_t)lane * C::KCS;
+                    for (int sg = warp; sg < nseg; sg += NW) {
                         const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
-                        float s0 = 0.f, s1 = 0.f;
+                        float acc[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
                         for (int j = r0; j < r1; ++j) {
                             const uint32_t o2 = ws::row_off<C>(j);
-                            const uint32_t wh = *reinterpret_cast<const uint32_t*>(p0 + o2), wl = *reinterpret_cast<const uint32_t*>(p0 + o2 + 256);
+                            const uint4 wh = *reinterpret_cast<const uint4*>(p0 + o2), wl = *reinterpret_cast<const uint4*>(p0 + o2 + 256);
                             const float at = m.att[j];
-                            s0 = fmaf(__uint_as_float(wh << 16) + __uint_as_float(wl << 16), at, s0);
-                            s1 = fmaf(__uint_as_float(wh & 0xffff0000u) + __uint_as_float(wl & 0xffff0000u), at, s1);
+                            acc[0] = fmaf(__uint_as_float(wh.x << 16) + __uint_as_float(wl.x << 16), at, acc[0]);
+                            acc[1] = fmaf(__uint_as_float(wh.x & 0xffff0000u) + __uint_as_float(wl.x & 0xffff0000u), at, acc[1]);
+                            acc[2] = fmaf(__uint_as_float(wh.y << 16) + __uint_as_float(wl.y << 16), at, acc[2]);
+                            acc[3] = fmaf(__uint_as_float(wh.y & 0xffff0000u) + __uint_as_float(wl.y & 0xffff0000u), at, acc[3]);
+                            acc[4] = fmaf(__uint_as_float(wh.z << 16) + __uint_as_float(wl.z << 16), at, acc[4]);
+                            acc[5] = fmaf(__uint_as_float(wh.z & 0xffff0000u) + __uint_as_float(wl.z & 0xffff0000u), at, acc[5]);
+                            acc[6] = fmaf(__uint_as_float(wh.w << 16) + __uint_as_float(wl.w << 16), at, acc[6]);
+                            acc[7] = fmaf(__uint_as_float(wh.w & 0xffff0000u) + __uint_as_float(wl.w & 0xffff0000u), at, acc[7]);
                         }
                         const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
                         const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
-                        float* t = from_prev ? part0 + col : into_next ? part1 + col : a.hn + (size_t)m.dst_s[r0] * Hp + col;
-                        t[0] = s0; t[1] = s1;
+                        float* t = (from_prev ? part0 : into_next ? part1 : a.hn + (size_t)m.dst_s[r0] * Hp) + 8 * lane;
+                        *reinterpret_cast<float4*>(t) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        *reinterpret_cast<float4*>(t + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
                     }
                 }
-                if (tid < nlo) {                                    // the leftover feature columns
-                    const int col = nmain + tid;
-                    for (int sg = 0; sg < nseg; ++sg) {
-                        const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
-                        float s = 0.f;
-                        for (int j = r0; j < r1; ++j) s = fmaf(m.lo[j * 4 + tid], m.att[j], s);
-                        const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
-                        const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
-                        float* t = from_prev ? part0 + col : into_next ? part1 + col : a.hn + (size_t)m.dst_s[r0] * Hp + col;
-                        t[0] = s;
-                    }
-                }
-            } else if (tid < 3) {                                   // x messages; their partial slots follow the Hp feature columns
-                for (int sg = 0; sg < nseg; ++sg) {
+                // the leftover feature columns: one thread per (segment, column)
+                for (int i = tid; i < nseg * nlo; i += NT_SIMT) {
+                    const int sg = i / nlo, cc = i - sg * nlo;
                     const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
                     float s = 0.f;
-                    for (int j = r0; j < r1; ++j) s += m.xm[3 * j + tid];
+                    for (int j = r0; j < r1; ++j) s = fmaf(m.lo[j * 4 + cc], m.att[j], s);
                     const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
                     const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
-                    float* t = from_prev ? part0 + Hp + tid : into_next ? part1 + Hp + tid : a.xn + (size_t)m.dst_s[r0] * 4 + tid;
+                    float* t = from_prev ? part0 : into_next ? part1 : a.hn + (size_t)m.dst_s[r0] * Hp;
+                    t[nmain + cc] = s;
+                }
+            } else {
+                // x messages: one thread per (segment, component); their partial slots follow the Hp feature columns
+                for (int i = tid; i < nseg * 3; i += NT_SIMT) {
+                    const int sg = i / 3, cc = i - sg * 3;
+                    const int r0 = m.seg[sg], r1 = m.seg[sg + 1];
+                    float s = 0.f;
+                    for (int j = r0; j < r1; ++j) s += m.xm[3 * j + cc];
+                    const bool from_prev = (r0 == 0) && (m.rp[2 * r0] < tile_begin);
+                    const bool into_next = (r1 == n) && (m.rp[2 * r0 + 1] > tile_begin + n);
+                    float* t = from_prev ? part0 + Hp + cc : into_next ? part1 + Hp + cc : a.xn + (size_t)m.dst_s[r0] * 4 + cc;
                     t[0] = s;
                 }
             }

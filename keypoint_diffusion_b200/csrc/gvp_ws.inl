@@ -770,48 +770,52 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         ws::vf_store(v, VS + Ln.row * ws::VS_LD, Vd, Ln.t);
         ws::simt_bar<C>();
         {
-            constexpr int GRP = 160;
-            constexpr int NGRP = C::NT_SIMT / GRP;
-            const int grp = tid / GRP, p = tid - grp * GRP;
-            const int nsp = Sd >> 1, nvp = (Vd * 3 + 1) >> 1;
             const int nseg = m.seg[C::R + 1];
             float* part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
             float* part1 = a.part + ((size_t)blockIdx.x * 2 + 1) * L.pw;
-            if (grp < NGRP && p < nsp + nvp) {
-                const bool scal = p < nsp;
-                const int col = scal ? 2 * p : 2 * (p - nsp);
-                const bool has2 = scal || col + 1 < Vd * 3;
-                const unsigned char* p0 = m.A[0] + (size_t)(col >> 3) * C::KCS + (col & 7) * 2;
-                const unsigned char* p1 = m.A[1] + (size_t)(col >> 3) * C::KCS + (col & 7) * 2;
-                for (int sg = grp; sg < nseg; sg += NGRP) {
+            // scalars: one warp per group of segments, one lane per 8-column chunk: 16-byte reads of the plane(s)
+            // (bank-conflict free thanks to the +16 B chunk stride), 32-byte coalesced stores
+            if (lane < (Sd >> 3)) {
+                const unsigned char* p0 = m.A[0] + (size_t)lane * C::KCS;
+                for (int sg = warp; sg < nseg; sg += C::NW) {
                     const int ra = m.seg[sg], rb = m.seg[sg + 1];
-                    float s0 = 0.f, s1 = 0.f;
-                    if (scal) {
-                        for (int j = ra; j < rb; ++j) {
-                            const uint32_t ro = ws::row_off<C>(j);
-                            const uint32_t wv = *reinterpret_cast<const uint32_t*>(p0 + ro);
-                            float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
-                            if (C::NS == 2) {
-                                const uint32_t wl = *reinterpret_cast<const uint32_t*>(p1 + ro);
-                                x0 += __uint_as_float(wl << 16); x1 += __uint_as_float(wl & 0xffff0000u);
-                            }
-                            s0 += x0; s1 += x1;
+                    float acc[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                    for (int j = ra; j < rb; ++j) {
+                        const uint32_t ro = ws::row_off<C>(j);
+                        const uint4 wh = *reinterpret_cast<const uint4*>(p0 + ro);
+                        float x[8] = {__uint_as_float(wh.x << 16), __uint_as_float(wh.x & 0xffff0000u), __uint_as_float(wh.y << 16),
+                                      __uint_as_float(wh.y & 0xffff0000u), __uint_as_float(wh.z << 16), __uint_as_float(wh.z & 0xffff0000u),
+                                      __uint_as_float(wh.w << 16), __uint_as_float(wh.w & 0xffff0000u)};
+                        if (C::NS == 2) {
+                            const uint4 wl = *reinterpret_cast<const uint4*>(p0 + ro + 256);
+                            x[0] += __uint_as_float(wl.x << 16); x[1] += __uint_as_float(wl.x & 0xffff0000u);
+                            x[2] += __uint_as_float(wl.y << 16); x[3] += __uint_as_float(wl.y & 0xffff0000u);
+                            x[4] += __uint_as_float(wl.z << 16); x[5] += __uint_as_float(wl.z & 0xffff0000u);
+                            x[6] += __uint_as_float(wl.w << 16); x[7] += __uint_as_float(wl.w & 0xffff0000u);
                         }
-                    } else {
-                        for (int j = ra; j < rb; ++j) {
-                            const float2 x = *reinterpret_cast<const float2*>(VS + j * ws::VS_LD + col);
-                            s0 += x.x; s1 += x.y;
-                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[q] += x[q];
                     }
                     const bool from_prev = (ra == 0) && (m.rp[2 * ra] < tile_begin);
                     const bool into_next = (rb == n) && (m.rp[2 * ra + 1] > tile_begin + n);
-                    float* t;
-                    if (from_prev) t = part0 + (scal ? col : Sd + col);
-                    else if (into_next) t = part1 + (scal ? col : Sd + col);
-                    else t = scal ? a.sm + (size_t)m.dst_s[ra] * Sd + col : a.vm + (size_t)m.dst_s[ra] * (Vd * 3) + col;
-                    t[0] = s0;
-                    if (has2) t[1] = s1;
+                    float* t = (from_prev ? part0 : into_next ? part1 : a.sm + (size_t)m.dst_s[ra] * Sd) + 8 * lane;
+                    *reinterpret_cast<float4*>(t) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4*>(t + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 }
+            }
+            // vectors: one thread per (segment, vector column)
+            const int nvc = Vd * 3;
+            for (int i = tid; i < nseg * nvc; i += C::NT_SIMT) {
+                const int sg = i / nvc, col = i - sg * nvc;
+                const int ra = m.seg[sg], rb = m.seg[sg + 1];
+                float s0 = 0.f;
+                for (int j = ra; j < rb; ++j) s0 += VS[j * ws::VS_LD + col];
+                const bool from_prev = (ra == 0) && (m.rp[2 * ra] < tile_begin);
+                const bool into_next = (rb == n) && (m.rp[2 * ra + 1] > tile_begin + n);
+                float* t = from_prev ? part0 + Sd + col : into_next ? part1 + Sd + col : a.vm + (size_t)m.dst_s[ra] * nvc + col;
+                t[0] = s0;
             }
         }
         TC_T(e4);
