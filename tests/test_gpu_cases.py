@@ -34,7 +34,10 @@ def _inputs(pockets, n_lig, atom_nf, seed, with_v):
     return d
 
 
-def _run_both(arch, sd, kw, atom_nf, rec_nf, inputs, tvals=(0.3,), per_complex_t=False, z_effective=False):
+MODES = ["fp32", "bf16x3"]      # SIMT kernels / tcgen05 kernels with split bf16 operands: same 1e-4 bar
+
+
+def _run_both(arch, sd, kw, atom_nf, rec_nf, inputs, tvals=(0.3,), per_complex_t=False, z_effective=False, mode="fp32"):
     from test_gpu_parity import build_model, device_inputs
     from keypoint_diffusion_b200 import ops
     dev = _dev()
@@ -47,6 +50,9 @@ def _run_both(arch, sd, kw, atom_nf, rec_nf, inputs, tvals=(0.3,), per_complex_t
                               message_norm=kw["message_norm"], device=dev, z_effective=z_effective)
     else:
         model = build_model(arch, sd, kw, atom_nf, rec_nf, dev)
+    if mode != "fp32":
+        assert model.tc_blob2 is not None, "this case should be able to run on the tensor cores"
+        model.set_precision(mode)
     batch, kk, t_in = device_inputs(inputs, dev)
     gp = ops.GraphParams.from_module(kw.get("ll_k", 0), kw.get("kl_k", 0), kw["graph_cutoffs"])
     with_lk = bool(kw.get("update_kp_feat", kw.get("update_kp", False)))
@@ -71,7 +77,8 @@ def _run_both(arch, sd, kw, atom_nf, rec_nf, inputs, tvals=(0.3,), per_complex_t
     return out
 
 
-def test_egnn_all_atom_rows_span_many_tiles():
+@pytest.mark.parametrize("mode", MODES)
+def test_egnn_all_atom_rows_span_many_tiles(mode):
     """~300 pocket atoms as keypoints (fixed encoder): a ligand atom receives hundreds of kl edges, so
     its CSR row spans several 64-edge tiles and the per-tile partial slots are summed in tile order;
     includes a single-atom ligand (no ll edges, fewer than k candidates)."""
@@ -82,15 +89,16 @@ def test_egnn_all_atom_rows_span_many_tiles():
     sd = P.init_state_dict(P.egnn_dynamics_shapes(10, 10, 2, 32, True, True), seed=11, coord_gain=0.3)
     pockets = [synthetic.all_atom_pocket(i, 300, 10, 0, 3.5) for i in range(2)]
     inputs = _inputs(pockets, [20, 5, 1, 33], 10, seed=3, with_v=False)
-    (eh, ex, graphs, edges), = _run_both("egnn", sd, kw, 10, 10, inputs)
+    (eh, ex, graphs, edges), = _run_both("egnn", sd, kw, 10, 10, inputs, mode=mode)
     rp = graphs.kl.rowptr.cpu()
     assert int((rp[1:] - rp[:-1]).max()) > 3 * 64, "test should exercise rows spanning > 3 tiles"
-    print(f"all-atom egnn: max kl in-degree {int((rp[1:] - rp[:-1]).max())}, rel_err {eh:.2e} {ex:.2e}")
+    print(f"all-atom egnn [{mode}]: max kl in-degree {int((rp[1:] - rp[:-1]).max())}, rel_err {eh:.2e} {ex:.2e}")
     assert eh < TOL and ex < TOL
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("norm", ["mean", 0, 10.0])
-def test_gvp_ca_like_empty_kk_and_norm_modes(norm):
+def test_gvp_ca_like_empty_kk_and_norm_modes(norm, mode):
     """C-alpha style pocket: 42 nodes >= 3.8 A apart, kk = radius 3.5 graph => (almost) no kk edges, so
     keypoints with zero in-degree and an empty edge type are exercised in all three norm modes."""
     from oracle import params as P
@@ -106,13 +114,14 @@ def test_gvp_ca_like_empty_kk_and_norm_modes(norm):
         pk.kp_v = 0.1 * torch.randn(pk.n_kp, 16, 3, generator=torch.Generator().manual_seed(5))
     inputs = _inputs(pockets, [20, 1, 44, 9], 10, seed=4, with_v=True)
     assert inputs["kk_src"].numel() < 8
-    (eh, ex, _, _), = _run_both("gvp", sd, kw, 10, 10, inputs)
-    print(f"gvp ca-like norm={norm}: rel_err {eh:.2e} {ex:.2e}")
+    (eh, ex, _, _), = _run_both("gvp", sd, kw, 10, 10, inputs, mode=mode)
+    print(f"gvp ca-like norm={norm} [{mode}]: rel_err {eh:.2e} {ex:.2e}")
     assert eh < TOL and ex < TOL
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("message_norm", [0.0, 3.0])
-def test_egnn_intended_normalisation_flag(message_norm):
+def test_egnn_intended_normalisation_flag(message_norm, mode):
     """z_effective=True divides h_neigh / x_neigh by z (what the reference's comments intend, DESIGN N11)."""
     from oracle import params as P
     from keypoint_diffusion_b200 import synthetic
@@ -121,11 +130,11 @@ def test_egnn_intended_normalisation_flag(message_norm):
     sd = P.init_state_dict(P.egnn_dynamics_shapes(10, 24, 3, 48, True, True), seed=13, coord_gain=0.3)
     pockets = [synthetic.keypoint_pocket(i, 20, 24, 0, 8.0) for i in range(3)]
     inputs = _inputs(pockets, [20, 8, 35], 10, seed=6, with_v=False)
-    res = _run_both("egnn", sd, kw, 10, 24, inputs, z_effective=True, per_complex_t=True)
+    res = _run_both("egnn", sd, kw, 10, 24, inputs, z_effective=True, per_complex_t=True, mode=mode)
     for eh, ex, _, _ in res:
         assert eh < TOL and ex < TOL
     # and the flag matters: the default (as-executed) result differs
-    res0 = _run_both("egnn", sd, kw, 10, 24, inputs, z_effective=False)
+    res0 = _run_both("egnn", sd, kw, 10, 24, inputs, z_effective=False, mode=mode)
     assert res0[0][0] < TOL
 
 
