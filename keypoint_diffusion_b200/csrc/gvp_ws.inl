@@ -844,8 +844,20 @@ __device__ __forceinline__ void seg_gather8(const float* __restrict__ out, int l
     for (int t = t0 + 1; t <= t1; ++t) add(part + ((size_t)t * 2 + 0) * pw + c0);
 }
 
-// LayerNorm over a row held as 8 consecutive features per lane (features 8*lane .. 8*lane+7; lanes beyond Sdim idle)
-__device__ __forceinline__ void warp_layernorm8(float (&x)[8], bool act, int Sdim, const float* w, const float* b, int lane) {
+// LayerNorm over a row held as 8 consecutive features per lane (features 8*lane .. 8*lane+7; lanes beyond Sdim idle);
+// w8 / b8: this lane's slice of the affine parameters, loaded once per warp (ln_params8)
+__device__ __forceinline__ void ln_params8(const float* __restrict__ w, const float* __restrict__ b, bool act, int lane,
+                                           float (&w8)[8], float (&b8)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { w8[i] = 0.f; b8[i] = 0.f; }
+    if (act) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + 8 * lane)), w1 = __ldg(reinterpret_cast<const float4*>(w + 8 * lane + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + 8 * lane)), b1 = __ldg(reinterpret_cast<const float4*>(b + 8 * lane + 4));
+        w8[0] = w0.x; w8[1] = w0.y; w8[2] = w0.z; w8[3] = w0.w; w8[4] = w1.x; w8[5] = w1.y; w8[6] = w1.z; w8[7] = w1.w;
+        b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+    }
+}
+__device__ __forceinline__ void warp_layernorm8(float (&x)[8], bool act, int Sdim, const float (&w8)[8], const float (&b8)[8]) {
     float s = 0.f;
     if (act) {
 #pragma unroll
@@ -862,14 +874,8 @@ __device__ __forceinline__ void warp_layernorm8(float (&x)[8], bool act, int Sdi
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const float rstd = 1.0f / sqrtf(v / (float)Sdim + 1e-5f);
-    if (act) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * lane), w1 = *reinterpret_cast<const float4*>(w + 8 * lane + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(b + 8 * lane), b1 = *reinterpret_cast<const float4*>(b + 8 * lane + 4);
-        x[0] = (x[0] - mean) * rstd * w0.x + b0.x; x[1] = (x[1] - mean) * rstd * w0.y + b0.y;
-        x[2] = (x[2] - mean) * rstd * w0.z + b0.z; x[3] = (x[3] - mean) * rstd * w0.w + b0.w;
-        x[4] = (x[4] - mean) * rstd * w1.x + b1.x; x[5] = (x[5] - mean) * rstd * w1.y + b1.y;
-        x[6] = (x[6] - mean) * rstd * w1.z + b1.z; x[7] = (x[7] - mean) * rstd * w1.w + b1.w;
-    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (x[i] - mean) * rstd * w8[i] + b8[i];
 }
 
 // vector part of GVPLayerNorm (gvp.py:163-165) on the register-resident vectors of one row:
@@ -974,6 +980,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         //      features + messages / norm, LayerNorm -> residual (global) + A
         {
             const int lg = a.edge_tile == 128 ? 7 : 6;
+            float lw[8], lb[8];
+            ws::ln_params8(a.mln_w, a.mln_b, act, lane, lw, lb);
             float x[RPW][8];
             float4 ga[RPW][2][2], sa[RPW][2];
 #pragma unroll
@@ -1012,17 +1020,17 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                             g8[0] += q0.x; g8[1] += q0.y; g8[2] += q0.z; g8[3] += q0.w;
                             g8[4] += q1.x; g8[5] += q1.y; g8[6] += q1.z; g8[7] += q1.w;
                         }
-                        const float cnt = a.norm_mode == 1 ? (float)(r1 - r0) : 1.0f;
+                        const float icnt = a.norm_mode == 1 ? 1.0f / (float)(r1 - r0) : 1.0f;      // fn.mean per edge type
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) msg[i] += a.norm_mode == 1 ? g8[i] / cnt : g8[i];
+                        for (int i = 0; i < 8; ++i) msg[i] = fmaf(g8[i], icnt, msg[i]);
                     }
                 }
-                const float nv = nvs[r];
-                x[j][0] = sa[j][0].x + msg[0] / nv; x[j][1] = sa[j][0].y + msg[1] / nv;
-                x[j][2] = sa[j][0].z + msg[2] / nv; x[j][3] = sa[j][0].w + msg[3] / nv;
-                x[j][4] = sa[j][1].x + msg[4] / nv; x[j][5] = sa[j][1].y + msg[5] / nv;
-                x[j][6] = sa[j][1].z + msg[6] / nv; x[j][7] = sa[j][1].w + msg[7] / nv;
-                ws::warp_layernorm8(x[j], act, Sd, a.mln_w, a.mln_b, lane);
+                const float inv = 1.0f / nvs[r];          // (the tensor-core modes multiply by reciprocals)
+                x[j][0] = fmaf(msg[0], inv, sa[j][0].x); x[j][1] = fmaf(msg[1], inv, sa[j][0].y);
+                x[j][2] = fmaf(msg[2], inv, sa[j][0].z); x[j][3] = fmaf(msg[3], inv, sa[j][0].w);
+                x[j][4] = fmaf(msg[4], inv, sa[j][1].x); x[j][5] = fmaf(msg[5], inv, sa[j][1].y);
+                x[j][6] = fmaf(msg[6], inv, sa[j][1].z); x[j][7] = fmaf(msg[7], inv, sa[j][1].w);
+                ws::warp_layernorm8(x[j], act, Sd, lw, lb);
                 if (act) {
                     if (r < n) {
                         float* sp = a.s + (size_t)(n0 + r) * Sd + 8 * lane;
@@ -1043,7 +1051,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
             ws::vf_zero(msg);
             for (int e = 0; e < a.n_et; ++e) {
                 const int r0 = meta[4 * Ln.row + 2 * e], r1 = meta[4 * Ln.row + 2 * e + 1];
-                const float cnt = a.norm_mode == 1 ? (float)max(r1 - r0, 1) : 1.0f;
+                const float icnt = a.norm_mode == 1 ? 1.0f / (float)max(r1 - r0, 1) : 1.0f;
                 if (r1 > r0) {
                     const int t0 = r0 / a.edge_tile, t1 = (r1 - 1) / a.edge_tile;
                     ws::VF gsum;
@@ -1066,23 +1074,24 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                         for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
                             for (int ee = 0; ee < 2; ++ee)
-                                msg.x[c][ss][ee] += a.norm_mode == 1 ? gsum.x[c][ss][ee] / cnt : gsum.x[c][ss][ee];
+                                msg.x[c][ss][ee] = fmaf(gsum.x[c][ss][ee], icnt, msg.x[c][ss][ee]);
                 }
             }
             ws::vf_load(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
+            const float inv_nv = 1.0f / nv;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
-                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] += msg.x[c][ss][ee] / nv;
-            const float vn = ws::vec_norm(v, Vd, Ln);
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] = fmaf(msg.x[c][ss][ee], inv_nv, v.x[c][ss][ee]);
+            const float ivn = 1.0f / ws::vec_norm(v, Vd, Ln);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
-                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] = v.x[c][ss][ee] / vn;
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] *= ivn;
             if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
         ws::publish(m.feats_ready);
@@ -1094,6 +1103,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         {
             float x[RPW][8];
             float4 sa[RPW][2];
+            float lw[8], lb[8];
+            ws::ln_params8(a.uln_w, a.uln_b, act, lane, lw, lb);
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
                 const int r = warp + C::NW * j;
@@ -1112,7 +1123,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                     x[j][0] += sa[j][0].x; x[j][1] += sa[j][0].y; x[j][2] += sa[j][0].z; x[j][3] += sa[j][0].w;
                     x[j][4] += sa[j][1].x; x[j][5] += sa[j][1].y; x[j][6] += sa[j][1].z; x[j][7] += sa[j][1].w;
                 }
-                ws::warp_layernorm8(x[j], act, Sd, a.uln_w, a.uln_b, lane);
+                ws::warp_layernorm8(x[j], act, Sd, lw, lb);
                 if (act && r < n) {
                     const size_t o = (size_t)(n0 + r) * Sd + 8 * lane;
                     *reinterpret_cast<float4*>(a.s + o) = make_float4(x[j][0], x[j][1], x[j][2], x[j][3]);
@@ -1131,13 +1142,13 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
                     for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] += res.x[c][ss][ee];
-            const float vn = ws::vec_norm(v, Vd, Ln);
+            const float ivn = 1.0f / ws::vec_norm(v, Vd, Ln);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
-                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] = v.x[c][ss][ee] / vn;
+                    for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] *= ivn;
             if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
         TC_T(n5t);
