@@ -238,6 +238,63 @@ __global__ void __launch_bounds__(128) egnn_node_prep_kernel(const EgnnNodePrep 
 
 #include "egnn_ws.inl"
 
+// the same node stage for the tensor-core mode: one warp per node, a lane per 8-feature chunk (float4 traffic, all
+// loads of a node in flight together); h_neigh starts at column off_neigh of the cat row (a multiple of 4: the packed
+// node_mlp.0 weight has matching zero columns, pack.pack_egnn_tc)
+__global__ void __launch_bounds__(256) egnn_node_prep_warp_kernel(const EgnnNodePrep a, int off_neigh) {
+    const int nd = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (nd >= a.n) return;
+    float z = 1.0f;
+    if (a.z_mode == 1) z = a.z_const;
+    else if (a.z_mode == 2) {
+        const int b = a.node_batch[nd];
+        const int p0 = a.ptr[b], p1 = a.ptr[b + 1];
+        int tot = 0;
+        for (int e = 0; e < a.n_et; ++e) tot += a.rowptr[e][p1] - a.rowptr[e][p0];
+        z = (float)tot / (float)(p1 - p0) + 1.0f;     // (:281-283)
+    }
+    const float iz = a.z_mode ? 1.0f / z : 1.0f;
+    int r0[2], r1[2];
+    for (int e = 0; e < 2; ++e) { r0[e] = e < a.n_et ? a.rowptr[e][nd] : 0; r1[e] = e < a.n_et ? a.rowptr[e][nd + 1] : 0; }
+    float* crow = a.cat + (size_t)nd * a.ldcat;
+    const float* hrow = a.h + (size_t)nd * a.Hp;
+    const int nfull = a.H >> 3;
+    if (lane < nfull) {
+        const float4 h0 = *reinterpret_cast<const float4*>(hrow + 8 * lane), h1 = *reinterpret_cast<const float4*>(hrow + 8 * lane + 4);
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int e = 0; e < a.n_et; ++e) {
+            if (r1[e] <= r0[e]) continue;
+            const int t0 = r0[e] / TE, t1 = (r1[e] - 1) / TE;
+            const float* p = t0 == t1 ? a.hn[e] + (size_t)nd * a.Hp : a.part[e] + ((size_t)t0 * 2 + 1) * a.pw;
+            for (int t = t0;; ++t) {
+                const float4 u0 = *reinterpret_cast<const float4*>(p + 8 * lane), u1 = *reinterpret_cast<const float4*>(p + 8 * lane + 4);
+                s[0] += u0.x; s[1] += u0.y; s[2] += u0.z; s[3] += u0.w; s[4] += u1.x; s[5] += u1.y; s[6] += u1.z; s[7] += u1.w;
+                if (t + 1 > t1 || t0 == t1) break;
+                p = a.part[e] + ((size_t)(t + 1) * 2 + 0) * a.pw;
+            }
+        }
+        *reinterpret_cast<float4*>(crow + 8 * lane) = h0;
+        *reinterpret_cast<float4*>(crow + 8 * lane + 4) = h1;
+        *reinterpret_cast<float4*>(crow + off_neigh + 8 * lane) = make_float4(s[0] * iz, s[1] * iz, s[2] * iz, s[3] * iz);
+        *reinterpret_cast<float4*>(crow + off_neigh + 8 * lane + 4) = make_float4(s[4] * iz, s[5] * iz, s[6] * iz, s[7] * iz);
+    }
+    // leftover features (H = 257: feature 256), the zero gap up to off_neigh, and x += x_neigh (:206)
+    for (int c = 8 * nfull + lane; c < a.H + 3; c += 32) {
+        if (c < a.H) {
+            float s = 0.f;
+            for (int e = 0; e < a.n_et; ++e) s += seg_gather(a.hn[e], a.Hp, a.part[e], a.pw, r0[e], r1[e], nd, c);
+            crow[c] = hrow[c];
+            crow[off_neigh + c] = s * iz;
+        } else {
+            const int k = c - a.H;
+            float s = 0.f;
+            for (int e = 0; e < a.n_et; ++e) s += seg_gather(a.xn[e], 4, a.part[e] + a.Hp, a.pw, r0[e], r1[e], nd, k);
+            a.x[3 * nd + k] += s * iz;
+        }
+    }
+    for (int c = a.H + lane; c < off_neigh; c += 32) crow[c] = 0.f;
+}
+
 }  // namespace kpd
 
 using namespace kpd;
@@ -286,7 +343,7 @@ static EgnnWs egnn_carve(const kpd_egnn_model* m, const kpd_batch* b, const int 
         w.part[e] = c.take<float>((int64_t)egnn_ntiles(caps[e]) * 2 * m->pw);
     }
     for (int nt = 0; nt < 2; ++nt) {
-        w.cat[nt] = c.take<float>((int64_t)N[nt] * (2 * m->H + 4));
+        w.cat[nt] = c.take<float>((int64_t)N[nt] * (m->Hp + m->H + 4));
         w.tmp1[nt] = c.take<float>((int64_t)N[nt] * m->Hp);
         w.y[nt] = c.take<float>((int64_t)N[nt] * m->Hp);
     }
@@ -514,7 +571,9 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
         prof_end(PROF_EGNN_EDGE, st);
         prof_begin(PROF_EGNN_NODE, st);
 
-        const int ldcat = (2 * H + 3) & ~3;
+        // tensor-core mode: h_neigh starts at the 4-aligned column Hp of the cat row (zero gap [H, Hp))
+        const int off_neigh = m->mode == 2 ? Hp : H;
+        const int ldcat = (off_neigh + H + 3) & ~3;
         for (int nt = 0; nt < m->n_upd; ++nt) {
             EgnnNodePrep a;
             memset(&a, 0, sizeof(a));
@@ -530,7 +589,10 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             a.z_const = m->cfg.message_norm;
             a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
             a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
-            if (a.n > 0) {
+            if (a.n > 0 && m->mode == 2) {
+                egnn_node_prep_warp_kernel<<<cdiv(a.n, 8), 256, 0, st>>>(a, off_neigh);
+                KPD_TRY(check_launch("egnn_node_prep_warp_kernel"));
+            } else if (a.n > 0) {
                 egnn_node_prep_kernel<<<a.n, 128, 0, st>>>(a);
                 KPD_TRY(check_launch("egnn_node_prep_kernel"));
             }
@@ -541,7 +603,7 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             memset(&T1, 0, sizeof(T1));
             memset(&T2, 0, sizeof(T2));
             for (int nt = 0; nt < m->n_upd; ++nt) {
-                T1.p[nt] = tc_problem(w.cat[nt], ldcat, W.Wn1P[nt], W.bn1[nt], nullptr, 0, w.tmp1[nt], Hp, N[nt], 2 * H, H, 1);
+                T1.p[nt] = tc_problem(w.cat[nt], ldcat, W.Wn1P[nt], W.bn1[nt], nullptr, 0, w.tmp1[nt], Hp, N[nt], off_neigh + H, H, 1);
                 T2.p[nt] = tc_problem(w.tmp1[nt], Hp, W.Wn2P[nt], W.bn2[nt], w.h[nt], Hp, w.y[nt], Hp, N[nt], H, H, 0);
             }
             KPD_TRY(launch_tc_batch(T1, m->n_upd, 2, st));

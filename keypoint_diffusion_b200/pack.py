@@ -216,7 +216,9 @@ def pack_egnn_tc(sd: Dict[str, torch.Tensor], *, hidden_nf, n_layers, update_kp_
             for mlp in ("edge_mlp", "coord_mlp"):
                 add(sd[f"{q}{mlp}.{et}.2.weight"].detach().float().cpu()[:nmain, :])
         for nt in upd:
-            add(sd[f"{q}node_mlp.{nt}.0.weight"].detach().float().cpu())
+            # the tensor-core node stage stores cat = [h (H) | zero gap up to Hp | h_neigh (H)]: matching zero columns
+            W1 = sd[f"{q}node_mlp.{nt}.0.weight"].detach().float().cpu()           # [H, 2H]
+            add(torch.cat([W1[:, :H], torch.zeros(H, Hp - H), W1[:, H:]], dim=1))
             add(sd[f"{q}node_mlp.{nt}.2.weight"].detach().float().cpu())
     return torch.cat(parts).to(device), offs
 
