@@ -1,5 +1,6 @@
 """Batch helpers with the reference's names (reference utils.py:81-170), on the duck-typed
-graph surface of hetero.HeteroBatch (or a real DGL heterograph)."""
+graph surface of hetero.HeteroBatch (or a real DGL heterograph), and the output decode that follows the
+sampling path (reference utils.py:11-21, test.py:199-209)."""
 from typing import Dict, List, Tuple
 
 import torch
@@ -41,4 +42,29 @@ def copy_graph(g, n_copies: int, lig_atoms_per_copy: torch.Tensor = None, batche
         edges = {et: tuple(t.clone() for t in g.edges(form="uv", etype=et)) for et in g.canonical_etypes}
         bne = {et: g.batch_num_edges(et).clone() for et in g.canonical_etypes}
         out.append(hetero.HeteroBatch(bnn, nd, edges, bne))
+    return out
+
+
+def write_xyz_file(coords, atom_types, filename=None):
+    """reference utils.py:11-21 (taken there from DiffSBDD): an XYZ block for one molecule; returns the text when
+    ``filename`` is None, else writes it."""
+    out = f"{len(coords)}\n\n"
+    assert len(coords) == len(atom_types)
+    for i in range(len(coords)):
+        out += f"{atom_types[i]} {coords[i, 0]:.3f} {coords[i, 1]:.3f} {coords[i, 2]:.3f}\n"
+    if filename is None:
+        return out
+    with open(filename, 'w') as f:
+        f.write(out)
+
+
+def decode_ligands(lig_pos: List[torch.Tensor], lig_feat: List[torch.Tensor], lig_elements: List[str]) -> List[Tuple]:
+    """What the reference does with the sampler's output before molecule building (test.py:199-203): the atom type
+    of every generated atom is the argmax over its feature channels, mapped through the dataset's ``lig_elements``
+    (``dataset.lig_atom_idx_to_element``).  Returns one (positions [n,3], element symbols) pair per ligand; bond
+    perception / sanitisation (OpenBabel, RDKit) stay with the caller."""
+    out = []
+    for pos, feat in zip(lig_pos, lig_feat):
+        idx = torch.argmax(feat, dim=1).tolist()
+        out.append((pos, [lig_elements[i] for i in idx]))
     return out

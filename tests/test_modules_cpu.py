@@ -104,3 +104,15 @@ def test_edge_capacity_and_packer_offsets():
     assert ops.DeviceBatch.edge_capacity(b, gp) == (20 * 19 + 3 * 2 + 60 * 59, 20 * 5 + 20 * 3 + 40 * 5)
     gp = ops.GraphParams(ll_k=4, kl_k=0, kl_r=8)
     assert ops.DeviceBatch.edge_capacity(b, gp) == (20 * 4 + 3 * 2 + 60 * 4, 20 * 20 + 20 * 3 + 40 * 60)
+
+
+def test_output_decode_matches_reference_format():
+    """argmax -> element symbols and the XYZ text block of reference utils.py:11-21 / test.py:199-203."""
+    from keypoint_diffusion_b200.utils import decode_ligands, write_xyz_file
+    elements = ["C", "N", "O", "S", "P", "F", "Cl", "Br", "I", "B"]
+    pos = [torch.tensor([[0.0, 1.0, 2.0], [1.23456, -2.0, 3.5]]), torch.zeros(1, 3)]
+    feat = [torch.tensor([[0.1, 0.9] + [0.0] * 8, [0.0] * 6 + [2.0] + [0.0] * 3]), torch.eye(10)[2:3]]
+    dec = decode_ligands(pos, feat, elements)
+    assert [d[1] for d in dec] == [["N", "Cl"], ["O"]]
+    txt = write_xyz_file(dec[0][0], dec[0][1])
+    assert txt == "2\n\nN 0.000 1.000 2.000\nCl 1.235 -2.000 3.500\n"
