@@ -49,7 +49,7 @@ struct Sm {
     float* wsm;
     float* gate;      // [R][GATE_LD]
     int *src_s, *dst_s, *seg, *rp;
-    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full;
+    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full, *half_ready;
     uint32_t* tmem_slot;
     int* warp_cnt;
 };
@@ -62,7 +62,7 @@ __host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C
 template <class C>
 static size_t smem_bytes(int kch) {
     return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * MAXG * C::WSM +
-           sizeof(float) * GATE_LD * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 9) + 16 + 128;
+           sizeof(float) * GATE_LD * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 10) + 16 + 128;
 }
 
 template <class C>
@@ -89,7 +89,8 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.acc_done = m.tail_ready + 1;
     m.gates_done = m.acc_done + 1;
     m.wsm_full = m.gates_done + 1;
-    m.tmem_slot = reinterpret_cast<uint32_t*>(m.wsm_full + 1);
+    m.half_ready = m.wsm_full + 1;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.half_ready + 1);
     return m;
 }
 
@@ -105,6 +106,7 @@ __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
     tc::mbar_init(m.acc_done, 1);
     tc::mbar_init(m.gates_done, 1);
     tc::mbar_init(m.wsm_full, 1);
+    tc::mbar_init(m.half_ready, C::NW);
     tc::fence_barrier_init();
 }
 
@@ -248,21 +250,33 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         }
         tc::mma_commit(m.acc_done);
         WS_TRACE(4);
-        // epilogue 1 of this GVP done: feats_out is in A, the accumulator columns are free again
-        tc::mbar_wait(m.feats_ready, (g + 1) & 1);
-        tc::fence_after_sync();
-        WS_TRACE(5);
-        tc::mbar_wait(&m.wg_full[g % C::WGB], (g / C::WGB) & 1);
-        tc::fence_after_sync();
+        // gates GEMM, issued progressively: every epilogue-1 warp writes its feats_out columns in two halves, so the
+        // k-steps over the first halves run on the tensor core while the second halves are still being produced
+        constexpr int cpw = 256 / C::NCG, hb = cpw / 2;
         const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
         const uint32_t wg = tc::smem_u32(m.Wg[0] + (g % C::WGB) * C::WG_BYTES);
-        for (int j = 0; j < ksg; ++j) {
-            const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
-            const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
-            tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, j > 0 ? 1u : 0u);
-            if (C::NS == 2) {       // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
-                const uint64_t b1 = tc::make_smem_desc(wg + j * 1024 + 512, 256, 128);
-                tc::mma_bf16_ss(tmem + GATE_COL, a0, b1, idg, 1u);
+        uint32_t gacc = 0u;
+        for (int half = 0; half < 2; ++half) {
+            if (half == 0) {
+                tc::mbar_wait(m.half_ready, g & 1);
+                tc::fence_after_sync();
+                tc::mbar_wait(&m.wg_full[g % C::WGB], (g / C::WGB) & 1);
+            } else {
+                // epilogue 1 of this GVP done: feats_out is in A, the accumulator columns are free again
+                tc::mbar_wait(m.feats_ready, (g + 1) & 1);
+                WS_TRACE(5);
+            }
+            tc::fence_after_sync();
+            for (int j = 0; j < ksg; ++j) {
+                if ((((16 * j) % cpw) >= hb) != (half == 1)) continue;
+                const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
+                tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, gacc);
+                gacc = 1u;
+                if (C::NS == 2) {       // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                    const uint64_t b1 = tc::make_smem_desc(wg + j * 1024 + 512, 256, 128);
+                    tc::mma_bf16_ss(tmem + GATE_COL, a0, b1, idg, 1u);
+                }
             }
         }
         tc::mma_commit(m.gates_done);
@@ -539,40 +553,35 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     TC_T(t3);
     WS_TRACE(13);
     {
-        constexpr int cpw = 256 / C::NCG;
+        constexpr int cpw = 256 / C::NCG, hb = cpw / 2;      // the warp's columns, written in two halves (see issue())
         const int row0 = C::R == 128 ? 32 * q : 16 * q;
         const int cend = row0 < rows_valid ? min(NBf, cg * cpw + cpw) : 0;   // warps of empty row quarters skip
-        if constexpr (C::R == 128) {
-            for (int cb = cg * cpw; cb < cend; cb += 64) {
-                uint32_t v0[32], v1[32];
-                const bool two = cb + 32 < cend;
-                tc::tmem_ld_x32(taddr + cb, v0);
-                if (two) tc::tmem_ld_x32(taddr + cb + 32, v1);
-                tc::tmem_ld_wait();
-                epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
-                if (two) epi1_chunk<C>(v1, cb + 32, g.fout, NBf, bf_s, m, row_e);
-            }
-        } else if constexpr (C::NS == 1) {
-            for (int cb = cg * cpw; cb < cend; cb += 128) {
-                uint32_t v0[32], v1[32];
-                const bool two = cb + 64 < cend;
-                tc::tmem_ld_16x256b_x8(taddr + cb, v0);
-                if (two) tc::tmem_ld_16x256b_x8(taddr + cb + 64, v1);
-                tc::tmem_ld_wait();
-                epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
-                if (two) epi1_frag64<C>(v1, cb + 64, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
-            }
-        } else {
-            // stacked operand: lanes [32q, 32q+16) = A_hi (W_hi + W_lo), lanes [32q+16, 32q+32) = A_lo (W_hi + W_lo)
-            for (int cb = cg * cpw; cb < cend; cb += 64) {
-                uint32_t v0[32], v1[32];
-                tc::tmem_ld_16x256b_x8(taddr + cb, v0);
-                tc::tmem_ld_16x256b_x8(taddr + (16u << 16) + cb, v1);
-                tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
-                epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+        for (int half = 0; half < 2; ++half) {
+            const int cb = cg * cpw + half * hb;
+            if (cb < cend) {
+                if constexpr (C::R == 128) {                 // hb = 32 columns: thread = row
+                    uint32_t v0[32];
+                    tc::tmem_ld_x32(taddr + cb, v0);
+                    tc::tmem_ld_wait();
+                    epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
+                } else if constexpr (C::NS == 1) {           // hb = 64 columns, M = 64 accumulator
+                    uint32_t v0[32];
+                    tc::tmem_ld_16x256b_x8(taddr + cb, v0);
+                    tc::tmem_ld_wait();
+                    epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                } else {
+                    // stacked operand: lanes [32q, 32q+16) = A_hi (W_hi + W_lo), lanes [32q+16, 32q+32) = A_lo (W_hi + W_lo)
+                    uint32_t v0[32], v1[32];
+                    tc::tmem_ld_16x256b_x8(taddr + cb, v0);
+                    tc::tmem_ld_16x256b_x8(taddr + (16u << 16) + cb, v1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
+                    epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                }
             }
+            if (half == 0) publish(m.half_ready);
         }
     }
     tc::fence_before_sync();
