@@ -280,6 +280,16 @@ int kpd_sampler_edge_stats(kpd_sampler* s, double* out);
 /* kernels launched per reverse step by the captured sequence (for bench.py's gpu_launches) */
 int32_t kpd_sampler_launches_per_step(const kpd_sampler* s);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics (tools/tc_phase_times.py, tools/eg_phase_times.py, tools/ws_trace.py): in-kernel phase timers of the
+ * warp-specialised kernels, in SM cycles summed over CTAs; each call synchronises the device, copies the counters
+ * out and resets them.  kpd_debug_ws_trace returns the (tag, warp, clock) event list of one CTA and is empty unless
+ * the library was built with `make TRACE=1`.
+ * ------------------------------------------------------------------------------------------ */
+int kpd_debug_ws_times(unsigned long long* out64);
+int kpd_debug_eg_times(unsigned long long* out16);
+int kpd_debug_ws_trace(unsigned long long* out, int32_t cap, int32_t* count);
+
 #ifdef __cplusplus
 }
 #endif

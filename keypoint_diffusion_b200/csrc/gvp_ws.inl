@@ -1,23 +1,27 @@
 // Warp-specialised tensor-core GVP kernels (included inside namespace kpd by gvp.cu).
 //
-// A tile is R rows (edges or nodes).  Its scalar features live in shared memory ONLY as bf16 in the UMMA
-// K-major canonical layout (tc.cuh), i.e. directly as the A operand of tcgen05.mma; with NS = 2 there are two
-// planes (hi, lo = bf16(x - hi)) and every product runs as three MMAs (hi*hi + lo*hi + hi*lo): the "bf16x3"
-// mode, which keeps ~16 mantissa bits per operand and meets the 1e-4 fp32 parity bar (tools/
-// split_precision_study.py); NS = 1 is the plain bf16 mode.  Vector channels never touch shared memory
-// during the chain: lane (row, c) of a SIMT warp owns component c of all vector channels of one row in
-// registers, so Vh = V^T Wh, Vu = Vh^T Wu and the gating are register FMAs against broadcast weights.
+// A tile is R rows (edges or nodes).  Its scalar features live in shared memory ONLY as bf16 in the UMMA K-major
+// canonical layout (tc.cuh), i.e. directly as the A operand of tcgen05.mma.  NS = 1: plain bf16, R = 128 (M = 128)
+// or R = 64 (M = 64).  NS = 2 ("bf16x3"): every row is kept as hi = bf16(x) and lo = bf16(x - hi) and the hi / lo
+// rows of 64 tile rows are STACKED into one 128-row operand (ws_common.cuh: row_off); two MMAs per k-step (W_hi,
+// W_lo) then give all four hi/lo products, the epilogue adds the hi-row and lo-row accumulators: ~16 mantissa bits
+// per operand, inside the 1e-4 fp32 parity bar (tools/split_precision_study.py).
+// Vector channels never touch shared memory during the chain: they live in registers as mma.sync fragments (VF), so
+// Vh = V^T Wh and Vu = Vh^T Wu are warp-level tensor-core GEMMs (TF32, 3xTF32 for NS = 2) chained without shuffles.
 //
 // Warp roles (one CTA): R/8 SIMT warps | 1 MMA-issuing warp (one lane) | 1 weight-producer warp (one lane).
-//   producer: streams every GVP's packed to_feats_out weight as k-step slabs through a cp.async.bulk ring
-//             (full/empty mbarriers) and the small gates weight into a double buffer;
+//   producer: bulk-copies the shared-memory images of the chain's small fp32 weights (pack.pack_gvp_small), streams
+//             every GVP's packed to_feats_out weight as k-step slabs through a cp.async.bulk ring (full/empty
+//             mbarriers) and the small gates weight behind them;
 //   MMA warp: issues the k-steps over the feats columns as soon as those are complete (feats_ready) -- i.e.
 //             while the SIMT warps still compute Vh -- then the k-steps over the |Vh| columns (tail_ready),
-//             commits acc_done; after epilogue 1 (feats_ready again) it issues the gates GEMM and, right
-//             behind it, the NEXT GVP's main k-steps;
+//             commits acc_done; the gates GEMM follows progressively behind the two halves of epilogue 1
+//             (half_ready, feats_ready) and, right behind it, the NEXT GVP's main k-steps;
 //   SIMT:     Vh, |Vh| -> A, Vu, epilogue 1 (TMEM -> bias + SiLU -> bf16 planes of A), epilogue 2 (gates ->
-//             sigmoid -> V), gathers, LayerNorms and the deterministic segmented reduction.
-// SIMT-only synchronisation uses named barrier 1; cross-role synchronisation uses mbarriers only.
+//             sigmoid -> V), gathers (16-byte cp.async straight into A), LayerNorms and the deterministic
+//             segmented reduction.
+// SIMT-only synchronisation uses named barrier 1; cross-role synchronisation uses mbarriers only.  Optional
+// thread-block clusters (Cfg::CL > 1) let neighbouring tiles share ONE multicast weight stream.
 // phase timers of the warp-specialised kernels (cycles, SIMT thread 0, summed over CTAs):
 // [0..6] gvp_simt: Vh+|Vh|, Vu, wait acc, epilogue 1, wait gates, epilogue 2, calls
 __device__ unsigned long long g_ws_times[64];   // edge kernel: base 0, node kernel: base 16, head kernel: base 32 (+8..13: kernel phases)
