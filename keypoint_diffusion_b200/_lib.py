@@ -73,6 +73,9 @@ def _load():
         "kpd_egnn_destroy": (None, [P]),
         "kpd_egnn_attach_tc": (I, [P, P, C.POINTER(L), I, I]),
         "kpd_egnn_set_mode": (I, [P, I]),
+        "kpd_debug_ws_times": (I, [P]),
+        "kpd_debug_eg_times": (I, [P]),
+        "kpd_debug_ws_trace": (I, [P, I, P]),
         "kpd_egnn_dims": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "kpd_egnn_workspace_bytes": (L, [P, C.POINTER(KpdBatch), I, I, I]),
         "kpd_egnn_forward": (I, [P, C.POINTER(KpdBatch), P, P, P, P, P, P, I, C.POINTER(KpdCsr),
