@@ -106,7 +106,7 @@ __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
     for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], 1); }
     tc::mbar_init(m.feats_ready, C::NW);
-    tc::mbar_init(m.tail_ready, C::NW);
+    tc::mbar_init(m.tail_ready, C::NWV);
     tc::mbar_init(m.acc_done, 1);
     tc::mbar_init(m.gates_done, 1);
     tc::mbar_init(m.wsm_full, 1);
@@ -476,13 +476,13 @@ __device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], int c0, int 
 
 // M = 64 accumulators: 64 columns loaded with the 16x256b shape (all 32 lanes hold data: rows t/4 and t/4 + 8 of the
 // warp's 16-lane TMEM quarter, column pairs 2(t%4) + 8i).  bias + SiLU -> bf16x2 -> A plane(s), 4-byte stores.
-template <class C>
-__device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
+template <class C, int NBLK>
+__device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[4 * NBLK], int c0, int fout, int NBf, const float* bf_s,
                                             const Sm& m, int row_a, int lane) {
     const int cp = 2 * (lane & 3);
     const uint32_t ro = row_off<C>(row_a) + cp * 2;     // row_a + 8 is the next 8-row group: + 128 bytes
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NBLK; ++i) {
         const int col = c0 + 8 * i;
         if (col < NBf) {
             float fa0 = 0.f, fa1 = 0.f, fb0 = 0.f, fb1 = 0.f;
@@ -522,6 +522,9 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     WS_TRACE(10);
     if (gi == 0) tc::mbar_wait(m.wsm_full, 0);
     float vh[3][3][2];
+    float vu[3][2][2];
+    const bool vecw = warp < C::NWV;          // (warp-uniform) this warp owns vector rows
+    if (vecw) {
     vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -540,11 +543,11 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         }
     }
     publish(m.tail_ready);
+    }
     TC_T(t1);
     WS_TRACE(11);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
-    float vu[3][2][2];
-    vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
+    if (vecw) vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
     // c. epilogue 1: feats_out = SiLU(acc + b) -> A[:, 0:fout)   (gvp.py:101-103)
     const int q = warp & 3, cg = warp >> 2;
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
@@ -573,8 +576,8 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     uint32_t v0[32];
                     tc::tmem_ld_16x256b_x8(taddr + cb, v0);
                     tc::tmem_ld_wait();
-                    epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
-                } else {
+                    epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                } else if constexpr (hb == 64) {
                     // stacked operand: lanes [32q, 32q+16) = A_hi (W_hi + W_lo), lanes [32q+16, 32q+32) = A_lo (W_hi + W_lo)
                     uint32_t v0[32], v1[32];
                     tc::tmem_ld_16x256b_x8(taddr + cb, v0);
@@ -582,7 +585,15 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
-                    epi1_frag64<C>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                    epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                } else {                                       // 16 SIMT warps: 32 columns per half
+                    uint32_t v0[16], v1[16];
+                    tc::tmem_ld_16x256b_x4(taddr + cb, v0);
+                    tc::tmem_ld_16x256b_x4(taddr + (16u << 16) + cb, v1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
+                    epi1_frag64<C, 4>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
                 }
             }
             if (half == 0) publish(m.half_ready);
@@ -614,14 +625,16 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         }
     }
     simt_bar<C>();
+    if (vecw) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const float2 gt = *reinterpret_cast<const float2*>(m.gate + L.row * GATE_LD + 8 * j + 2 * L.t);
+        for (int j = 0; j < 2; ++j) {
+            const float2 gt = *reinterpret_cast<const float2*>(m.gate + L.row * GATE_LD + 8 * j + 2 * L.t);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * gt.x; v.x[c][j][1] = vu[c][j][1] * gt.y; }
+            for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * gt.x; v.x[c][j][1] = vu[c][j][1] * gt.y; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v.x[c][2][0] = v.x[c][2][1] = 0.f;
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) v.x[c][2][0] = v.x[c][2][1] = 0.f;
     TC_T(t6);
     WS_TRACE(16);
     WS_ACC(tb + 0, t0, t1); WS_ACC(tb + 1, t1, t2); WS_ACC(tb + 2, t2, t3); WS_ACC(tb + 3, t3, t4); WS_ACC(tb + 4, t4, t5);
@@ -662,7 +675,11 @@ __device__ __forceinline__ void build_segments(const Sm& m, int n) {
 #define KPD_WS_CLUSTER 1
 #endif
 using WsBf16 = ws::Cfg<128, 1, KPD_WS_CLUSTER>;    // bf16 operands, 128-row tiles (M = 128)
-using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER>;    // bf16 (hi, lo) rows stacked into one M = 128 operand, 64-row tiles
+#ifndef KPD_WS_SPLIT_XWARPS
+#define KPD_WS_SPLIT_XWARPS 8
+#endif
+// bf16 (hi, lo) rows stacked into one M = 128 operand, 64-row tiles; 8 vector warps + 8 extra epilogue warps
+using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;
 using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
 
 // fp32 node scalars -> bf16 hi (and lo) planes, row-major [n][S]: what the edge kernels gather with 16-byte cp.async
@@ -746,17 +763,21 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         }
         // geometry + v_src -> registers (gvp.py:474-480), in flight together with the gather
         const ws::Lane Ln = ws::lane_geometry<C>();
+        const bool vecw = warp < C::NWV;              // this warp owns 8 tile rows of vectors
         ws::VF v;
-        const int sI = m.src_s[Ln.row], dI = m.dst_s[Ln.row];
-        const float dx = a.xs[3 * sI] - a.xd[3 * dI], dy = a.xs[3 * sI + 1] - a.xd[3 * dI + 1], dz = a.xs[3 * sI + 2] - a.xd[3 * dI + 2];
-        ws::vf_load(v, a.v_src + (size_t)sI * (Vd * 3), Vd, Ln.t);
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (vecw) {
+            const int sI = m.src_s[Ln.row], dI = m.dst_s[Ln.row];
+            dx = a.xs[3 * sI] - a.xd[3 * dI]; dy = a.xs[3 * sI + 1] - a.xd[3 * dI + 1]; dz = a.xs[3 * sI + 2] - a.xd[3 * dI + 2];
+            ws::vf_load(v, a.v_src + (size_t)sI * (Vd * 3), Vd, Ln.t);
+        }
         if (ASYNC) {        // only the k-chunks behind the gathered scalars need zeros (rbf / |Vh| columns and K padding)
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             const int c0 = Sd >> 3, per = C::KCS / 16;
             for (int i = tid; i < (L.kch - c0) * per; i += C::NT_SIMT) reinterpret_cast<uint4*>(m.A[0] + (size_t)c0 * C::KCS)[i] = z;
         }
         ws::build_segments<C>(m, n);             // (its barriers also order the zero fill before the rbf stores)
-        {
+        if (vecw) {
             const float dij = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-8f)) + 1e-8f;
             // the unit x_diff is the LAST input channel here (channel Vd; Wh is staged with its rows permuted to match)
             const int sx = Vd >> 3, tx = (Vd & 7) >> 1, ex = Vd & 1;
@@ -780,7 +801,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         TC_T(e3);
         // ---- deterministic segmented reduction by destination (all MMAs and bulk copies have completed)
         float* VS = reinterpret_cast<float*>(m.ring);
-        ws::vf_store(v, VS + Ln.row * ws::VS_LD, Vd, Ln.t);
+        if (vecw) ws::vf_store(v, VS + Ln.row * ws::VS_LD, Vd, Ln.t);
         ws::simt_bar<C>();
         {
             const int nseg = m.seg[C::R + 1];
@@ -1057,7 +1078,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         // ---- phase 1b: vectors of lane (row, c) -> registers; residual stash in global
         TC_T(n2t);
         ws::VF v;
-        {
+        const bool vecw = warp < C::NWV;              // this warp owns 8 tile rows of vectors
+        if (vecw) {
             const int nd = n0 + min(Ln.row, n - 1);
             const float nv = nvs[Ln.row];
             ws::VF msg;
@@ -1145,7 +1167,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 }
             }
         }
-        {
+        if (vecw) {
             const int nd = n0 + min(Ln.row, n - 1);
             ws::VF res;
             ws::vf_load(res, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
@@ -1200,7 +1222,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
             cp_async_commit();
         }
         ws::VF v;
-        ws::vf_load(v, a.v + (size_t)(n0 + min(Ln.row, n - 1)) * (3 * Vd), Vd, Ln.t);
+        const bool vecw = warp < C::NWV;
+        if (vecw) ws::vf_load(v, a.v + (size_t)(n0 + min(Ln.row, n - 1)) * (3 * Vd), Vd, Ln.t);
         cp_async_wait<0>();
         ws::publish(m.feats_ready);
         for (int i = 0; i < a.n_gvps; ++i) ws::gvp_simt<C>(a.g[i], i, m, tmem, v, Ln, n, 32);
@@ -1211,7 +1234,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
             for (int k = 0; k < a.hid_out; ++k) s = fmaf(ws::get_scalar<C>(m, r, k), a.WoT[k * a.Fp + c], s);
             a.eps_h[(size_t)(n0 + r) * a.F + c] = s;
         }
-        if (Ln.t == 0 && Ln.row < n) {
+        if (vecw && Ln.t == 0 && Ln.row < n) {
             float* ex = a.eps_x + (size_t)(n0 + Ln.row) * 3;
             ex[0] = v.x[0][0][0]; ex[1] = v.x[1][0][0]; ex[2] = v.x[2][0][0];
         }

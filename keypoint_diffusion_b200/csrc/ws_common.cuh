@@ -23,11 +23,13 @@ constexpr int WH_LD = 36, WU_LD = 20;
 constexpr int WH_SZ = 12 * WH_LD * 2, WU_SZ = 12 * WU_LD * 2;
 template <int NS> constexpr int wsm_floats() { return NS * (WH_SZ + WU_SZ) + 256 + 16; }   // (hi[, lo]) Wh | Wu | bf | bg
 
-template <int R_, int NS_, int CL_>
+template <int R_, int NS_, int CL_, int NWX_ = 0>
 struct Cfg {
     static constexpr int R = R_, NS = NS_;
     static constexpr int CL = CL_;                   // CTAs per cluster: neighbouring tiles share ONE weight stream (multicast)
-    static constexpr int NW = R / 8;                 // SIMT warps: 8 rows each, lanes = (row, xyz component)
+    static constexpr int NWV = R / 8;                // vector-owning SIMT warps: 8 tile rows each (mma.sync fragments)
+    static constexpr int NW = NWV + NWX_;            // all SIMT warps; the NWX extra ones only help with the epilogues,
+                                                     // gathers and reductions (more warps in flight per SM quadrant)
     static constexpr int NT_SIMT = 32 * NW;
     static constexpr int NT = NT_SIMT + 64;
     static constexpr int MMA_M = R * NS;             // NS = 2 stacks the hi and lo rows of a tile into ONE 128-row A operand
