@@ -572,11 +572,16 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     tc::tmem_ld_x32(taddr + cb, v0);
                     tc::tmem_ld_wait();
                     epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
-                } else if constexpr (C::NS == 1) {           // hb = 64 columns, M = 64 accumulator
+                } else if constexpr (C::NS == 1 && hb == 64) {           // hb = 64 columns, M = 64 accumulator
                     uint32_t v0[32];
                     tc::tmem_ld_16x256b_x8(taddr + cb, v0);
                     tc::tmem_ld_wait();
                     epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                } else if constexpr (C::NS == 1) {                        // 16 SIMT warps: 32 columns per half
+                    uint32_t v0[16];
+                    tc::tmem_ld_16x256b_x4(taddr + cb, v0);
+                    tc::tmem_ld_wait();
+                    epi1_frag64<C, 4>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
                 } else if constexpr (hb == 64) {
                     // stacked operand: lanes [32q, 32q+16) = A_hi (W_hi + W_lo), lanes [32q+16, 32q+32) = A_lo (W_hi + W_lo)
                     uint32_t v0[32], v1[32];
@@ -674,13 +679,13 @@ __device__ __forceinline__ void build_segments(const Sm& m, int n) {
 #ifndef KPD_WS_CLUSTER
 #define KPD_WS_CLUSTER 1
 #endif
-using WsBf16 = ws::Cfg<128, 1, KPD_WS_CLUSTER>;    // bf16 operands, 128-row tiles (M = 128)
 #ifndef KPD_WS_SPLIT_XWARPS
 #define KPD_WS_SPLIT_XWARPS 8
 #endif
+using WsBf16 = ws::Cfg<128, 1, KPD_WS_CLUSTER>;    // bf16 operands, 128-row tiles (M = 128)
 // bf16 (hi, lo) rows stacked into one M = 128 operand, 64-row tiles; 8 vector warps + 8 extra epilogue warps
 using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;
-using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
+using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
 
 // fp32 node scalars -> bf16 hi (and lo) planes, row-major [n][S]: what the edge kernels gather with 16-byte cp.async
 __global__ void split_planes_kernel(const float* __restrict__ s0, int n0, const float* __restrict__ s1, int n1, int S,
