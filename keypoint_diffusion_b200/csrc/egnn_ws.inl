@@ -19,7 +19,9 @@ __device__ unsigned long long g_eg_times[16];
 
 namespace egws {
 
-using C = ws::Cfg<64, 2, 1>;              // 64-edge tiles, (hi, lo) stacked: M = 128
+using C = ws::Cfg<64, 2, 1, 8>;           // 64-edge tiles, (hi, lo) stacked: M = 128; 16 SIMT warps
+constexpr int NCG = C::NCG;               // column groups of the epilogue (4 TMEM lane quarters x NCG warps)
+constexpr int CPW = 256 / NCG;            // accumulator columns per epilogue warp
 constexpr int R = C::R, NW = C::NW, NT_SIMT = C::NT_SIMT, NT = C::NT;
 constexpr int VEC_LD = 264;                   // per-etype vectors staged in shared memory (floats; even, >= Hp)
 static_assert(VEC_LD >= KPD_MAX_HIDDEN + 3 && VEC_LD % 2 == 0, "VEC_LD");
@@ -28,7 +30,7 @@ struct Sm {
     unsigned char* A[2];
     unsigned char* ring;
     float *w1c[2], *b2[2], *wv[2], *w2lo[2];     // [VEC_LD] each; w2lo: [3][VEC_LD]
-    float *dij, *xsc, *lo, *dotp, *att, *xm;     // [R], [R][3], [2][R][4], [2][R], [R], [R][3]
+    float *dij, *xsc, *lo, *dotp, *att, *xm;     // [R], [R][3], [2][R][4], [NCG][R], [R], [R][3]
     int *src_s, *dst_s, *seg, *rp, *warp_cnt;
     uint64_t *full, *empty, *a_ready, *acc_done;
     uint32_t* tmem_slot;
@@ -38,7 +40,7 @@ __host__ __device__ inline size_t a_bytes(int kch) { return ((size_t)kch * C::KC
 
 static size_t smem_bytes(int kch) {
     return 2 * a_bytes(kch) + (size_t)C::STAGES * C::SLAB + sizeof(float) * (2 * 3 * VEC_LD + 2 * 3 * VEC_LD) +
-           sizeof(float) * (R + 3 * R + 8 * R + 2 * R + R + 3 * R) + sizeof(int) * (5 * R + 16) +
+           sizeof(float) * (R + 3 * R + 8 * R + NCG * R + R + 3 * R) + sizeof(int) * (5 * R + 16) +
            sizeof(uint64_t) * (2 * C::STAGES + 4) + 16 + 128;
 }
 
@@ -53,7 +55,7 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.dij = f; f += R;
     m.xsc = f; f += 3 * R;
     m.lo = f; f += 8 * R;
-    m.dotp = f; f += 2 * R;
+    m.dotp = f; f += NCG * R;
     m.att = f; f += R;
     m.xm = f; f += 3 * R;
     m.src_s = reinterpret_cast<int*>(f);
@@ -93,6 +95,13 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
     const EgnnEdgeLaunch& L = W.L;
     const EgnnEtypeArgs& a = L.e[blockIdx.y];
     const int tile_begin = blockIdx.x * R;
+    // this thread's edge, fetched together with the edge count (arrays are sized at capacity: the speculative read is
+    // in bounds; rows past the end are re-read from the tile's last edge below)
+    int my_s = 0, my_d = 0;
+    if (threadIdx.x < R) {
+        const int e = min(tile_begin + (int)threadIdx.x, max(a.cap, 1) - 1);
+        my_s = __ldg(a.src + e); my_d = __ldg(a.dst + e);
+    }
     const int E = a.rowptr[a.n_dst];
     if (tile_begin >= E) return;
     const int n = min(R, E - tile_begin);
@@ -163,8 +172,8 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             for (int c = 0; c < 3; ++c) m.w2lo[br][c * VEC_LD + k] = c < nlo ? a.W2lo[br][c * Hp + k] : 0.f;
         }
         if (tid < R) {
-            const int e = tile_begin + min(tid, n - 1);     // rows >= n replicate the last valid edge
-            const int s = a.src[e], d = a.dst[e];
+            int s = my_s, d = my_d;
+            if (tid >= n) { s = a.src[tile_begin + n - 1]; d = a.dst[tile_begin + n - 1]; }     // rows >= n replicate the last valid edge
             m.src_s[tid] = s;
             m.dst_s[tid] = d;
             m.rp[2 * tid] = a.rowptr[d];
@@ -290,14 +299,14 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             tc::fence_after_sync();
             const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + 256 * br;
             float dota = 0.f, dotb = 0.f;
-            const int cend = min(nmain, cg * 128 + 128);
-            for (int cb = cg * 128; cb < cend; cb += 64) {
-                uint32_t v0[32], v1[32];
-                tc::tmem_ld_16x256b_x8(taddr + cb, v0);
-                tc::tmem_ld_16x256b_x8(taddr + (16u << 16) + cb, v1);
+            const int cend = min(nmain, cg * CPW + CPW);
+            for (int cb = cg * CPW; cb < cend; cb += 32) {
+                uint32_t v0[16], v1[16];
+                tc::tmem_ld_16x256b_x4(taddr + cb, v0);
+                tc::tmem_ld_16x256b_x4(taddr + (16u << 16) + cb, v1);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const int col = cb + 8 * i + cp;
                     if (cb + 8 * i < nmain) {
                         const float2 b = *reinterpret_cast<const float2*>(m.b2[br] + col);
@@ -326,7 +335,9 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             if ((lane & 3) == 0) { m.dotp[cg * R + ra] = dota; m.dotp[cg * R + ra + 8] = dotb; }
             simt_bar();
             if (tid < R) {
-                float dot = m.dotp[tid] + m.dotp[R + tid];
+                float dot = 0.f;
+#pragma unroll
+                for (int c2 = 0; c2 < NCG; ++c2) dot += m.dotp[c2 * R + tid];
                 for (int cc = 0; cc < nlo; ++cc) dot = fmaf(m.lo[(br * R + tid) * 4 + cc], m.wv[br][nmain + cc], dot);
                 if (br == 0) {
                     m.att[tid] = ws::sigmoid_acc(dot + a.batt[0]);          // msg_h = m2 * sigmoid(Linear(m2))  (:111-112)
