@@ -14,7 +14,8 @@
 namespace kpd {
 
 constexpr int TCG_STAGES = 4;
-constexpr int TCG_THREADS = 192;      // warps 0-3: stage A + epilogues | warp 4: MMA issuer | warp 5: weight producer
+constexpr int TCG_EW = 8;             // SIMT warps: stage A + epilogues (two per TMEM lane quarter)
+constexpr int TCG_THREADS = 32 * TCG_EW + 64;      // + warp TCG_EW: MMA issuer | warp TCG_EW + 1: weight producer
 
 template <int NS>
 __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinBatch B) {
@@ -42,11 +43,11 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
 
     if (tid == 0) {
         for (int i = 0; i < TCG_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(a_ready, 4);
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], 4); }
+        tc::mbar_init(a_ready, TCG_EW);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], TCG_EW); }
         tc::fence_barrier_init();
     }
-    if (warp == 4) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }     // two 256-column accumulators
+    if (warp == TCG_EW) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }     // two 256-column accumulators
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
     // all blocks before the last one are full (256 rows): their slabs are NS * 2 * 32 * 128 B per k-step
     auto block_W = [&](int blk) { return P.Wp + (size_t)blk * ksteps * (NS * 2 * 32 * 128 / 16); };
 
-    if (warp == 5) {
+    if (warp == TCG_EW + 1) {
         // ---- weight producer: the k-step slabs of this CTA's column blocks through the ring
         if (lane == 0) {
             uint32_t it = 0;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TCG_EW) {
         // ---- MMA issuer: accumulator bi % 2, so that the epilogue of one block overlaps the MMAs of the next
         if (lane == 0) {
             tc::mbar_wait(a_ready, 0);
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
         //      the lanes in order (coalesced 32-byte reads), four items per lane in flight
         {
             const int nch = 2 * ksteps;
-            constexpr int RPW = C::R / 4;
+            constexpr int RPW = C::R / TCG_EW;
             const int items = RPW * nch;
             for (int base = 0; base < items; base += 128) {
                 float v[4][8];
@@ -139,14 +140,15 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
             if (lane == 0) tc::mbar_arrive(a_ready);
         }
         // ---- epilogues
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int q = warp & 3, chalf = warp >> 2;       // TMEM lane quarter; which 64-column chunks (c0 / 64 parity)
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int bi = 0; bi < nb_cta; ++bi) {
             const int buf = bi & 1, blk = blk0 + bi, NB = block_NB(blk);
             tc::mbar_wait(&acc_done[buf], (bi >> 1) & 1);
             tc::fence_after_sync();
             if (NS == 1) {          // thread r reads its accumulator row from TMEM
-                const int gm = m0 + tid;
-                for (int c0 = 0; c0 < NB; c0 += 32) {
+                const int gm = m0 + 32 * q + lane;
+                for (int c0 = 32 * chalf; c0 < NB; c0 += 64) {
                     uint32_t v[32];
                     tc::tmem_ld_x32(lane_addr + 256 * buf + c0, v);
                     tc::tmem_ld_wait();
@@ -164,9 +166,9 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                     }
                 }
             } else {                // lanes [32w, 32w+16) = hi rows, [32w+16, 32w+32) = lo rows of tile rows [16w, 16w+16)
-                const int ra = 16 * warp + (lane >> 2), cp = 2 * (lane & 3);
+                const int ra = 16 * q + (lane >> 2), cp = 2 * (lane & 3);
                 const bool vec2 = (P.ldy & 1) == 0 && (!P.R || (P.ldr & 1) == 0);      // 8-byte accesses possible
-                for (int c0 = 0; c0 < NB; c0 += 64) {
+                for (int c0 = 64 * chalf; c0 < NB; c0 += 128) {
                     uint32_t v0[32], v1[32];
                     tc::tmem_ld_16x256b_x8(lane_addr + 256 * buf + c0, v0);
                     tc::tmem_ld_16x256b_x8(lane_addr + (16u << 16) + 256 * buf + c0, v1);
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+    if (warp == TCG_EW) tc::tmem_dealloc(tmem_base, 512);
 }
 
 template <int NS>
