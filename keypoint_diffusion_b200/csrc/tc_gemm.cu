@@ -14,7 +14,11 @@
 namespace kpd {
 
 constexpr int TCG_STAGES = 4;
-constexpr int TCG_EW = 8;             // SIMT warps: stage A + epilogues (two per TMEM lane quarter)
+#ifndef KPD_TCG_EW
+#define KPD_TCG_EW 8
+#endif
+constexpr int TCG_EW = KPD_TCG_EW;    // SIMT warps: stage A + epilogues (TCG_EW / 4 per TMEM lane quarter)
+constexpr int TCG_CS = TCG_EW / 4;    // ... which take every TCG_CS-th column chunk of a block
 constexpr int TCG_THREADS = 32 * TCG_EW + 64;      // + warp TCG_EW: MMA issuer | warp TCG_EW + 1: weight producer
 
 template <int NS>
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
             tc::fence_after_sync();
             if (NS == 1) {          // thread r reads its accumulator row from TMEM
                 const int gm = m0 + 32 * q + lane;
-                for (int c0 = 32 * chalf; c0 < NB; c0 += 64) {
+                for (int c0 = 32 * chalf; c0 < NB; c0 += 32 * TCG_CS) {
                     uint32_t v[32];
                     tc::tmem_ld_x32(lane_addr + 256 * buf + c0, v);
                     tc::tmem_ld_wait();
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
             } else {                // lanes [32w, 32w+16) = hi rows, [32w+16, 32w+32) = lo rows of tile rows [16w, 16w+16)
                 const int ra = 16 * q + (lane >> 2), cp = 2 * (lane & 3);
                 const bool vec2 = (P.ldy & 1) == 0 && (!P.R || (P.ldr & 1) == 0);      // 8-byte accesses possible
-                for (int c0 = 64 * chalf; c0 < NB; c0 += 128) {
+                for (int c0 = 64 * chalf; c0 < NB; c0 += 64 * TCG_CS) {
                     uint32_t v0[32], v1[32];
                     tc::tmem_ld_16x256b_x8(lane_addr + 256 * buf + c0, v0);
                     tc::tmem_ld_16x256b_x8(lane_addr + (16u << 16) + 256 * buf + c0, v1);
