@@ -113,16 +113,26 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
     const int ksteps = W.kch >> 1;
     const int NB = (nmain + 15) & ~15;
 
-    if (tid == 0) {
-        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.a_ready[i], NW); tc::mbar_init(&m.acc_done[i], 1); }
-        tc::fence_barrier_init();
+    // asynchronous set-up: the control warps initialise the barriers and TMEM and start streaming weights at once; the
+    // SIMT warps meet them at named barrier 3 only when they first need a barrier (after building the first A tile)
+    uint32_t tmem = 0;
+    if (warp >= NW) {
+        if (warp == NW) {
+            if (lane == 0) {
+                for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], 1); }
+                for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.a_ready[i], NW); tc::mbar_init(&m.acc_done[i], 1); }
+                tc::fence_barrier_init();
+            }
+            __syncwarp();
+            tc::tmem_alloc(m.tmem_slot, 512);
+            tc::tmem_relinquish();
+            tc::fence_before_sync();
+        }
+        asm volatile("bar.sync 2, 64;" ::: "memory");
+        asm volatile("bar.arrive 3, %0;" ::"n"(egws::NT) : "memory");
+        tc::fence_after_sync();
+        tmem = *m.tmem_slot;
     }
-    if (warp == NW) { tc::tmem_alloc(m.tmem_slot, 512); tc::tmem_relinquish(); }
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = *m.tmem_slot;
 
     if (warp == NW + 1) {
         // ---- producer: W2 slabs of the edge branch, then of the coord branch
@@ -286,6 +296,11 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                         if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(sdot + m.b2[br][nmain + cc]);
                     }
                 }
+            }
+            if (br == 0) {          // first use of an mbarrier / of TMEM: join the control warps' set-up
+                asm volatile("bar.sync 3, %0;" ::"n"(egws::NT) : "memory");
+                tc::fence_after_sync();
+                tmem = *m.tmem_slot;
             }
             publish(&m.a_ready[br]);
             gt[br] = clock64();
