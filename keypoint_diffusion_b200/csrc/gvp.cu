@@ -644,6 +644,24 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     const int S = m->S, V = m->V;
 
     // ---- encoders: time concatenated first, Linear + SiLU + LayerNorm (dynamics_gvp.py:161-169)
+    if (m->mode != 0) {       // tensor-core modes: everything up to the first conv in one launch
+        GvpEncArgs ea;
+        memset(&ea, 0, sizeof(ea));
+        ea.n[0] = N[0]; ea.n[1] = N[1]; ea.K[0] = m->F; ea.K[1] = m->C;
+        ea.in[0] = h_lig; ea.in[1] = h_kp;
+        for (int nt = 0; nt < 2; ++nt) {
+            const float* const* enc = nt == 0 ? m->lig_enc : m->kp_enc;
+            ea.WT[nt] = enc[0]; ea.bias[nt] = enc[1]; ea.lnw[nt] = enc[2]; ea.lnb[nt] = enc[3];
+            ea.s[nt] = w.s[nt]; ea.s_hi[nt] = w.s_hi[nt]; ea.s_lo[nt] = w.s_lo[nt]; ea.v[nt] = w.v[nt];
+        }
+        ea.batch[0] = b->lig_batch; ea.batch[1] = b->kp_batch;
+        ea.v_kp = v_kp; ea.t_ptr = t_ptr; ea.t_per_complex = t_per_complex; ea.S = S; ea.Sp = m->Sp; ea.V = V;
+        const int mx = N[0] > N[1] ? N[0] : N[1];
+        if (mx > 0) {
+            gvp_encode_kernel<<<dim3(cdiv(mx, 8 * ENC_ROWS), 2), 256, 0, st>>>(ea);
+            KPD_TRY(check_launch("gvp_encode_kernel"));
+        }
+    } else {
     KPD_TRY(launch_concat_time(h_lig, m->F, w.tin, m->F + 1, N[0], t_ptr, b->lig_batch, t_per_complex, st));
     KPD_TRY(launch_linear(w.tin, m->F + 1, m->lig_enc[0], m->Sp, m->lig_enc[1], nullptr, 0, w.tenc, S, N[0], m->F + 1, S, 1, st));
     KPD_TRY(launch_layernorm(w.tenc, S, w.s[0], S, N[0], S, m->lig_enc[2], m->lig_enc[3], st));
@@ -654,16 +672,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     cudaError_t ce = cudaMemsetAsync(w.v[0], 0, sizeof(float) * (size_t)N[0] * V * 3, st);
     KPD_REQUIRE(ce == cudaSuccess, "kpd_gvp_forward: memset failed: %s", cudaGetErrorString(ce));
     KPD_TRY(launch_copy_rows(v_kp, V * 3, w.v[1], V * 3, N[1], V * 3, st));
-
-    auto split_planes = [&](int n_types) -> int {
-        const int mx = N[0] > N[1] ? N[0] : N[1];
-        if (m->mode == 0 || mx == 0) return 0;
-        const int blocks = cdiv(cdiv(mx * S, 8), 256);
-        split_planes_kernel<<<dim3(blocks, n_types), 256, 0, st>>>(w.s[0], N[0], w.s[1], N[1], S, w.s_hi[0], w.s_lo[0],
-                                                                    w.s_hi[1], w.s_lo[1]);
-        return check_launch("split_planes_kernel");
-    };
-    KPD_TRY(split_planes(2));
+    }
     const int src_nt[4] = {0, 1, 0, 1}, dst_nt[4] = {0, 0, 1, 1};
     const float* X[2] = {x_lig, x_kp};
     const int norm_mode = m->cfg.norm_mode;

@@ -687,29 +687,6 @@ using WsBf16 = ws::Cfg<128, 1, KPD_WS_CLUSTER>;    // bf16 operands, 128-row til
 using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;
 using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
 
-// fp32 node scalars -> bf16 hi (and lo) planes, row-major [n][S]: what the edge kernels gather with 16-byte cp.async
-__global__ void split_planes_kernel(const float* __restrict__ s0, int n0, const float* __restrict__ s1, int n1, int S,
-                                    __nv_bfloat16* __restrict__ h0, __nv_bfloat16* __restrict__ l0,
-                                    __nv_bfloat16* __restrict__ h1, __nv_bfloat16* __restrict__ l1) {
-    const float* s = blockIdx.y == 0 ? s0 : s1;
-    __nv_bfloat16* hp = blockIdx.y == 0 ? h0 : h1;
-    __nv_bfloat16* lp = blockIdx.y == 0 ? l0 : l1;
-    const int n = blockIdx.y == 0 ? n0 : n1;
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (i >= (size_t)n * S) return;
-    const float4 a = *reinterpret_cast<const float4*>(s + i), b = *reinterpret_cast<const float4*>(s + i + 4);
-    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint4 hi, lo;
-    hi.x = tc::pack_bf16x2(f[0], f[1]); hi.y = tc::pack_bf16x2(f[2], f[3]);
-    hi.z = tc::pack_bf16x2(f[4], f[5]); hi.w = tc::pack_bf16x2(f[6], f[7]);
-    lo.x = tc::pack_bf16x2(f[0] - __uint_as_float(hi.x << 16), f[1] - __uint_as_float(hi.x & 0xffff0000u));
-    lo.y = tc::pack_bf16x2(f[2] - __uint_as_float(hi.y << 16), f[3] - __uint_as_float(hi.y & 0xffff0000u));
-    lo.z = tc::pack_bf16x2(f[4] - __uint_as_float(hi.z << 16), f[5] - __uint_as_float(hi.z & 0xffff0000u));
-    lo.w = tc::pack_bf16x2(f[6] - __uint_as_float(hi.w << 16), f[7] - __uint_as_float(hi.w & 0xffff0000u));
-    *reinterpret_cast<uint4*>(hp + i) = hi;
-    *reinterpret_cast<uint4*>(lp + i) = lo;
-}
-
 // ------------------------------------------------------------------ edge kernel
 // GVPMultiEdgeConv.message + aggregation (models/gvp.py:472-497, :540-550) for all edge types in one launch
 template <class C>
@@ -965,6 +942,80 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* hp, __nv_bfloat16* 
 }
 
 }  // namespace ws
+
+// ------------------------------------------------------------------ encoders (tensor-core modes)
+// Both node encoders of LigRecDynamicsGVP.forward in ONE launch (dynamics_gvp.py:161-184): time concatenated first,
+// Linear + SiLU + LayerNorm -> s (fp32 + bf16 planes); ligand vectors start at zero, keypoint vectors are copied.
+// One warp per ENC_ROWS rows (weights re-used across them), a lane per 8 output features.
+constexpr int ENC_ROWS = 4;
+struct GvpEncArgs {
+    int n[2], K[2];                       // rows and input width (without the time channel) per node type
+    const float* in[2];                   // [n][K]
+    const float* WT[2]; const float* bias[2]; const float* lnw[2]; const float* lnb[2];   // WT: [K + 1][Sp] K-major
+    const int* batch[2];
+    float* s[2]; __nv_bfloat16* s_hi[2]; __nv_bfloat16* s_lo[2];
+    float* v[2]; const float* v_kp;
+    const float* t_ptr; int t_per_complex, S, Sp, V;
+};
+__global__ void __launch_bounds__(256) gvp_encode_kernel(const __grid_constant__ GvpEncArgs a) {
+    const int nt = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = (blockIdx.x * 8 + warp) * ENC_ROWS;
+    const int n = a.n[nt], K = a.K[nt], S = a.S;
+    if (r0 >= n) return;
+    const bool act = 8 * lane < S;
+    const int col = act ? 8 * lane : 0;
+    float acc[ENC_ROWS][8];
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(a.bias[nt] + col), b1 = *reinterpret_cast<const float4*>(a.bias[nt] + col + 4);
+#pragma unroll
+        for (int j = 0; j < ENC_ROWS; ++j) {
+            acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b0.z; acc[j][3] = b0.w;
+            acc[j][4] = b1.x; acc[j][5] = b1.y; acc[j][6] = b1.z; acc[j][7] = b1.w;
+        }
+    }
+    const float* WT = a.WT[nt];
+    for (int k0 = 0; k0 <= K; k0 += 32) {
+        // lane l holds input feature k0 + l of each row (the time channel is feature K)
+        float xin[ENC_ROWS];
+#pragma unroll
+        for (int j = 0; j < ENC_ROWS; ++j) {
+            const int r = min(r0 + j, n - 1), k = k0 + lane;
+            xin[j] = k < K ? a.in[nt][(size_t)r * K + k] : (k == K ? a.t_ptr[a.t_per_complex ? a.batch[nt][r] : 0] : 0.f);
+        }
+        const int kend = min(32, K + 1 - k0);
+#pragma unroll 8
+        for (int kk = 0; kk < kend; ++kk) {
+            const float4 w0 = *reinterpret_cast<const float4*>(WT + (size_t)(k0 + kk) * a.Sp + col);
+            const float4 w1 = *reinterpret_cast<const float4*>(WT + (size_t)(k0 + kk) * a.Sp + col + 4);
+#pragma unroll
+            for (int j = 0; j < ENC_ROWS; ++j) {
+                const float x = __shfl_sync(0xffffffffu, xin[j], kk);
+                acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]); acc[j][2] = fmaf(x, w0.z, acc[j][2]);
+                acc[j][3] = fmaf(x, w0.w, acc[j][3]); acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
+                acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
+            }
+        }
+    }
+    float lw[8], lb[8];
+    ws::ln_params8(a.lnw[nt], a.lnb[nt], act, lane, lw, lb);
+#pragma unroll
+    for (int j = 0; j < ENC_ROWS; ++j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = act ? silu_f(acc[j][i]) : 0.f;
+        ws::warp_layernorm8(acc[j], act, S, lw, lb);
+        const int r = r0 + j;
+        if (r < n && act) {
+            const size_t o = (size_t)r * S + col;
+            *reinterpret_cast<float4*>(a.s[nt] + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            *reinterpret_cast<float4*>(a.s[nt] + o + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+            ws::store_planes8(a.s_hi[nt], a.s_lo[nt], o, acc[j]);
+        }
+        if (r < n) {
+            const int nv = 3 * a.V;
+            for (int c = lane; c < nv; c += 32) a.v[nt][(size_t)r * nv + c] = nt == 0 ? 0.f : a.v_kp[(size_t)r * nv + c];
+        }
+    }
+}
 
 // node / head tiles hold NODE_ROWS valid rows of the C::R-row MMA tile: node counts per launch are small, so
 // more, lighter CTAs (one wave) beat full tiles; rows are dealt round-robin to the SIMT warps for the scalar phases
