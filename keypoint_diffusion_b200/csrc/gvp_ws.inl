@@ -51,7 +51,7 @@ struct Sm {
     unsigned char* ring;
     unsigned char* Wg[2];
     float* wsm;
-    float* gate;      // [R][GATE_LD]
+    float* gate;      // NS = 1: gates [R][GATE_LD]; NS = 2: per-column-group partial gates [NCG][R][16]
     int *src_s, *dst_s, *seg, *rp;
     uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full, *half_ready;
     uint32_t* tmem_slot;
@@ -66,7 +66,7 @@ __host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C
 template <class C>
 static size_t smem_bytes(int kch) {
     return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * MAXG * C::WSM +
-           sizeof(float) * GATE_LD * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 10) + 16 + 128;
+           sizeof(float) * (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 10) + 16 + 128;
 }
 
 template <class C>
@@ -79,7 +79,7 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.Wg[1] = m.Wg[0] + C::WG_BYTES;
     m.wsm = reinterpret_cast<float*>(m.Wg[0] + C::WGB * C::WG_BYTES);
     m.gate = m.wsm + MAXG * C::WSM;
-    m.src_s = reinterpret_cast<int*>(m.gate + GATE_LD * C::R);
+    m.src_s = reinterpret_cast<int*>(m.gate + (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R);
     m.dst_s = m.src_s + C::R;
     m.seg = m.dst_s + C::R;            // [R + 8]
     m.rp = m.seg + C::R + 8;           // [2R]
@@ -104,7 +104,8 @@ __device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n
 template <class C>
 __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
     for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], 1); }
+    // wg_empty: NS = 1 the tcgen05 gates GEMM commits it; NS = 2 every SIMT warp arrives after its mma.sync gates
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], C::NS == 2 ? C::NW : 1); }
     tc::mbar_init(m.feats_ready, C::NW);
     tc::mbar_init(m.tail_ready, C::NWV);
     tc::mbar_init(m.acc_done, 1);
@@ -254,6 +255,14 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         }
         tc::mma_commit(m.acc_done);
         WS_TRACE(4);
+        if constexpr (C::NS == 2) {
+            // bf16x3: the gates GEMM runs on the warp-level tensor cores straight from the epilogue registers
+            // (gates_mma); only wait until epilogue 1 has written feats_out and drained the accumulator
+            tc::mbar_wait(m.feats_ready, (g + 1) & 1);
+            tc::fence_after_sync();
+            WS_TRACE(5);
+            continue;
+        }
         // gates GEMM, issued progressively: every epilogue-1 warp writes its feats_out columns in two halves, so the
         // k-steps over the first halves run on the tensor core while the second halves are still being produced
         constexpr int cpw = 256 / C::NCG, hb = cpw / 2;
@@ -476,9 +485,11 @@ __device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], int c0, int 
 
 // M = 64 accumulators: 64 columns loaded with the 16x256b shape (all 32 lanes hold data: rows t/4 and t/4 + 8 of the
 // warp's 16-lane TMEM quarter, column pairs 2(t%4) + 8i).  bias + SiLU -> bf16x2 -> A plane(s), 4-byte stores.
+// fr (NS = 2 only): the packed bf16 pairs just written, [hi row a, hi row b, lo row a, lo row b][block] -- as they are,
+// the mma.sync A fragments of the gates GEMM (gates_mma)
 template <class C, int NBLK>
 __device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[4 * NBLK], int c0, int fout, int NBf, const float* bf_s,
-                                            const Sm& m, int row_a, int lane) {
+                                            const Sm& m, int row_a, int lane, uint32_t (&fr)[4][NBLK]) {
     const int cp = 2 * (lane & 3);
     const uint32_t ro = row_off<C>(row_a) + cp * 2;     // row_a + 8 is the next 8-row group: + 128 bytes
 #pragma unroll
@@ -495,11 +506,49 @@ __device__ __forceinline__ void epi1_frag64(const uint32_t (&v)[4 * NBLK], int c
             const uint32_t ha = tc::pack_bf16x2(fa0, fa1), hb = tc::pack_bf16x2(fb0, fb1);
             *reinterpret_cast<uint32_t*>(m.A[0] + off) = ha;
             *reinterpret_cast<uint32_t*>(m.A[0] + off + 128) = hb;       // row + 8: next 8-row group
+            fr[0][i] = ha; fr[1][i] = hb; fr[2][i] = 0u; fr[3][i] = 0u;
             if (C::NS == 2) {
-                *reinterpret_cast<uint32_t*>(m.A[1] + off) =
-                    tc::pack_bf16x2(fa0 - __uint_as_float(ha << 16), fa1 - __uint_as_float(ha & 0xffff0000u));
-                *reinterpret_cast<uint32_t*>(m.A[1] + off + 128) =
-                    tc::pack_bf16x2(fb0 - __uint_as_float(hb << 16), fb1 - __uint_as_float(hb & 0xffff0000u));
+                const uint32_t la = tc::pack_bf16x2(fa0 - __uint_as_float(ha << 16), fa1 - __uint_as_float(ha & 0xffff0000u));
+                const uint32_t lb = tc::pack_bf16x2(fb0 - __uint_as_float(hb << 16), fb1 - __uint_as_float(hb & 0xffff0000u));
+                *reinterpret_cast<uint32_t*>(m.A[1] + off) = la;
+                *reinterpret_cast<uint32_t*>(m.A[1] + off + 128) = lb;
+                fr[2][i] = la; fr[3][i] = lb;
+            }
+        } else {
+            fr[0][i] = fr[1][i] = fr[2][i] = fr[3][i] = 0u;
+        }
+    }
+}
+
+// warp-level bf16 tensor-core MMA, D(16x8) += A(16x16) B(16x8), fp32 accumulation
+__device__ __forceinline__ void mma_bf16_k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Gates GEMM of the bf16x3 mode on the warp-level tensor cores, straight from the epilogue registers: the 16x256b
+// TMEM fragment of epilogue 1 (rows g, g+8; column pairs 2t + 8i) IS the m16n8k16 A fragment layout, so feats_out never
+// has to be re-read.  gD[j]: this warp's partial gates (16 rows x n-tile j) over its own feats_out columns.
+// Wg: staged fragments (pack.pack_gates_frag): [hi | lo][k16 step][t][(n + 4t) & 15][2 words].
+template <int NBLK>
+__device__ __forceinline__ void gates_mma(const uint32_t (&fr)[4][NBLK], int c0, int NBf, const uint32_t* __restrict__ Wg,
+                                          int lo_words, int lane, float (&gD)[2][4]) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int p = 0; p < NBLK / 2; ++p) {
+        const int col = c0 + 16 * p;
+        if (col < NBf) {
+            const int S = col >> 4;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int wi = ((S * 4 + t) * 16 + ((8 * j + g + 4 * t) & 15)) * 2;
+                const uint2 bh = *reinterpret_cast<const uint2*>(Wg + wi);
+                const uint2 bl = *reinterpret_cast<const uint2*>(Wg + lo_words + wi);
+                mma_bf16_k16(gD[j], fr[0][2 * p], fr[1][2 * p], fr[0][2 * p + 1], fr[1][2 * p + 1], bh.x, bh.y);
+                mma_bf16_k16(gD[j], fr[2][2 * p], fr[3][2 * p], fr[2][2 * p + 1], fr[3][2 * p + 1], bh.x, bh.y);
+                mma_bf16_k16(gD[j], fr[0][2 * p], fr[1][2 * p], fr[0][2 * p + 1], fr[1][2 * p + 1], bl.x, bl.y);
             }
         }
     }
@@ -523,6 +572,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     if (gi == 0) tc::mbar_wait(m.wsm_full, 0);
     float vh[3][3][2];
     float vu[3][2][2];
+    [[maybe_unused]] float gD[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};     // bf16x3: this warp's partial gates
     const bool vecw = warp < C::NWV;          // (warp-uniform) this warp owns vector rows
     if (vecw) {
     vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
@@ -562,6 +612,13 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     {
         constexpr int cpw = 256 / C::NCG, hb = cpw / 2;      // the warp's columns, written in two halves (see issue())
         const int row0 = C::R == 128 ? 32 * q : 16 * q;
+        [[maybe_unused]] uint32_t fr8[4][8];
+        [[maybe_unused]] uint32_t fr4[4][4];
+        if constexpr (C::NS == 2) {                          // the gates weight fragments of this GVP have landed
+            tc::mbar_wait(&m.wg_full[gi % C::WGB], (gi / C::WGB) & 1);
+        }
+        const uint32_t* wgf = reinterpret_cast<const uint32_t*>(m.Wg[0] + (gi % C::WGB) * C::WG_BYTES);
+        const int wg_lo = ((NBf >> 4) * 512) / 4;            // words between the hi and the lo fragment image
         const int cend = row0 < rows_valid ? min(NBf, cg * cpw + cpw) : 0;   // warps of empty row quarters skip
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -576,12 +633,12 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     uint32_t v0[32];
                     tc::tmem_ld_16x256b_x8(taddr + cb, v0);
                     tc::tmem_ld_wait();
-                    epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                    epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane, fr8);
                 } else if constexpr (C::NS == 1) {                        // 16 SIMT warps: 32 columns per half
                     uint32_t v0[16];
                     tc::tmem_ld_16x256b_x4(taddr + cb, v0);
                     tc::tmem_ld_wait();
-                    epi1_frag64<C, 4>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                    epi1_frag64<C, 4>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane, fr4);
                 } else if constexpr (hb == 64) {
                     // stacked operand: lanes [32q, 32q+16) = A_hi (W_hi + W_lo), lanes [32q+16, 32q+32) = A_lo (W_hi + W_lo)
                     uint32_t v0[32], v1[32];
@@ -590,7 +647,8 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
-                    epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                    epi1_frag64<C, 8>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane, fr8);
+                    gates_mma<8>(fr8, cb, NBf, wgf, wg_lo, lane, gD);
                 } else {                                       // 16 SIMT warps: 32 columns per half
                     uint32_t v0[16], v1[16];
                     tc::tmem_ld_16x256b_x4(taddr + cb, v0);
@@ -598,17 +656,56 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(v1[i]));
-                    epi1_frag64<C, 4>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane);
+                    epi1_frag64<C, 4>(v0, cb, g.fout, NBf, bf_s, m, 16 * q + (lane >> 2), lane, fr4);
+                    gates_mma<4>(fr4, cb, NBf, wgf, wg_lo, lane, gD);
                 }
             }
             if (half == 0) publish(m.half_ready);
         }
+    }
+    if constexpr (C::NS == 2) {
+        // partial gates of this warp (its 16 rows x its feats_out columns) -> shared memory; the buffer of the gates
+        // weight is free again
+        const int ra = 16 * q + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float* gp = m.gate + ((size_t)cg * C::R + ra) * 16 + 8 * j + 2 * (lane & 3);
+            *reinterpret_cast<float2*>(gp) = make_float2(gD[j][0], gD[j][1]);
+            *reinterpret_cast<float2*>(gp + 8 * 16) = make_float2(gD[j][2], gD[j][3]);
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&m.wg_empty[gi % C::WGB]);
     }
     tc::fence_before_sync();
     publish(m.feats_ready);
     TC_T(t4);
     WS_TRACE(14);
     // d. epilogue 2: vectors_out = act(gating) * Vu   (gvp.py:105-111)
+    if constexpr (C::NS == 2) {
+        TC_T(t5);
+        simt_bar<C>();
+        if (vecw) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int u = 8 * j + 2 * L.t;
+                float a0 = bg_s[u], a1 = bg_s[u + 1];
+#pragma unroll
+                for (int c2 = 0; c2 < C::NCG; ++c2) {
+                    const float2 pp = *reinterpret_cast<const float2*>(m.gate + ((size_t)c2 * C::R + L.row) * 16 + u);
+                    a0 += pp.x; a1 += pp.y;
+                }
+                if (g.sigmoid_gate) { a0 = sigmoid_acc(a0); a1 = sigmoid_acc(a1); }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * a0; v.x[c][j][1] = vu[c][j][1] * a1; }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v.x[c][2][0] = v.x[c][2][1] = 0.f;
+        }
+        TC_T(t6);
+        WS_ACC(tb + 0, t0, t1); WS_ACC(tb + 1, t1, t2); WS_ACC(tb + 2, t2, t3); WS_ACC(tb + 3, t3, t4); WS_ACC(tb + 4, t4, t5);
+        WS_ACC(tb + 5, t5, t6); WS_ACC(tb + 6, 0, 1);
+        return;
+    }
     tc::mbar_wait(m.gates_done, gi & 1);
     tc::fence_after_sync();
     TC_T(t5);

@@ -287,14 +287,43 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
         n += t.numel() + pad
 
     for name in names:
-        for key in (".to_feats_out.0.weight", ".scalar_to_vector_gates.weight"):
-            add(pack_tc_weight(sd[name + key], split))
+        add(pack_tc_weight(sd[name + ".to_feats_out.0.weight"], split))
+        # gates weight: tcgen05 slabs in the bf16 mode; mma.sync B fragments in the bf16x3 mode (the gates GEMM then
+        # runs on the warp-level tensor cores straight from the epilogue registers)
+        wg = sd[name + ".scalar_to_vector_gates.weight"]
+        add(pack_gates_frag(wg) if split else pack_tc_weight(wg, False))
         # message GVP 0 of every edge type takes the unit x_diff as its first input vector channel
         xfirst = ".edge_message_fns." in name and name.endswith(".0")
         img = pack_gvp_small(sd[name + ".Wh"], sd[name + ".Wu"], sd[name + ".to_feats_out.0.bias"],
                              sd[name + ".scalar_to_vector_gates.bias"], xfirst, split)
         add(img.view(torch.bfloat16))                # fp32 image carried in the bf16 blob (two bf16 per float)
     return torch.cat(parts).to(device), offs
+
+
+def pack_gates_frag(wg: torch.Tensor) -> torch.Tensor:
+    """scalar_to_vector_gates.weight [vout <= 16, fout] -> m16n8k16 bf16 B fragments for csrc/gvp_ws.inl gates_mma:
+    [hi | lo][k16 step S][t][n'][2 words], word 0 = (W[n][16S+2t], W[n][16S+2t+1]), word 1 = (W[n][16S+2t+8], +9) as bf16
+    pairs (low half = even k), n' = (n + 4t) & 15 (bank swizzle); hi = bf16(W), lo = bf16(W - hi).  Same byte size as
+    the tcgen05 packing (ksg * 512 B per plane)."""
+    w = wg.detach().float().cpu()
+    vout, fout = w.shape
+    ks = (fout + 15) // 16
+    full = torch.zeros(16, ks * 16)
+    full[:vout, :fout] = w
+    hi = full.to(torch.bfloat16).float()
+    planes = []
+    for plane in (hi, full - hi):
+        b = plane.to(torch.bfloat16).view(torch.int16).to(torch.int64) & 0xFFFF          # [16][ks*16] bf16 bits
+        words = torch.zeros(ks, 4, 16, 2, dtype=torch.int64)
+        for t in range(4):
+            for n in range(16):
+                nsw = (n + 4 * t) & 15
+                for half in range(2):
+                    k = 2 * t + 8 * half
+                    words[:, t, nsw, half] = b[n, k::16] | (b[n, k + 1::16] << 16)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+        planes.append(words.reshape(-1))
+    return torch.cat(planes).view(torch.bfloat16)
 
 
 # shared-memory image of the small fp32 weights of one GVP (csrc/gvp_ws.inl: ws::WH_LD, WU_LD, wsm_floats)
