@@ -158,6 +158,7 @@ class HeteroBatch:
                         {nt: {k: v.to(device, non_blocking=True) for k, v in st.items()} for nt, st in self._ndata.items()},
                         {et: (_edge_to(s, device), _edge_to(d, device)) for et, (s, d) in self._edges.items()},
                         {et: v.to(device) for et, v in self._bne.items()})
+        g._edata = {et: {k: v.to(device) for k, v in st.items()} for et, st in self._edata.items()}
         return g
 
     # ---- construction helpers
@@ -207,7 +208,10 @@ def batch(graphs: List[HeteroBatch]) -> HeteroBatch:
             so += g.num_nodes(et[0]); do += g.num_nodes(et[2])
         edges[et] = (torch.cat(ss), torch.cat(dd))
         bne[et] = torch.cat([g.batch_num_edges(et) for g in graphs])
-    return HeteroBatch(bnn, nd, edges, bne)
+    out = HeteroBatch(bnn, nd, edges, bne)
+    for et, st in graphs[0]._edata.items():
+        out._edata[et] = {k: torch.cat([g._edata[et][k] for g in graphs]) for k in st}
+    return out
 
 
 def unbatch(g: HeteroBatch) -> List[HeteroBatch]:
@@ -224,8 +228,13 @@ def unbatch(g: HeteroBatch) -> List[HeteroBatch]:
             s, d = g._edges[et]
             edges[et] = (s[eoff[et]:eoff[et] + ne] - noff[et[0]], d[eoff[et]:eoff[et] + ne] - noff[et[2]])
             bne[et] = torch.tensor([ne], device=s.device)
-            eoff[et] += ne
-        out.append(HeteroBatch({nt: torch.tensor([nn_[nt]], device=g.device) for nt in NTYPES}, nd, edges, bne))
+        one = HeteroBatch({nt: torch.tensor([nn_[nt]], device=g.device) for nt in NTYPES}, nd, edges, bne)
+        for et, st in g._edata.items():
+            ne = int(g.batch_num_edges(et)[b])
+            one._edata[et] = {k: v[eoff[et]:eoff[et] + ne] for k, v in st.items()}
+        for et in CANONICAL_ETYPES:
+            eoff[et] += int(g.batch_num_edges(et)[b])
+        out.append(one)
         for nt in NTYPES:
             noff[nt] += nn_[nt]
     return out
@@ -242,3 +251,29 @@ def readout_nodes(g, feat, op="mean", ntype=None):
     if op == "mean":
         out = out / counts.to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
     return out
+
+
+def build_initial_complex_graph(rec_atom_positions: torch.Tensor, rec_atom_features: torch.Tensor, pocket_res_idx: torch.Tensor,
+                                n_keypoints: int, cutoffs: dict, lig_atom_positions: torch.Tensor = None,
+                                lig_atom_features: torch.Tensor = None) -> HeteroBatch:
+    """The raw (un-encoded) graph of one complex, as the reference's data pipeline builds it
+    (data_processing/pdbbind_processing.py:221-274): rr = radius graph (cutoffs['rr'], at most 100 neighbours) with the
+    `same_res` edge flag, rk = every pocket atom -> every keypoint placeholder, the other edge types empty."""
+    from .receptor_encoder import radius_graph
+    if (lig_atom_positions is not None) ^ (lig_atom_features is not None):
+        raise ValueError('ligand position and features must be either be both supplied or both left as None')
+    dev = rec_atom_positions.device
+    n_rec = rec_atom_positions.shape[0]
+    n_lig = 0 if lig_atom_positions is None else lig_atom_positions.shape[0]
+    cnt = lambda n: torch.tensor([n], dtype=torch.long, device=dev)
+    rr_s, rr_d = radius_graph(rec_atom_positions.float(), cutoffs['rr'], cnt(n_rec), 100)
+    rk_s = torch.arange(n_rec, device=dev).repeat(n_keypoints)
+    rk_d = torch.arange(n_keypoints, device=dev).repeat_interleave(n_rec)
+    nd = {"rec": {"x_0": rec_atom_positions, "h_0": rec_atom_features}, "kp": {}, "lig": {}}
+    if lig_atom_positions is not None:
+        nd["lig"] = {"x_0": lig_atom_positions, "h_0": lig_atom_features}
+    g = HeteroBatch({"rec": cnt(n_rec), "kp": cnt(n_keypoints), "lig": cnt(n_lig)}, nd,
+                    {("rec", "rr", "rec"): (rr_s, rr_d), ("rec", "rk", "kp"): (rk_s, rk_d)},
+                    {("rec", "rr", "rec"): cnt(rr_s.shape[0]), ("rec", "rk", "kp"): cnt(rk_s.shape[0])})
+    g.edges["rr"].data["same_res"] = (pocket_res_idx[rr_s] == pocket_res_idx[rr_d]).view(-1, 1)
+    return g

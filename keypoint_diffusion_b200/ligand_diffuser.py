@@ -15,21 +15,9 @@ import torch.nn as nn
 from . import hetero, ops
 from .dynamics import LigRecDynamics, LigRecDynamicsGVP
 from .n_nodes_dist import LigandSizeDistribution
-from .param_layout import ParamTree, egnn_rec_encoder_shapes, gvp_rec_encoder_shapes
+from .receptor_encoder import ReceptorEncoder, ReceptorEncoderGVP
 from .schedule import PredefinedNoiseSchedule, alpha, coefficient_table, sigma, sigma_and_alpha_t_given_s
 from .utils import copy_graph, get_batch_idxs
-
-
-class _LearnedReceptorEncoder(ParamTree):
-    """Parameter holder for ReceptorEncoder / ReceptorEncoderGVP (reference
-    models/receptor_encoder.py:381-555, models/receptor_encoder_gvp.py:97-322) so that shipped
-    checkpoints load with strict=True.  Encoding raw pockets is the row after this path
-    (SURVEY.md section 8f #1) and is not implemented yet: start from encoded pockets."""
-
-    def forward(self, g, batch_idxs=None):
-        raise NotImplementedError(
-            "learned receptor encoders are outside the sampling hot path (SURVEY 8f #1): pass already-encoded "
-            "pockets (kp x_0/h_0[/v_0] + kk edges) to sample_from_encoded_receptors")
 
 
 class FixedReceptorEncoder(nn.Module):
@@ -81,9 +69,8 @@ class KeypointDiffusion(nn.Module):
         if rec_encoder_type not in ['learned', 'fixed']:
             raise ValueError(f'Receptor encoder type must be either "learned" or "fixed". Got {rec_encoder_type=} instead.')
         if rec_encoder_type == 'learned':
-            cfg = {**graph_config, **rec_encoder_config}
-            shapes = egnn_rec_encoder_shapes(**cfg) if architecture == 'egnn' else gvp_rec_encoder_shapes(**cfg)
-            self.rec_encoder = _LearnedReceptorEncoder(shapes)
+            encoder_class = ReceptorEncoder if architecture == 'egnn' else ReceptorEncoderGVP
+            self.rec_encoder = encoder_class(**graph_config, **rec_encoder_config)
         else:
             self.rec_encoder = FixedReceptorEncoder(rec_encoder_config['vector_size'] if architecture == 'gvp' else None)
         object.__setattr__(self, "_samplers", {})
@@ -211,7 +198,15 @@ class KeypointDiffusion(nn.Module):
         """ref_graphs: one single-complex graph per receptor.  ``encoded=True`` skips the receptor
         encoder (graphs already hold kp nodes + kk edges).  init_lig_pos: optional [3] tensor per receptor."""
         n_receptors = len(ref_graphs)
-        enc_graphs = ref_graphs if encoded else hetero.unbatch(self.encode_receptors(hetero.batch(ref_graphs)))
+        if encoded:
+            enc_graphs = ref_graphs
+        else:
+            # encode the pockets rec_enc_batch_size at a time (reference :277-287), on the device the weights live on
+            dev = self.gamma.gamma.device
+            enc_graphs = []
+            for b in range(ceil(n_receptors / rec_enc_batch_size)):
+                chunk = hetero.batch(ref_graphs[b * rec_enc_batch_size:(b + 1) * rec_enc_batch_size])
+                enc_graphs.extend(hetero.unbatch(self.encode_receptors(chunk if chunk.device == dev else chunk.to(dev))))
         graphs, centers = [], []
         for rec_idx, ref_graph in enumerate(enc_graphs):
             sizes = n_lig_atoms[rec_idx]

@@ -102,3 +102,10 @@ def ligand_noise_state(n_lig_atoms: List[int], atom_nf: int, seed: int):
     x = 2.0 * torch.randn(N, 3, generator=g)
     h = torch.randn(N, atom_nf, generator=g)
     return x, h
+
+
+def raw_pocket(pocket_id: int, n_atoms: int = 336, n_elements: int = 10, atoms_per_residue: int = 8):
+    """An un-encoded synthetic pocket for the learned receptor encoders: (positions [n,3], one-hot elements [n,F],
+    residue index [n]); the all-atom lattice above with consecutive atoms grouped into residues."""
+    pk = all_atom_pocket(pocket_id, n_atoms, n_elements)
+    return pk.kp_x, pk.kp_h, torch.arange(pk.n_kp) // atoms_per_residue

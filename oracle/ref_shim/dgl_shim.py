@@ -50,10 +50,11 @@ class _MsgBuiltin:
 
 
 def _bcast_mul(a, b):
+    # DGL broadcasts the FEATURE shapes numpy-style (right-aligned): (3,) x (1, 1) -> (1, 3)
     while b.dim() < a.dim():
-        b = b.unsqueeze(-1)
+        b = b.unsqueeze(1)
     while a.dim() < b.dim():
-        a = a.unsqueeze(-1)
+        a = a.unsqueeze(1)
     return a * b
 
 
@@ -83,6 +84,11 @@ class _EdgeBatch:
         self.src = _Gather(g._ndata[cet[0]], s)
         self.dst = _Gather(g._ndata[cet[2]], d)
         self.data = g._edata[cet]
+
+
+class _NodeBatch:
+    def __init__(self, mailbox):
+        self.mailbox = mailbox
 
 
 class _Gather:
@@ -325,6 +331,20 @@ class DGLHeteroGraph:
 
     def update_all(self, mfunc, rfunc, etype=None):
         cet = self.to_canonical_etype(etype)
+        if not isinstance(rfunc, _Reducer):
+            # user-defined reduce function over nodes.mailbox (reference receptor_encoder.py:294,299-300).  DGL buckets
+            # nodes by in-degree and orders each node's mailbox by edge id; the reference only uses this with one
+            # common in-degree (k nearest neighbours per keypoint), which is the case restated here.
+            msgs = mfunc(_EdgeBatch(self, cet))
+            d = self._edges[cet][1]
+            n = self._num_nodes[cet[2]]
+            deg = torch.bincount(d, minlength=n)
+            assert n > 0 and bool((deg == deg[0]).all()) and int(deg[0]) > 0, "mailbox stand-in needs one common in-degree"
+            order = torch.sort(d, stable=True).indices
+            mailbox = {k: v[order].reshape((n, int(deg[0])) + tuple(v.shape[1:])) for k, v in msgs.items()}
+            for k, v in rfunc(_NodeBatch(mailbox)).items():
+                self._ndata[cet[2]][k] = v
+            return
         self._ndata[cet[2]][rfunc.out] = self._reduce(cet, mfunc, rfunc)
 
     def multi_update_all(self, etype_dict, cross_reducer="sum"):

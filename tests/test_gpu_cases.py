@@ -255,3 +255,40 @@ def test_fixed_encoder_path():
     model.n_timesteps = 1000
     pos, feat = model.sample_from_encoded_receptors(enc, init_lig_pos=torch.zeros(B, 3), seed=2)
     assert [p.shape for p in pos] == [(9, 3), (14, 3)] and all(torch.isfinite(p).all() for p in pos)
+
+
+@pytest.mark.parametrize("arch", ["egnn", "gvp"])
+def test_raw_pocket_to_ligands_with_learned_encoder(arch):
+    """raw pocket atoms -> build_initial_complex_graph -> learned receptor encoder -> sampler, through
+    sample_given_pocket / _sample as a user of the reference calls them (no init_lig_pos: the pocket centroid is used)."""
+    import yaml
+    import os
+    from pathlib import Path
+    from helpers import GOLDEN
+    from keypoint_diffusion_b200 import hetero, model_from_config, synthetic
+    os.chdir(Path(__file__).resolve().parents[1])
+    cfg = yaml.safe_load(open(GOLDEN / "shipped_configs.yml"))[f"{arch}_20kp"]
+    torch.manual_seed(4)
+    model = model_from_config(cfg).to(_dev()).eval()
+    cut = cfg["graph"]["graph_cutoffs"]
+    raws = []
+    for i, n in enumerate((150, 211)):
+        x, h, res = synthetic.raw_pocket(i, n, 10)
+        raws.append(hetero.build_initial_complex_graph(x, h, res, cfg["graph"]["n_keypoints"], cut))
+    with torch.no_grad():
+        enc = model.encode_receptors(hetero.batch(raws).to(_dev()))
+        one = model.encode_receptors(raws[1].to(_dev()))
+    assert enc.num_nodes("kp") == 40 and enc.nodes["kp"].data["h_0"].shape == (40, 128)
+    assert torch.isfinite(enc.nodes["kp"].data["x_0"]).all() and torch.isfinite(enc.nodes["kp"].data["h_0"]).all()
+    if arch == "gvp":
+        assert enc.nodes["kp"].data["v_0"].shape == (40, 16, 3)
+    # encoding the pockets one at a time gives the same keypoints as encoding the batch
+    assert rel_err(one.nodes["kp"].data["x_0"].cpu(), enc.nodes["kp"].data["x_0"][20:].cpu()) < 1e-4
+    assert rel_err(one.nodes["kp"].data["h_0"].cpu(), enc.nodes["kp"].data["h_0"][20:].cpu()) < 1e-4
+    torch.manual_seed(11)
+    samples = model._sample(raws, [[9, 14], [12]], rec_enc_batch_size=1, diff_batch_size=2)
+    assert [len(s["positions"]) for s in samples] == [2, 1]
+    assert [p.shape for p in samples[0]["positions"]] == [(9, 3), (14, 3)] and samples[1]["features"][0].shape == (12, 10)
+    assert all(torch.isfinite(p).all() for s in samples for p in s["positions"])
+    pos, feat = model.sample_given_pocket(raws[0], torch.tensor([7, 8]))
+    assert [p.shape for p in pos] == [(7, 3), (8, 3)] and [f.shape for f in feat] == [(7, 10), (8, 10)]
