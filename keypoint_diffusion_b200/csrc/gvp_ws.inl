@@ -50,10 +50,11 @@ struct Sm {
     unsigned char* A[2];
     unsigned char* ring;
     unsigned char* Wg[2];
-    float* wsm;
+    float* wsm;       // Wh | Wu of the current GVP (one buffer, refilled after every Vu GEMM)
+    float* bias;      // bf | bg, two buffers (GVP parity)
     float* gate;      // NS = 1: gates [R][GATE_LD]; NS = 2: per-column-group partial gates [NCG][R][16]
     int *src_s, *dst_s, *seg, *rp;
-    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full, *half_ready;
+    uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full, *half_ready, *wsm_empty;
     uint32_t* tmem_slot;
     int* warp_cnt;
 };
@@ -63,10 +64,15 @@ template <class C>
 __host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C::KCS + 127) & ~(size_t)127; }
 
 
+// Stages of the weight ring.  The ring is latency-bound (a slab is re-requested when its MMA has completed and lands
+// ~1350 cycles later), so the k-step rate is (MMA completion + copy latency) / stages: as deep as shared memory allows.
+template <class C>
+constexpr int GST = C::NS == 1 ? 10 : 6;
+
 template <class C>
 static size_t smem_bytes(int kch) {
-    return plane_bytes<C>(kch) + (size_t)C::STAGES * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * MAXG * C::WSM +
-           sizeof(float) * (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * C::STAGES + 10) + 16 + 128;
+    return plane_bytes<C>(kch) + (size_t)GST<C> * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * (C::WSM_W + 2 * C::WSM_B) +
+           sizeof(float) * (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * GST<C> + 12) + 16 + 128;
 }
 
 template <class C>
@@ -75,18 +81,19 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.A[0] = smem;
     m.A[1] = smem + (C::NS - 1) * 256;            // lo rows: 2 row groups after their hi rows
     m.ring = smem + plane_bytes<C>(kch);
-    m.Wg[0] = m.ring + C::STAGES * C::SLAB;
+    m.Wg[0] = m.ring + GST<C> * C::SLAB;
     m.Wg[1] = m.Wg[0] + C::WG_BYTES;
     m.wsm = reinterpret_cast<float*>(m.Wg[0] + C::WGB * C::WG_BYTES);
-    m.gate = m.wsm + MAXG * C::WSM;
+    m.bias = m.wsm + C::WSM_W;
+    m.gate = m.bias + 2 * C::WSM_B;
     m.src_s = reinterpret_cast<int*>(m.gate + (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R);
     m.dst_s = m.src_s + C::R;
     m.seg = m.dst_s + C::R;            // [R + 8]
     m.rp = m.seg + C::R + 8;           // [2R]
     m.warp_cnt = m.rp + 2 * C::R;      // [8]
     m.full = reinterpret_cast<uint64_t*>(m.warp_cnt + 8);
-    m.empty = m.full + C::STAGES;
-    m.wg_full = m.empty + C::STAGES;   // [2]
+    m.empty = m.full + GST<C>;
+    m.wg_full = m.empty + GST<C>;      // [2]
     m.wg_empty = m.wg_full + 2;        // [2]
     m.feats_ready = m.wg_empty + 2;
     m.tail_ready = m.feats_ready + 1;
@@ -94,7 +101,8 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.gates_done = m.acc_done + 1;
     m.wsm_full = m.gates_done + 1;
     m.half_ready = m.wsm_full + 1;
-    m.tmem_slot = reinterpret_cast<uint32_t*>(m.half_ready + 1);
+    m.wsm_empty = m.half_ready + 1;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.wsm_empty + 1);
     return m;
 }
 
@@ -103,7 +111,7 @@ __device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n
 
 template <class C>
 __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
-    for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
+    for (int i = 0; i < GST<C>; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
     // wg_empty: NS = 1 the tcgen05 gates GEMM commits it; NS = 2 every SIMT warp arrives after its mma.sync gates
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], C::NS == 2 ? C::NW : 1); }
     tc::mbar_init(m.feats_ready, C::NW);
@@ -112,6 +120,7 @@ __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
     tc::mbar_init(m.gates_done, 1);
     tc::mbar_init(m.wsm_full, 1);
     tc::mbar_init(m.half_ready, C::NW);
+    tc::mbar_init(m.wsm_empty, C::NWV);
     tc::fence_barrier_init();
 }
 
@@ -164,17 +173,33 @@ __device__ __forceinline__ void teardown(uint32_t tmem) {
     if (C::CL > 1) tc::cluster_sync();      // no CTA leaves while a peer may still signal its barriers
 }
 
+// Order of the feats GEMM's k-steps.  bf16x3 (NS = 2), GVPs after the first of a chain: epilogue 1 of the previous GVP
+// writes the A columns in two halves per column group, and the k-steps over the first halves are issued (into the
+// other TMEM accumulator) while the second halves are still being produced -- so sequence position i maps to k-step
+// j = first halves of all column groups, then second halves, then the |Vh| tail.  Otherwise j = i.
+template <class C>
+__device__ __forceinline__ int kstep_at(int i, int ksm, bool chained) {
+    if (C::NS != 2 || !chained || i >= ksm) return i;
+    constexpr int kpg = (256 / C::NCG) / 16, kph = kpg / 2;      // k-steps per column group / per half
+    int n0 = (ksm / kpg) * kph + min(ksm % kpg, kph);            // k-steps that lie in first halves
+    const bool second = i >= n0;
+    const int r = second ? i - n0 : i;
+    // r-th k-step of its half-set: full groups contribute kph each (the last group may be partial)
+    if (!second) return (r / kph) * kpg + (r % kph);
+    return (r / kph) * kpg + kph + (r % kph);
+}
+template <class C>
+__device__ __forceinline__ int first_half_ksteps(int ksm) {
+    constexpr int kpg = (256 / C::NCG) / 16, kph = kpg / 2;
+    return (ksm / kpg) * kph + min(ksm % kpg, kph);
+}
+
 // ------------------------------------------------------------------ producer (one thread)
 template <class C>
 __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool dead = false) {
     uint32_t it = 0;
     const uint32_t rank = C::CL > 1 ? tc::cluster_ctarank() : 0u;
     constexpr uint16_t mask = (uint16_t)((1u << C::CL) - 1u);
-    if (!dead) {                // shared-memory images of the small fp32 weights of the whole chain
-        tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)(n_gvps * C::WSM * sizeof(float)));
-        for (int g = 0; g < n_gvps; ++g)
-            tc::bulk_g2s(m.wsm + g * C::WSM, C::NS == 2 ? gv[g].wsmP2 : gv[g].wsmP, C::WSM * sizeof(float), m.wsm_full);
-    }
 #ifdef KPD_WS_TRACE
     unsigned long long tp[64];
 #endif
@@ -184,9 +209,19 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
         const uint32_t slab = C::NS * 2 * (NBf / 8) * 128;
         const int b = g % C::WGB;
         const uint4* WfP = C::NS == 2 ? w.WfP2 : w.WfP;
-        for (int j = 0; j < ksf; ++j, ++it) {
-            const uint32_t st = it % C::STAGES;
-            if (it >= (uint32_t)C::STAGES) tc::mbar_wait(&m.empty[st], ((it / C::STAGES) - 1) & 1);
+        if (!dead) {
+            // shared-memory image of this GVP's small fp32 weights: Wh | Wu into the single buffer once the vector warps
+            // are through the previous GVP's Vu GEMM, bf | bg into the buffer of this GVP's parity
+            if (g > 0) tc::mbar_wait(m.wsm_empty, (g - 1) & 1);
+            const float* img = C::NS == 2 ? w.wsmP2 : w.wsmP;
+            tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)(C::WSM * sizeof(float)));
+            tc::bulk_g2s(m.wsm, img, C::WSM_W * sizeof(float), m.wsm_full);
+            tc::bulk_g2s(m.bias + (g & 1) * C::WSM_B, img + C::WSM_W, C::WSM_B * sizeof(float), m.wsm_full);
+        }
+        for (int i = 0; i < ksf; ++i, ++it) {
+            const int j = kstep_at<C>(i, w.fin >> 4, g > 0);
+            const uint32_t st = it % GST<C>;
+            if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
             tc::mbar_arrive_expect_tx(&m.full[st], slab);
             if (C::CL == 1) {
                 tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
@@ -234,10 +269,25 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksm = w.fin >> 4, ksg = NBf >> 4;
         const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NBf);
         const uint32_t b_k = (NBf / 8) * 128, slab1 = 2 * b_k;
-        for (int j = 0; j < ksf; ++j, ++it) {
-            if (j == ksm) { WS_TRACE(2); tc::mbar_wait(m.tail_ready, g & 1); tc::fence_after_sync(); WS_TRACE(3); }
-            const uint32_t st = it % C::STAGES;
-            tc::mbar_wait(&m.full[st], (it / C::STAGES) & 1);
+        // bf16x3: two accumulators, so that the next GVP's k-steps can start while epilogue 1 still reads this one
+        const uint32_t acc = tmem + ((C::NS == 2 && (g & 1)) ? 256u : 0u);
+        const bool chained = C::NS == 2 && g > 0;
+        const int n_first = first_half_ksteps<C>(ksm);
+        if (chained) { tc::mbar_wait(m.half_ready, (g - 1) & 1); tc::fence_after_sync(); }
+        for (int i = 0; i < ksf; ++i, ++it) {
+            const int j = kstep_at<C>(i, ksm, g > 0);
+            if (chained && i == n_first) {
+                // epilogue 1 of the previous GVP done: all of its feats_out is in A
+                tc::mbar_wait(m.feats_ready, g & 1);
+                tc::fence_after_sync();
+                WS_TRACE(5);
+            }
+            if (i == ksm) {
+                if (chained && n_first >= ksm) { tc::mbar_wait(m.feats_ready, g & 1); tc::fence_after_sync(); }
+                WS_TRACE(2); tc::mbar_wait(m.tail_ready, g & 1); tc::fence_after_sync(); WS_TRACE(3);
+            }
+            const uint32_t st = it % GST<C>;
+            tc::mbar_wait(&m.full[st], (it / GST<C>) & 1);
             tc::fence_after_sync();
 #ifdef KPD_WS_TRACE
             if (it < 64) tk[it] = clock64();
@@ -245,10 +295,10 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
-            tc::mma_bf16_ss(tmem, a0, b0, idesc, j > 0 ? 1u : 0u);
+            tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
             if (C::NS == 2) {       // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
                 const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
-                tc::mma_bf16_ss(tmem, a0, b1, idesc, 1u);
+                tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
             }
             if (C::CL == 1) tc::mma_commit(&m.empty[st]);
             else tc::mma_commit_multicast(&m.empty[st], (uint16_t)((1u << C::CL) - 1u));   // frees the slot in every CTA
@@ -257,10 +307,7 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         WS_TRACE(4);
         if constexpr (C::NS == 2) {
             // bf16x3: the gates GEMM runs on the warp-level tensor cores straight from the epilogue registers
-            // (gates_mma); only wait until epilogue 1 has written feats_out and drained the accumulator
-            tc::mbar_wait(m.feats_ready, (g + 1) & 1);
-            tc::fence_after_sync();
-            WS_TRACE(5);
+            // (gates_mma); the next GVP's k-steps wait for epilogue 1 half by half (above)
             continue;
         }
         // gates GEMM, issued progressively: every epilogue-1 warp writes its feats_out columns in two halves, so the
@@ -314,8 +361,8 @@ __device__ __forceinline__ void drain(const GvpW* gv, int n_gvps, Sm& m) {
     for (int g = 0; g < n_gvps; ++g) {
         const int ksf = (gv[g].fin + gv[g].hd + 15) >> 4;
         for (int j = 0; j < ksf; ++j, ++it) {
-            const uint32_t st = it % C::STAGES;
-            tc::mbar_wait(&m.full[st], (it / C::STAGES) & 1);
+            const uint32_t st = it % GST<C>;
+            tc::mbar_wait(&m.full[st], (it / GST<C>) & 1);
             for (uint32_t r = 0; r < (uint32_t)C::CL; ++r) tc::mbar_arrive_remote(tc::map_to_cta(&m.empty[st], r));
         }
     }
@@ -561,15 +608,15 @@ template <class C>
 __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uint32_t tmem, VF& v, const Lane& L,
                                          int rows_valid, int tb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* Wh_s = m.wsm + gi * C::WSM;
+    const float* Wh_s = m.wsm;
     const float* Wu_s = Wh_s + C::NS * WH_SZ;
-    const float* bf_s = Wu_s + C::NS * WU_SZ;
+    const float* bf_s = m.bias + (gi & 1) * C::WSM_B;
     const float* bg_s = bf_s + 256;
     const int NBf = (g.fout + 15) & ~15;
     // a. Vh = V^T Wh (gvp.py:96) on the warp-level tensor cores; sh = sqrt(clamp(|Vh|^2)) -> A[:, fin + h] (gvp.py:99)
     TC_T(t0);
     WS_TRACE(10);
-    if (gi == 0) tc::mbar_wait(m.wsm_full, 0);
+    tc::mbar_wait(m.wsm_full, gi & 1);
     float vh[3][3][2];
     float vu[3][2][2];
     [[maybe_unused]] float gD[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};     // bf16x3: this warp's partial gates
@@ -597,12 +644,16 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     TC_T(t1);
     WS_TRACE(11);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
-    if (vecw) vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
+    if (vecw) {
+        vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(m.wsm_empty);     // Wh | Wu may be overwritten with the next GVP's
+    }
     // c. epilogue 1: feats_out = SiLU(acc + b) -> A[:, 0:fout)   (gvp.py:101-103)
     const int q = warp & 3, cg = warp >> 2;
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
     const bool valid_e = C::R == 128 ? true : lane < 16;
-    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + ((C::NS == 2 && (gi & 1)) ? 256u : 0u);
     TC_T(t2);
     WS_TRACE(12);
     tc::mbar_wait(m.acc_done, gi & 1);
