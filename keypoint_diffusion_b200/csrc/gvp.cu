@@ -402,6 +402,7 @@ struct kpd_gvp_model {
     GvpW head[MAXG];
     const float* WoT; const float* bo;
     size_t smem, smem_node, smem_ws1, smem_ws2, smem_ws1n;
+    bool edge_pair;     // bf16x3: the edge kernel runs as CTA pairs (message GVP weights pair-packed, pack.pack_gvp_tc)
     int kch;           // k-chunks of the bf16 tile (tensor-core mode)
     int mode;          // 0 = fp32 SIMT, 1 = bf16 tcgen05, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
     bool tc_ready, tc2_ready;
@@ -512,6 +513,11 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         m->kch = 2 * ((wmax + 15) / 16);
         m->smem_ws1 = ws::smem_bytes<WsBf16>(m->kch);
         m->smem_ws2 = ws::smem_bytes<WsSplit>(m->kch);
+#ifdef KPD_EDGE_PAIR      // experimental (slower): needs pack_gvp_tc(..., pair=True), i.e. KPD_EDGE_PAIR=1 at run time
+        m->edge_pair = m->cfg.n_hidden_scalars % 32 == 0;
+#else
+        m->edge_pair = false;
+#endif
         m->smem_ws1n = ws::smem_bytes<WsBf16N>(m->kch);
         m->mode = 0;
         m->tc_ready = false;
@@ -557,6 +563,7 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
     }
     if (nsplit == 2) {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplitPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws2);
@@ -704,6 +711,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             int tiles_tc = 1;
             for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, edge_rows); if (t > tiles_tc) tiles_tc = t; }
             if (m->mode == 1) launch_clustered(gvp_edge_ws_kernel<WsBf16>, dim3(tiles_tc, W.n_et), WsBf16::NT, m->smem_ws1, st, WsBf16::CL, L);
+            else if (m->edge_pair) launch_clustered(gvp_edge_ws_kernel<WsSplitPair>, dim3(tiles_tc, W.n_et), WsSplitPair::NT, m->smem_ws2, st, 2, L);
             else launch_clustered(gvp_edge_ws_kernel<WsSplit>, dim3(tiles_tc, W.n_et), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, L);
             KPD_TRY(check_launch("gvp_edge_ws_kernel"));
         } else {

@@ -29,9 +29,12 @@ __device__ unsigned long long g_ws_times[64];   // edge kernel: base 0, node ker
 
 // event trace of ONE CTA (block (1, 1) of the edge kernel) for timeline analysis: (tag, warp, clock) triples
 #ifdef KPD_WS_TRACE
+#ifndef KPD_TRACE_BX
+#define KPD_TRACE_BX 2          // (even: the leader of a CTA pair)
+#endif
 __device__ unsigned long long g_ws_trace[3 * 2048];
 __device__ int g_ws_trace_n;
-#define WS_TRACE(tag) do { if (blockIdx.x == 1 && blockIdx.y == 1 && (threadIdx.x & 31) == 0) { \
+#define WS_TRACE(tag) do { if (blockIdx.x == KPD_TRACE_BX && blockIdx.y == 1 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) >= 16)) { \
         const int _i = atomicAdd(&g_ws_trace_n, 1); \
         if (_i < 2048) { g_ws_trace[3 * _i] = (tag); g_ws_trace[3 * _i + 1] = threadIdx.x >> 5; g_ws_trace[3 * _i + 2] = clock64(); } } } while (0)
 #else
@@ -57,6 +60,9 @@ struct Sm {
     uint64_t *full, *empty, *wg_full, *wg_empty, *feats_ready, *tail_ready, *acc_done, *gates_done, *wsm_full, *half_ready, *wsm_empty;
     uint32_t* tmem_slot;
     int* warp_cnt;
+    // CTA pairs (Cfg::CL == 2): rank in the pair; solo = the peer's tile is empty (it only lends its half of B)
+    uint32_t rank;
+    bool solo;
 };
 
 // bytes of the A operand (all MMA_M rows)
@@ -103,6 +109,8 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     m.half_ready = m.wsm_full + 1;
     m.wsm_empty = m.half_ready + 1;
     m.tmem_slot = reinterpret_cast<uint32_t*>(m.wsm_empty + 1);
+    m.rank = 0;
+    m.solo = false;
     return m;
 }
 
@@ -111,15 +119,18 @@ __device__ __forceinline__ void simt_bar() { asm volatile("bar.sync 1, %0;" ::"n
 
 template <class C>
 __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
-    for (int i = 0; i < GST<C>; ++i) { tc::mbar_init(&m.full[i], 1); tc::mbar_init(&m.empty[i], C::CL); }
+    // CTA pairs: the leader's MMA thread waits for BOTH CTAs' operands, so the leader's full / *_ready barriers count
+    // one more arrival: the peer's forwarding threads (relay(), forward_ready()); everything else stays per CTA
+    const uint32_t extra = (C::CL == 2 && m.rank == 0 && !m.solo) ? 1u : 0u;
+    for (int i = 0; i < GST<C>; ++i) { tc::mbar_init(&m.full[i], (C::CL == 2 && m.rank == 0) ? 2 : 1); tc::mbar_init(&m.empty[i], 1); }
     // wg_empty: NS = 1 the tcgen05 gates GEMM commits it; NS = 2 every SIMT warp arrives after its mma.sync gates
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], C::NS == 2 ? C::NW : 1); }
-    tc::mbar_init(m.feats_ready, C::NW);
-    tc::mbar_init(m.tail_ready, C::NWV);
+    tc::mbar_init(m.feats_ready, C::NW + extra);
+    tc::mbar_init(m.tail_ready, C::NWV + extra);
     tc::mbar_init(m.acc_done, 1);
     tc::mbar_init(m.gates_done, 1);
     tc::mbar_init(m.wsm_full, 1);
-    tc::mbar_init(m.half_ready, C::NW);
+    tc::mbar_init(m.half_ready, C::NW + extra);
     tc::mbar_init(m.wsm_empty, C::NWV);
     tc::fence_barrier_init();
 }
@@ -130,14 +141,17 @@ template <class C>
 __device__ __forceinline__ uint32_t setup(Sm& m, int kch) {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) init_barriers<C>(m);
-    if (warp == C::NW) { tc::tmem_alloc(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish(); }
+    if (warp == C::NW) {
+        if (C::CL == 2) { tc::tmem_alloc_pair(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish_pair(); }
+        else { tc::tmem_alloc(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish(); }
+    }
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     const int nz = (int)(plane_bytes<C>(kch) / 16);
     for (int i = tid; i < nz; i += C::NT) reinterpret_cast<uint4*>(m.A[0])[i] = z;
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
-    if (C::CL > 1) tc::cluster_sync();      // every CTA's barriers exist before a peer multicasts into it
+    if (C::CL > 1) tc::cluster_sync();      // both CTAs' barriers and TMEM exist before the pair's first MMA / remote arrive
     tc::fence_after_sync();
     return *m.tmem_slot;
 }
@@ -169,8 +183,11 @@ template <class C>
 __device__ __forceinline__ void teardown(uint32_t tmem) {
     tc::fence_before_sync();
     __syncthreads();
-    if ((threadIdx.x >> 5) == C::NW) tc::tmem_dealloc(tmem, TMEM_COLS);
-    if (C::CL > 1) tc::cluster_sync();      // no CTA leaves while a peer may still signal its barriers
+    if (C::CL > 1) tc::cluster_sync();      // no CTA frees TMEM or leaves while the pair's MMAs / arrives may still touch it
+    if ((threadIdx.x >> 5) == C::NW) {
+        if (C::CL == 2) tc::tmem_dealloc_pair(tmem, TMEM_COLS);
+        else tc::tmem_dealloc(tmem, TMEM_COLS);
+    }
 }
 
 // Order of the feats GEMM's k-steps.  bf16x3 (NS = 2), GVPs after the first of a chain: epilogue 1 of the previous GVP
@@ -198,8 +215,6 @@ __device__ __forceinline__ int first_half_ksteps(int ksm) {
 template <class C>
 __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool dead = false) {
     uint32_t it = 0;
-    const uint32_t rank = C::CL > 1 ? tc::cluster_ctarank() : 0u;
-    constexpr uint16_t mask = (uint16_t)((1u << C::CL) - 1u);
 #ifdef KPD_WS_TRACE
     unsigned long long tp[64];
 #endif
@@ -222,16 +237,17 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
             const int j = kstep_at<C>(i, w.fin >> 4, g > 0);
             const uint32_t st = it % GST<C>;
             if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
-            tc::mbar_arrive_expect_tx(&m.full[st], slab);
             if (C::CL == 1) {
+                tc::mbar_arrive_expect_tx(&m.full[st], slab);
                 tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
             } else {
-                // this CTA fetches 1/CL of the slab and multicasts it to the whole cluster; every CTA's full[st]
-                // expects the whole slab (the CL parts arrive from the CL producers)
-                const uint32_t part = slab / C::CL;
-                tc::bulk_g2s_multicast(m.ring + (size_t)st * C::SLAB + rank * part,
-                                       reinterpret_cast<const unsigned char*>(WfP) + (size_t)j * slab + rank * part, part,
-                                       &m.full[st], mask);
+                // CTA pair: this CTA holds rows [rank * N/2, (rank + 1) * N/2) of the weight; pack.pack_tc_weight_pair
+                // stores the slab as [half][hi, lo][2 k-chunks][N/16 row groups x 128 B]: one contiguous copy per CTA
+                // (four 2 KB pieces of the single-CTA packing instead were 2.5x slower: measured)
+                const uint32_t half = C::NS * 2 * (NBf / 16) * 128;
+                tc::mbar_arrive_expect_tx(&m.full[st], half);
+                tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, reinterpret_cast<const unsigned char*>(WfP) + (size_t)j * slab + m.rank * half,
+                             half, &m.full[st]);
             }
 #ifdef KPD_WS_TRACE
             if (it < 64) tp[it] = clock64();
@@ -245,7 +261,7 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
         }
     }
 #ifdef KPD_WS_TRACE
-    if (blockIdx.x == 1 && blockIdx.y == 1) {
+    if (blockIdx.x == KPD_TRACE_BX && blockIdx.y == 1) {
         for (uint32_t i = 0; i < it && i < 64; ++i) {
             const int k = atomicAdd(&g_ws_trace_n, 1);
             if (k < 2048) { g_ws_trace[3 * k] = 100 + i; g_ws_trace[3 * k + 1] = threadIdx.x >> 5; g_ws_trace[3 * k + 2] = tp[i]; }
@@ -256,38 +272,46 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
 
 // ------------------------------------------------------------------ MMA issuer (one thread)
 template <class C>
+__device__ __forceinline__ void wait_ready(uint64_t* bar, uint32_t parity) {     // barriers the peer CTA also arrives on
+#ifdef KPD_PAIR_CLUSTER_ACQUIRE
+    if (C::CL == 2) { tc::mbar_wait_cluster(bar, parity); return; }
+#endif
+    tc::mbar_wait(bar, parity);
+}
+template <class C>
 __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_t tmem) {
     uint32_t it = 0;
 #ifdef KPD_WS_TRACE
     unsigned long long tk[64];
 #endif
-    tc::mbar_wait(m.feats_ready, 0);
+    wait_ready<C>(m.feats_ready, 0);
     tc::fence_after_sync();
     WS_TRACE(1);
     for (int g = 0; g < n_gvps; ++g) {
         const GvpW& w = gv[g];
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksm = w.fin >> 4, ksg = NBf >> 4;
-        const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NBf);
-        const uint32_t b_k = (NBf / 8) * 128, slab1 = 2 * b_k;
+        constexpr bool PAIR = C::CL == 2;
+        const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 2 * C::MMA_M : C::MMA_M, NBf);
+        const uint32_t b_k = PAIR ? (NBf / 16) * 128 : (NBf / 8) * 128, slab1 = 2 * b_k;    // (pair: N / 2 rows per CTA)
         // bf16x3: two accumulators, so that the next GVP's k-steps can start while epilogue 1 still reads this one
         const uint32_t acc = tmem + ((C::NS == 2 && (g & 1)) ? 256u : 0u);
         const bool chained = C::NS == 2 && g > 0;
         const int n_first = first_half_ksteps<C>(ksm);
-        if (chained) { tc::mbar_wait(m.half_ready, (g - 1) & 1); tc::fence_after_sync(); }
+        if (chained) { wait_ready<C>(m.half_ready, (g - 1) & 1); tc::fence_after_sync(); }
         for (int i = 0; i < ksf; ++i, ++it) {
             const int j = kstep_at<C>(i, ksm, g > 0);
             if (chained && i == n_first) {
                 // epilogue 1 of the previous GVP done: all of its feats_out is in A
-                tc::mbar_wait(m.feats_ready, g & 1);
+                wait_ready<C>(m.feats_ready, g & 1);
                 tc::fence_after_sync();
                 WS_TRACE(5);
             }
             if (i == ksm) {
-                if (chained && n_first >= ksm) { tc::mbar_wait(m.feats_ready, g & 1); tc::fence_after_sync(); }
-                WS_TRACE(2); tc::mbar_wait(m.tail_ready, g & 1); tc::fence_after_sync(); WS_TRACE(3);
+                if (chained && n_first >= ksm) { wait_ready<C>(m.feats_ready, g & 1); tc::fence_after_sync(); }
+                WS_TRACE(2); wait_ready<C>(m.tail_ready, g & 1); tc::fence_after_sync(); WS_TRACE(3);
             }
             const uint32_t st = it % GST<C>;
-            tc::mbar_wait(&m.full[st], (it / GST<C>) & 1);
+            wait_ready<C>(&m.full[st], (it / GST<C>) & 1);
             tc::fence_after_sync();
 #ifdef KPD_WS_TRACE
             if (it < 64) tk[it] = clock64();
@@ -295,15 +319,18 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
-            tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
+            if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
+            else tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
             if (C::NS == 2) {       // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
                 const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
-                tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
+                if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b1, idesc, 1u);
+                else tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
             }
-            if (C::CL == 1) tc::mma_commit(&m.empty[st]);
-            else tc::mma_commit_multicast(&m.empty[st], (uint16_t)((1u << C::CL) - 1u));   // frees the slot in every CTA
+            if (PAIR) tc::mma_commit_pair(&m.empty[st], 3);       // frees the slot in both CTAs
+            else tc::mma_commit(&m.empty[st]);
         }
-        tc::mma_commit(m.acc_done);
+        if (PAIR) tc::mma_commit_pair(m.acc_done, 3);
+        else tc::mma_commit(m.acc_done);
         WS_TRACE(4);
         if constexpr (C::NS == 2) {
             // bf16x3: the gates GEMM runs on the warp-level tensor cores straight from the epilogue registers
@@ -344,7 +371,7 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         WS_TRACE(6);
     }
 #ifdef KPD_WS_TRACE
-    if (blockIdx.x == 1 && blockIdx.y == 1) {
+    if (blockIdx.x == KPD_TRACE_BX && blockIdx.y == 1) {
         for (uint32_t i = 0; i < it && i < 64; ++i) {
             const int k = atomicAdd(&g_ws_trace_n, 1);
             if (k < 2048) { g_ws_trace[3 * k] = 200 + i; g_ws_trace[3 * k + 1] = threadIdx.x >> 5; g_ws_trace[3 * k + 2] = tk[i]; }
@@ -353,18 +380,36 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
 #endif
 }
 
-// A CTA of a live cluster whose own tile is empty still takes part in the shared weight stream: its producer
-// fetches its share, and this loop releases every ring slot as soon as it has filled.
+// CTA pairs: the peer's control thread tells the leader's MMA thread when the peer's half of a weight slab has landed
+// (remote arrive on the leader's full barrier, which counts its own producer + this relay).
 template <class C>
-__device__ __forceinline__ void drain(const GvpW* gv, int n_gvps, Sm& m) {
+__device__ __forceinline__ void relay(const GvpW* gv, int n_gvps, Sm& m) {
     uint32_t it = 0;
     for (int g = 0; g < n_gvps; ++g) {
         const int ksf = (gv[g].fin + gv[g].hd + 15) >> 4;
         for (int j = 0; j < ksf; ++j, ++it) {
             const uint32_t st = it % GST<C>;
             tc::mbar_wait(&m.full[st], (it / GST<C>) & 1);
-            for (uint32_t r = 0; r < (uint32_t)C::CL; ++r) tc::mbar_arrive_remote(tc::map_to_cta(&m.empty[st], r));
+            tc::mbar_arrive_remote_relaxed(tc::map_to_cta(&m.full[st], 0));
         }
+    }
+}
+
+// CTA pairs: one thread of the peer forwards the phases of its CTA's tail_ready / half_ready / feats_ready barriers to
+// the leader's (in the order the SIMT warps complete them; a phase cannot complete twice before the leader has
+// consumed the forward, so the parities cannot alias).
+template <class C>
+__device__ __forceinline__ void forward_ready(int n_gvps, Sm& m) {
+    const uint32_t feats = tc::map_to_cta(m.feats_ready, 0), tail = tc::map_to_cta(m.tail_ready, 0), half = tc::map_to_cta(m.half_ready, 0);
+    tc::mbar_wait(m.feats_ready, 0);
+    tc::mbar_arrive_remote_relaxed(feats);
+    for (int g = 0; g < n_gvps; ++g) {
+        tc::mbar_wait(m.tail_ready, g & 1);
+        tc::mbar_arrive_remote_relaxed(tail);
+        tc::mbar_wait(m.half_ready, g & 1);
+        tc::mbar_arrive_remote_relaxed(half);
+        tc::mbar_wait(m.feats_ready, (g + 1) & 1);
+        tc::mbar_arrive_remote_relaxed(feats);
     }
 }
 
@@ -411,6 +456,12 @@ __device__ __forceinline__ void publish(uint64_t* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
 }
+
+// same, on a barrier the MMA thread waits on.  In a CTA pair that thread lives in the leader CTA; the peer's warps still
+// arrive on their own CTA's barrier and ONE peer thread forwards each completed phase (forward_ready): a remote
+// release-arrive per warp would wait for the SM's in-flight bulk copies every time (measured: +15 % epilogue time).
+template <class C>
+__device__ __forceinline__ void publish_mma(const Sm& m, uint64_t* bar) { publish(bar); }
 
 // Register-resident vectors.  The 8 tile rows of a SIMT warp x 3 components form the 24 (of 32) rows of two
 // m16n8k8 MMA tiles, ordered component-major: tile 0 rows 0-7 = x, rows 8-15 = y; tile 1 rows 0-7 = z.  Lane
@@ -639,7 +690,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     tc::pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
         }
     }
-    publish(m.tail_ready);
+    publish_mma<C>(m, m.tail_ready);
     }
     TC_T(t1);
     WS_TRACE(11);
@@ -711,7 +762,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     gates_mma<4>(fr4, cb, NBf, wgf, wg_lo, lane, gD);
                 }
             }
-            if (half == 0) publish(m.half_ready);
+            if (half == 0) publish_mma<C>(m, m.half_ready);
         }
     }
     if constexpr (C::NS == 2) {
@@ -728,7 +779,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         if (lane == 0) tc::mbar_arrive(&m.wg_empty[gi % C::WGB]);
     }
     tc::fence_before_sync();
-    publish(m.feats_ready);
+    publish_mma<C>(m, m.feats_ready);
     TC_T(t4);
     WS_TRACE(14);
     // d. epilogue 2: vectors_out = act(gating) * Vu   (gvp.py:105-111)
@@ -833,6 +884,9 @@ __device__ __forceinline__ void build_segments(const Sm& m, int n) {
 using WsBf16 = ws::Cfg<128, 1, KPD_WS_CLUSTER>;    // bf16 operands, 128-row tiles (M = 128)
 // bf16 (hi, lo) rows stacked into one M = 128 operand, 64-row tiles; 8 vector warps + 8 extra epilogue warps
 using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;
+// bf16x3 edge kernel as CTA pairs (cta_group::2): two neighbouring 64-row tiles share every weight slab, each SM
+// holding (and reading) half of it
+using WsSplitPair = ws::Cfg<64, 2, 2, KPD_WS_SPLIT_XWARPS>;
 using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
 
 // ------------------------------------------------------------------ edge kernel
@@ -850,20 +904,29 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
     }
     const int E = a.rowptr[a.n_dst];
     if ((int)(blockIdx.x / C::CL) * C::CL * C::R >= E) return;      // the whole cluster is past the last edge
-    const bool dead = tile_begin >= E;                              // this CTA only helps to stream the weights
+    const bool dead = tile_begin >= E;                              // (CTA pairs) this CTA only lends its half of the weights
     const int n = min(C::R, E - tile_begin);
     extern __shared__ __align__(128) unsigned char smem_ws[];
     TC_T(e0);
     ws::Sm m = ws::carve<C>(smem_ws, L.kch);
+    if (C::CL == 2) {
+        m.rank = blockIdx.x & 1;                                    // (1-D clusters along x: rank in the pair)
+        m.solo = (int)(blockIdx.x | 1) * C::R >= E;                 // the odd CTA's tile is empty
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = L.Sdim, Vd = L.Vdim;
-    constexpr bool ASYNC = C::CL == 1;        // clusters need every CTA's barriers before any multicast: common set-up
+    constexpr bool ASYNC = C::CL == 1;        // pairs need both CTAs' barriers and TMEM before the first MMA: common set-up
     uint32_t tmem = 0;
     if (!ASYNC) tmem = ws::setup<C>(m, L.kch);
     if (warp >= C::NW) {
         if (ASYNC) { ws::control_setup<C>(m); tmem = *m.tmem_slot; }
         if (warp == C::NW) {
-            if (lane == 0) { if (dead) ws::drain<C>(a.msg, L.n_msg, m); else ws::issue<C>(a.msg, L.n_msg, m, tmem); }
+            if (lane == 0) {
+                if (C::CL == 2 && m.rank != 0) ws::relay<C>(a.msg, L.n_msg, m);
+                else ws::issue<C>(a.msg, L.n_msg, m, tmem);
+            } else if (lane == 1 && C::CL == 2 && m.rank != 0 && !dead) {
+                ws::forward_ready<C>(L.n_msg, m);
+            }
         } else {
             if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m, dead);
         }
@@ -925,7 +988,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         }
         if (ASYNC) tmem = ws::simt_join<C>(m);
         cp_async_wait<0>();
-        ws::publish(m.feats_ready);
+        ws::publish_mma<C>(m, m.feats_ready);
         TC_T(e2);
         for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R, 0);
         TC_T(e3);
@@ -1186,7 +1249,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) { if (dead) ws::drain<C>(a.upd, a.n_upd, m); else ws::issue<C>(a.upd, a.n_upd, m, tmem); }
+        if (lane == 0) ws::issue<C>(a.upd, a.n_upd, m, tmem);
     } else if (warp == C::NW + 1) {
         if (lane == 0) ws::produce<C>(a.upd, a.n_upd, m, dead);
     } else if (!dead) {
@@ -1333,7 +1396,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                     for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] *= ivn;
             if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
-        ws::publish(m.feats_ready);
+        ws::publish_mma<C>(m, m.feats_ready);
         TC_T(n3t);
         // ---- phase 2: update GVPs on the tensor cores
         for (int i = 0; i < a.n_upd; ++i) ws::gvp_simt<C>(a.upd[i], i, m, tmem, v, Ln, n, 16);
@@ -1409,7 +1472,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) { if (dead) ws::drain<C>(a.g, a.n_gvps, m); else ws::issue<C>(a.g, a.n_gvps, m, tmem); }
+        if (lane == 0) ws::issue<C>(a.g, a.n_gvps, m, tmem);
     } else if (warp == C::NW + 1) {
         if (lane == 0) ws::produce<C>(a.g, a.n_gvps, m, dead);
     } else if (!dead) {
@@ -1429,7 +1492,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
         const bool vecw = warp < C::NWV;
         if (vecw) ws::vf_load(v, a.v + (size_t)(n0 + min(Ln.row, n - 1)) * (3 * Vd), Vd, Ln.t);
         cp_async_wait<0>();
-        ws::publish(m.feats_ready);
+        ws::publish_mma<C>(m, m.feats_ready);
         for (int i = 0; i < a.n_gvps; ++i) ws::gvp_simt<C>(a.g[i], i, m, tmem, v, Ln, n, 32);
         // to_scalar_output + vectors.squeeze(1)  (dynamics_gvp.py:42-43)
         for (int idx = tid; idx < n * a.F; idx += C::NT_SIMT) {
