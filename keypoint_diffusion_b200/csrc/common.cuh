@@ -247,6 +247,7 @@ enum ProfId { PROF_EGNN_EDGE = 1, PROF_GVP_EDGE = 2, PROF_GRAPH = 3, PROF_STEP =
               PROF_GVP_HEAD = 6, PROF_EGNN_NODE = 7, PROF_EGNN_PRE = 8, PROF_ENCDEC = 9 };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
+bool prof_enabled();      // a kernel id is being timed: callers keep to one stream and one launch per stage
 
 int build_graph_impl(const kpd_batch* batch, const float* x_lig, const float* x_kp, const kpd_graph_params* p,
                      kpd_csr* ll, kpd_csr* kl, kpd_csr* lk, int32_t* counts_ll, int32_t* counts_kl, void* workspace,

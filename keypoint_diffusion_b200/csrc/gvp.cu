@@ -252,8 +252,11 @@ __global__ void __launch_bounds__(NT, 1) gvp_edge_kernel(const GvpEdgeLaunch L) 
 
 struct GvpNodeArgs {
     int n, Sdim, Vdim, lds, pw, n_upd, n_et, kch, edge_tile;
-    float* s; float* v;                        // node features, updated in place
-    __nv_bfloat16* s_hi; __nv_bfloat16* s_lo;  // tensor-core modes: bf16 planes of the updated s (for the next gathers)
+    float* s; float* v;                        // node features (fp32 SIMT kernel: updated in place)
+    __nv_bfloat16* s_hi; __nv_bfloat16* s_lo;  // tensor-core modes: bf16 planes of s (what the edge kernels gather)
+    // tensor-core modes: the updated features go to a SECOND buffer set (== the inputs when the caller runs the layers
+    // serially), so that edge kernels still reading the old features may overlap this kernel (kpd_gvp_forward)
+    float* s_out; float* v_out; __nv_bfloat16* s_hi_out; __nv_bfloat16* s_lo_out;
     const int* rowptr[2]; const float* sm[2]; const float* vm[2]; const float* part[2];
     int norm_mode; float norm_const;           // 0 const, 1 per-etype mean, 2 mean in-degree + 1
     const int* node_batch; const int* ptr;
@@ -407,11 +410,20 @@ struct kpd_gvp_model {
     int mode;          // 0 = fp32 SIMT, 1 = bf16 tcgen05, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
     bool tc_ready, tc2_ready;
     std::vector<GvpW*> all_gvps;   // enumeration order of kpd_gvp_attach_tc
+    // tensor-core modes: the layers run as a dependency graph over one stream per edge type (see kpd_gvp_forward);
+    // created on first use
+    mutable cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // ll, lk, kk edges; lig, kp nodes
+    mutable cudaEvent_t ev_edge[4] = {nullptr, nullptr, nullptr, nullptr}, ev_node[2] = {nullptr, nullptr};
+    mutable bool dag_ready = false;
+    bool serial = false;          // KPD_GVP_SERIAL=1: one stream, one edge launch and one node launch per conv
 };
 
+// node features and per-edge-type aggregates exist twice (conv parity): conv l reads set l % 2 and writes set
+// (l + 1) % 2, so that the kernels of neighbouring convs may overlap (kpd_gvp_forward); the fp32 SIMT mode and the
+// serial tensor-core path only use set 0
 struct GvpWs {
-    float *s[2], *v[2], *sm[4], *vm[4], *part[4], *tin, *tenc;
-    __nv_bfloat16 *s_hi[2], *s_lo[2];
+    float *s[2][2], *v[2][2], *sm[2][4], *vm[2][4], *part[2][4], *tin, *tenc;
+    __nv_bfloat16 *s_hi[2][2], *s_lo[2][2];
 };
 
 static int gvp_ntiles(int cap) { return cdiv(cap > 0 ? cap : 1, TE) + 1; }
@@ -421,23 +433,23 @@ static GvpWs gvp_carve(const kpd_gvp_model* m, const kpd_batch* b, const int cap
     Carver c(ws);
     const int N[2] = {b->n_lig, b->n_kp};
     const int maxN = N[0] > N[1] ? N[0] : N[1];
-    for (int nt = 0; nt < 2; ++nt) {
-        w.s[nt] = c.take<float>((int64_t)N[nt] * m->S);
-        w.v[nt] = c.take<float>((int64_t)N[nt] * m->V * 3);
-    }
     const int dstN[4] = {N[0], N[0], N[1], N[1]};
-    for (int e = 0; e < 4; ++e) {
-        w.sm[e] = c.take<float>((int64_t)dstN[e] * m->S);
-        w.vm[e] = c.take<float>((int64_t)dstN[e] * m->V * 3);
-        w.part[e] = c.take<float>((int64_t)gvp_ntiles(caps[e]) * 2 * m->pw);
+    for (int p = 0; p < 2; ++p) {
+        for (int nt = 0; nt < 2; ++nt) {
+            w.s[p][nt] = c.take<float>((int64_t)N[nt] * m->S);
+            w.v[p][nt] = c.take<float>((int64_t)N[nt] * m->V * 3);
+            w.s_hi[p][nt] = c.take<__nv_bfloat16>((int64_t)N[nt] * m->S);
+            w.s_lo[p][nt] = c.take<__nv_bfloat16>((int64_t)N[nt] * m->S);
+        }
+        for (int e = 0; e < 4; ++e) {
+            w.sm[p][e] = c.take<float>((int64_t)dstN[e] * m->S);
+            w.vm[p][e] = c.take<float>((int64_t)dstN[e] * m->V * 3);
+            w.part[p][e] = c.take<float>((int64_t)gvp_ntiles(caps[e]) * 2 * m->pw);
+        }
     }
     const int win = (m->F > m->C ? m->F : m->C) + 1;
     w.tin = c.take<float>((int64_t)maxN * win);
     w.tenc = c.take<float>((int64_t)maxN * m->S);
-    for (int nt = 0; nt < 2; ++nt) {
-        w.s_hi[nt] = c.take<__nv_bfloat16>((int64_t)N[nt] * m->S);
-        w.s_lo[nt] = c.take<__nv_bfloat16>((int64_t)N[nt] * m->S);
-    }
     if (bytes) *bytes = c.bytes();
     return w;
 }
@@ -453,6 +465,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
     KPD_REQUIRE(cfg->rbf_dim >= 2 && cfg->rbf_dim <= 32, "kpd_gvp_create: rbf_dim %d unsupported", cfg->rbf_dim);
     auto* m = new kpd_gvp_model();
     m->cfg = *cfg;
+    { const char* e = getenv("KPD_GVP_SERIAL"); m->serial = e && e[0] == '1'; }
     m->S = cfg->n_hidden_scalars; m->Sp = m->S; m->V = cfg->vector_size;
     m->F = cfg->n_lig_scalars; m->Fp = (m->F + 3) & ~3; m->C = cfg->n_kp_scalars;
     {   // widest row any GVP of this model reads or writes: message GVP 0 reads S+rbf+V+1 columns,
@@ -536,7 +549,30 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
     return 0;
 }
 
-extern "C" void kpd_gvp_destroy(kpd_gvp_model* m) { delete m; }
+// streams and events of the dependency-graph path of kpd_gvp_forward
+static int gvp_dag_init(const kpd_gvp_model* m) {
+    if (m->dag_ready) return 0;
+    // the node kernels are the critical path (every edge launch of the next conv waits for one of them): their
+    // streams get the highest priority so that their few CTAs are dispatched ahead of the queued edge tiles
+    int pr_lo = 0, pr_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+    for (int i = 0; i < 5; ++i)
+        KPD_REQUIRE(cudaStreamCreateWithPriority(&m->aux[i], cudaStreamNonBlocking, i >= 3 ? pr_hi : pr_lo) == cudaSuccess, "kpd_gvp: stream creation failed");
+    for (int i = 0; i < 4; ++i) KPD_REQUIRE(cudaEventCreateWithFlags(&m->ev_edge[i], cudaEventDisableTiming) == cudaSuccess, "kpd_gvp: event creation failed");
+    for (int i = 0; i < 2; ++i) KPD_REQUIRE(cudaEventCreateWithFlags(&m->ev_node[i], cudaEventDisableTiming) == cudaSuccess, "kpd_gvp: event creation failed");
+    m->dag_ready = true;
+    return 0;
+}
+
+extern "C" void kpd_gvp_destroy(kpd_gvp_model* m) {
+    if (!m) return;
+    if (m->dag_ready) {
+        for (auto& s : m->aux) if (s) cudaStreamDestroy(s);
+        for (auto& e : m->ev_edge) cudaEventDestroy(e);
+        for (auto& e : m->ev_node) cudaEventDestroy(e);
+    }
+    delete m;
+}
 
 // bf16 tensor-core mode: tc_blob holds, for every GVP in creation order (per conv: message GVPs per edge
 // type, update GVPs per node type; then the noise head), the packed to_feats_out weight and the packed
@@ -568,7 +604,7 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws2);
         m->tc2_ready = true;
-        return 0;
+        return gvp_dag_init(m);
     }
     {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1);
@@ -577,7 +613,7 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws1);
     }
     m->tc_ready = true;
-    return 0;
+    return gvp_dag_init(m);
 }
 
 // event trace of one edge-kernel CTA (only with -DKPD_WS_TRACE): out = [n][3] (tag, warp, clock); returns n via *count
@@ -650,7 +686,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     const int N[2] = {b->n_lig, b->n_kp};
     const int S = m->S, V = m->V;
 
-    // ---- encoders: time concatenated first, Linear + SiLU + LayerNorm (dynamics_gvp.py:161-169)
+    // ---- encoders: time concatenated first, Linear + SiLU + LayerNorm (dynamics_gvp.py:161-169) -> buffer set 0
     if (m->mode != 0) {       // tensor-core modes: everything up to the first conv in one launch
         GvpEncArgs ea;
         memset(&ea, 0, sizeof(ea));
@@ -659,7 +695,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         for (int nt = 0; nt < 2; ++nt) {
             const float* const* enc = nt == 0 ? m->lig_enc : m->kp_enc;
             ea.WT[nt] = enc[0]; ea.bias[nt] = enc[1]; ea.lnw[nt] = enc[2]; ea.lnb[nt] = enc[3];
-            ea.s[nt] = w.s[nt]; ea.s_hi[nt] = w.s_hi[nt]; ea.s_lo[nt] = w.s_lo[nt]; ea.v[nt] = w.v[nt];
+            ea.s[nt] = w.s[0][nt]; ea.s_hi[nt] = w.s_hi[0][nt]; ea.s_lo[nt] = w.s_lo[0][nt]; ea.v[nt] = w.v[0][nt];
         }
         ea.batch[0] = b->lig_batch; ea.batch[1] = b->kp_batch;
         ea.v_kp = v_kp; ea.t_ptr = t_ptr; ea.t_per_complex = t_per_complex; ea.S = S; ea.Sp = m->Sp; ea.V = V;
@@ -671,49 +707,125 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     } else {
     KPD_TRY(launch_concat_time(h_lig, m->F, w.tin, m->F + 1, N[0], t_ptr, b->lig_batch, t_per_complex, st));
     KPD_TRY(launch_linear(w.tin, m->F + 1, m->lig_enc[0], m->Sp, m->lig_enc[1], nullptr, 0, w.tenc, S, N[0], m->F + 1, S, 1, st));
-    KPD_TRY(launch_layernorm(w.tenc, S, w.s[0], S, N[0], S, m->lig_enc[2], m->lig_enc[3], st));
+    KPD_TRY(launch_layernorm(w.tenc, S, w.s[0][0], S, N[0], S, m->lig_enc[2], m->lig_enc[3], st));
     KPD_TRY(launch_concat_time(h_kp, m->C, w.tin, m->C + 1, N[1], t_ptr, b->kp_batch, t_per_complex, st));
     KPD_TRY(launch_linear(w.tin, m->C + 1, m->kp_enc[0], m->Sp, m->kp_enc[1], nullptr, 0, w.tenc, S, N[1], m->C + 1, S, 1, st));
-    KPD_TRY(launch_layernorm(w.tenc, S, w.s[1], S, N[1], S, m->kp_enc[2], m->kp_enc[3], st));
+    KPD_TRY(launch_layernorm(w.tenc, S, w.s[0][1], S, N[1], S, m->kp_enc[2], m->kp_enc[3], st));
     // ligand vectors start at zero (:179-184); keypoint vectors come from the receptor encoder
-    cudaError_t ce = cudaMemsetAsync(w.v[0], 0, sizeof(float) * (size_t)N[0] * V * 3, st);
+    cudaError_t ce = cudaMemsetAsync(w.v[0][0], 0, sizeof(float) * (size_t)N[0] * V * 3, st);
     KPD_REQUIRE(ce == cudaSuccess, "kpd_gvp_forward: memset failed: %s", cudaGetErrorString(ce));
-    KPD_TRY(launch_copy_rows(v_kp, V * 3, w.v[1], V * 3, N[1], V * 3, st));
+    KPD_TRY(launch_copy_rows(v_kp, V * 3, w.v[0][1], V * 3, N[1], V * 3, st));
     }
     const int src_nt[4] = {0, 1, 0, 1}, dst_nt[4] = {0, 0, 1, 1};
     const float* X[2] = {x_lig, x_kp};
     const int norm_mode = m->cfg.norm_mode;
+    const int edge_rows = m->mode == 1 ? WsBf16::R : m->mode == 2 ? WsSplit::R : TE;
 
+    // Tensor-core modes run the convs as a DEPENDENCY GRAPH instead of a chain of launches: one edge launch per edge
+    // type, one node launch per node type, each waiting only for what it reads --
+    //     edge(l, e)  <- node(l-1, src type of e)                 (messages read source features only, gvp.py:472-497)
+    //     node(l, nt) <- edge(l, e) for the edge types into nt
+    // -- on one stream per edge type (kl: the caller's; ll, lk, kk: three auxiliary streams joined by events, which
+    // stream capture turns into graph edges).  Node features and aggregates are double-buffered by conv parity, so a
+    // node kernel never overwrites what a still-running edge kernel of the same conv reads.  The point: a conv's
+    // 650 edge tiles are 4.4 waves of one CTA per SM and its node tiles a fifth of a wave; as separate launches their
+    // tails leave SMs idle, as a graph the tail of one kernel is filled with the CTAs of the next ready one.
+    // The CUDA-event profiler (bench.py's roofline leg) and KPD_GVP_SERIAL=1 use the serial path below.
+    const bool dag = m->mode != 0 && !m->serial && !prof_enabled() && !m->edge_pair;
+    if (dag) KPD_TRY(gvp_dag_init(m));       // normally done by kpd_gvp_attach_tc, outside any stream capture
+    // stream of edge type e (ll, kl, lk, kk) and of node type nt
+    cudaStream_t es[4] = {st, st, st, st}, ns[2] = {st, st};
+    if (dag) { es[0] = m->aux[0]; es[2] = m->aux[1]; es[3] = m->aux[2]; ns[0] = m->aux[3]; ns[1] = m->aux[4]; }
+#define KPD_CU(x) do { cudaError_t e_ = (x); KPD_REQUIRE(e_ == cudaSuccess, "kpd_gvp_forward: %s", cudaGetErrorString(e_)); } while (0)
+    if (dag) {      // the encoder output is what every first-conv edge launch waits for
+        KPD_CU(cudaEventRecord(m->ev_node[0], st));
+        KPD_CU(cudaEventRecord(m->ev_node[1], st));
+    }
+    bool used[4] = {false, false, false, false}, nused[2] = {false, false};     // auxiliary work to join at the end
+
+    auto fill_edge = [&](GvpEdgeLaunch& L, int slot, int e, const GvpLayerW& W, int cur) {
+        GvpEtypeArgs& a = L.e[slot];
+        a.rowptr = G[e]->rowptr; a.src = G[e]->src; a.dst = G[e]->dst; a.n_dst = G[e]->n_dst; a.cap = caps[e] > 0 ? caps[e] : 1;
+        a.s_src = w.s[cur][src_nt[e]]; a.v_src = w.v[cur][src_nt[e]];
+        a.s_hi = w.s_hi[cur][src_nt[e]]; a.s_lo = w.s_lo[cur][src_nt[e]];
+        a.xs = X[src_nt[e]]; a.xd = X[dst_nt[e]];
+        for (int k = 0; k < L.n_msg; ++k) a.msg[k] = W.msg[e][k];
+        a.sm = w.sm[cur][e]; a.vm = w.vm[cur][e]; a.part = w.part[cur][e];
+    };
+    auto launch_edge_ws = [&](const GvpEdgeLaunch& L, int tiles, int n_et, cudaStream_t s_) -> int {
+        if (m->mode == 1) launch_clustered(gvp_edge_ws_kernel<WsBf16>, dim3(tiles, n_et), WsBf16::NT, m->smem_ws1, s_, WsBf16::CL, L);
+        else if (m->edge_pair) launch_clustered(gvp_edge_ws_kernel<WsSplitPair>, dim3(tiles, n_et), WsSplitPair::NT, m->smem_ws2, s_, 2, L);
+        else launch_clustered(gvp_edge_ws_kernel<WsSplit>, dim3(tiles, n_et), WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, L);
+        return check_launch("gvp_edge_ws_kernel");
+    };
+    auto fill_node = [&](GvpNodeLaunch& NL, int slot, int nt, const GvpLayerW& W, int cur, int nxt) {
+        GvpNodeArgs& a = NL.nt[slot];
+        a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
+        a.n_upd = m->cfg.n_update_gvps; a.n_et = 2; a.kch = m->kch; a.edge_tile = edge_rows;
+        a.s = w.s[cur][nt]; a.v = w.v[cur][nt]; a.s_hi = w.s_hi[cur][nt]; a.s_lo = w.s_lo[cur][nt];
+        a.s_out = w.s[nxt][nt]; a.v_out = w.v[nxt][nt]; a.s_hi_out = w.s_hi[nxt][nt]; a.s_lo_out = w.s_lo[nxt][nt];
+        for (int k = 0; k < 2; ++k) {
+            const int e = nt * 2 + k;
+            a.rowptr[k] = G[e]->rowptr; a.sm[k] = w.sm[cur][e]; a.vm[k] = w.vm[cur][e]; a.part[k] = w.part[cur][e];
+        }
+        a.norm_mode = norm_mode; a.norm_const = m->cfg.message_norm;
+        a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
+        a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
+        for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
+        a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
+    };
+    auto launch_node_ws = [&](const GvpNodeLaunch& NL, int max_n, int n_dst, cudaStream_t s_) -> int {
+        if (m->mode == 1) launch_clustered(gvp_node_ws_kernel<WsBf16N>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsBf16N::NT, m->smem_ws1n, s_, WsBf16N::CL, NL);
+        else launch_clustered(gvp_node_ws_kernel<WsSplit>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, NL);
+        return check_launch("gvp_node_ws_kernel");
+    };
+
+    int fin = 0;        // buffer set holding the final ligand features
     for (int l = 0; l < m->cfg.n_convs; ++l) {
         const GvpLayerW& W = m->layers[l];
+        // serial paths update in place (set 0); the graph path ping-pongs
+        const int cur = dag ? (l & 1) : 0, nxt = dag ? ((l + 1) & 1) : 0;
         GvpEdgeLaunch L;
         memset(&L, 0, sizeof(L));
         L.Sdim = S; L.Vdim = V; L.n_msg = m->cfg.n_message_gvps; L.lds = m->lds; L.pw = m->pw;
         L.rbf_dim = m->cfg.rbf_dim;
         L.rbf_step = m->cfg.rbf_dmax / (float)(m->cfg.rbf_dim - 1);   // linspace(0, D_max, D_count)
         L.rbf_sigma = m->cfg.rbf_dmax / (float)m->cfg.rbf_dim;
-        int max_tiles = 1;
-        for (int e = 0; e < W.n_et; ++e) {
-            GvpEtypeArgs& a = L.e[e];
-            a.rowptr = G[e]->rowptr; a.src = G[e]->src; a.dst = G[e]->dst; a.n_dst = G[e]->n_dst; a.cap = caps[e] > 0 ? caps[e] : 1;
-            a.s_src = w.s[src_nt[e]]; a.v_src = w.v[src_nt[e]];
-            a.s_hi = w.s_hi[src_nt[e]]; a.s_lo = w.s_lo[src_nt[e]];
-            a.xs = X[src_nt[e]]; a.xd = X[dst_nt[e]];
-            for (int k = 0; k < L.n_msg; ++k) a.msg[k] = W.msg[e][k];
-            a.sm = w.sm[e]; a.vm = w.vm[e]; a.part = w.part[e];
-            const int t = cdiv(caps[e] > 0 ? caps[e] : 1, TE);
-            if (t > max_tiles) max_tiles = t;
-        }
         L.kch = m->kch;
-        const int edge_rows = m->mode == 1 ? WsBf16::R : m->mode == 2 ? WsSplit::R : TE;
+        if (dag) {
+            for (int e = 0; e < W.n_et; ++e) {
+                GvpEdgeLaunch Le = L;
+                fill_edge(Le, 0, e, W, cur);
+                KPD_CU(cudaStreamWaitEvent(es[e], m->ev_node[src_nt[e]], 0));
+                KPD_TRY(launch_edge_ws(Le, cdiv(caps[e] > 0 ? caps[e] : 1, edge_rows), 1, es[e]));
+                KPD_CU(cudaEventRecord(m->ev_edge[e], es[e]));
+                used[e] = true;
+            }
+            for (int nt = 0; nt < W.n_dst; ++nt) {
+                if (N[nt] <= 0) continue;
+                GvpNodeLaunch NL;
+                memset(&NL, 0, sizeof(NL));
+                fill_node(NL, 0, nt, W, cur, nxt);
+                for (int k = 0; k < 2; ++k) KPD_CU(cudaStreamWaitEvent(ns[nt], m->ev_edge[2 * nt + k], 0));
+                KPD_TRY(launch_node_ws(NL, N[nt], 1, ns[nt]));
+                KPD_CU(cudaEventRecord(m->ev_node[nt], ns[nt]));
+                nused[nt] = true;
+            }
+            // a node type this conv does not update (the last conv is lig-only) simply keeps its current set; nothing
+            // reads it afterwards (dynamics_gvp.py:71-72)
+            fin = nxt;
+            continue;
+        }
+        int max_tiles = 1, tiles_tc = 1;
+        for (int e = 0; e < W.n_et; ++e) {
+            fill_edge(L, e, e, W, cur);
+            const int c1 = caps[e] > 0 ? caps[e] : 1;
+            if (cdiv(c1, TE) > max_tiles) max_tiles = cdiv(c1, TE);
+            if (cdiv(c1, edge_rows) > tiles_tc) tiles_tc = cdiv(c1, edge_rows);
+        }
         prof_begin(PROF_GVP_EDGE, st);
         if (m->mode != 0) {
-            int tiles_tc = 1;
-            for (int e = 0; e < W.n_et; ++e) { const int t = cdiv(caps[e] > 0 ? caps[e] : 1, edge_rows); if (t > tiles_tc) tiles_tc = t; }
-            if (m->mode == 1) launch_clustered(gvp_edge_ws_kernel<WsBf16>, dim3(tiles_tc, W.n_et), WsBf16::NT, m->smem_ws1, st, WsBf16::CL, L);
-            else if (m->edge_pair) launch_clustered(gvp_edge_ws_kernel<WsSplitPair>, dim3(tiles_tc, W.n_et), WsSplitPair::NT, m->smem_ws2, st, 2, L);
-            else launch_clustered(gvp_edge_ws_kernel<WsSplit>, dim3(tiles_tc, W.n_et), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, L);
-            KPD_TRY(check_launch("gvp_edge_ws_kernel"));
+            KPD_TRY(launch_edge_ws(L, tiles_tc, W.n_et, st));
         } else {
             gvp_edge_kernel<<<dim3(max_tiles, W.n_et), NT, m->smem, st>>>(L);
             KPD_TRY(check_launch("gvp_edge_kernel"));
@@ -724,29 +836,13 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             memset(&NL, 0, sizeof(NL));
             int max_n = 0;
             for (int nt = 0; nt < W.n_dst; ++nt) {
-                GvpNodeArgs& a = NL.nt[nt];
-                a.n = N[nt]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.pw = m->pw;
-                a.n_upd = m->cfg.n_update_gvps; a.n_et = 2; a.kch = m->kch; a.edge_tile = edge_rows;
-                a.s = w.s[nt]; a.v = w.v[nt]; a.s_hi = w.s_hi[nt]; a.s_lo = w.s_lo[nt];
-                for (int k = 0; k < 2; ++k) {
-                    const int e = nt * 2 + k;
-                    a.rowptr[k] = G[e]->rowptr; a.sm[k] = w.sm[e]; a.vm[k] = w.vm[e]; a.part[k] = w.part[e];
-                }
-                a.norm_mode = norm_mode; a.norm_const = m->cfg.message_norm;
-                a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
-                a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
-                for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
-                a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
-                if (a.n > max_n) max_n = a.n;
+                fill_node(NL, nt, nt, W, cur, nxt);
+                if (N[nt] > max_n) max_n = N[nt];
             }
             if (max_n > 0) {
                 prof_begin(PROF_GVP_NODE, st);
-                if (m->mode == 1) {
-                    launch_clustered(gvp_node_ws_kernel<WsBf16N>, dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsBf16N::NT, m->smem_ws1n, st, WsBf16N::CL, NL);
-                    KPD_TRY(check_launch("gvp_node_ws_kernel"));
-                } else if (m->mode == 2) {
-                    launch_clustered(gvp_node_ws_kernel<WsSplit>, dim3(cdiv(max_n, NODE_ROWS), W.n_dst), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, NL);
-                    KPD_TRY(check_launch("gvp_node_ws_kernel"));
+                if (m->mode != 0) {
+                    KPD_TRY(launch_node_ws(NL, max_n, W.n_dst, st));
                 } else {
                     gvp_node_kernel<<<dim3(cdiv(max_n, TN), W.n_dst), NT, m->smem_node, st>>>(NL);
                     KPD_TRY(check_launch("gvp_node_kernel"));
@@ -755,12 +851,18 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             }
         }
     }
+    if (dag) {
+        // join: everything launched on the auxiliary streams is ordered before the head / the end of this call
+        for (int e = 0; e < 4; ++e) if (used[e] && es[e] != st) KPD_CU(cudaStreamWaitEvent(st, m->ev_edge[e], 0));
+        for (int nt = 0; nt < 2; ++nt) if (nused[nt]) KPD_CU(cudaStreamWaitEvent(st, m->ev_node[nt], 0));
+    }
+#undef KPD_CU
     {
         GvpHeadArgs a;
         memset(&a, 0, sizeof(a));
         a.n = N[0]; a.Sdim = S; a.Vdim = V; a.lds = m->lds; a.n_gvps = m->cfg.n_noise_gvps;
         a.F = m->F; a.Fp = m->Fp; a.hid_out = 64;
-        a.s = w.s[0]; a.v = w.v[0]; a.s_hi = w.s_hi[0]; a.s_lo = w.s_lo[0];
+        a.s = w.s[fin][0]; a.v = w.v[fin][0]; a.s_hi = w.s_hi[fin][0]; a.s_lo = w.s_lo[fin][0];
         for (int k = 0; k < a.n_gvps; ++k) a.g[k] = m->head[k];
         a.WoT = m->WoT; a.bo = m->bo; a.eps_h = eps_h; a.eps_x = eps_x;
         if (a.n > 0) {

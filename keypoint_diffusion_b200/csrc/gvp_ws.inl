@@ -1334,7 +1334,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 ws::warp_layernorm8(x[j], act, Sd, lw, lb);
                 if (act) {
                     if (r < n) {
-                        float* sp = a.s + (size_t)(n0 + r) * Sd + 8 * lane;
+                        float* sp = a.s_out + (size_t)(n0 + r) * Sd + 8 * lane;
                         *reinterpret_cast<float4*>(sp) = make_float4(x[j][0], x[j][1], x[j][2], x[j][3]);
                         *reinterpret_cast<float4*>(sp + 4) = make_float4(x[j][4], x[j][5], x[j][6], x[j][7]);
                     }
@@ -1394,7 +1394,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
                     for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] *= ivn;
-            if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
+            if (Ln.row < n) ws::vf_store(v, a.v_out + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
         ws::publish_mma<C>(m, m.feats_ready);
         TC_T(n3t);
@@ -1412,8 +1412,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 const int r = warp + C::NW * j;
                 const int nd = n0 + min(r, n - 1);
                 const int col = act ? 8 * lane : 0;
-                sa[j][0] = *reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col);
-                sa[j][1] = *reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col + 4);
+                sa[j][0] = *reinterpret_cast<const float4*>(a.s_out + (size_t)nd * Sd + col);
+                sa[j][1] = *reinterpret_cast<const float4*>(a.s_out + (size_t)nd * Sd + col + 4);
             }
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
@@ -1428,16 +1428,16 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 ws::warp_layernorm8(x[j], act, Sd, lw, lb);
                 if (act && r < n) {
                     const size_t o = (size_t)(n0 + r) * Sd + 8 * lane;
-                    *reinterpret_cast<float4*>(a.s + o) = make_float4(x[j][0], x[j][1], x[j][2], x[j][3]);
-                    *reinterpret_cast<float4*>(a.s + o + 4) = make_float4(x[j][4], x[j][5], x[j][6], x[j][7]);
-                    ws::store_planes8(a.s_hi, a.s_lo, o, x[j]);
+                    *reinterpret_cast<float4*>(a.s_out + o) = make_float4(x[j][0], x[j][1], x[j][2], x[j][3]);
+                    *reinterpret_cast<float4*>(a.s_out + o + 4) = make_float4(x[j][4], x[j][5], x[j][6], x[j][7]);
+                    ws::store_planes8(a.s_hi_out, a.s_lo_out, o, x[j]);
                 }
             }
         }
         if (vecw) {
             const int nd = n0 + min(Ln.row, n - 1);
             ws::VF res;
-            ws::vf_load(res, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
+            ws::vf_load(res, a.v_out + (size_t)nd * (3 * Vd), Vd, Ln.t);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -1451,7 +1451,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 for (int ss = 0; ss < 2; ++ss)
 #pragma unroll
                     for (int ee = 0; ee < 2; ++ee) v.x[c][ss][ee] *= ivn;
-            if (Ln.row < n) ws::vf_store(v, a.v + (size_t)nd * (3 * Vd), Vd, Ln.t);
+            if (Ln.row < n) ws::vf_store(v, a.v_out + (size_t)nd * (3 * Vd), Vd, Ln.t);
         }
         TC_T(n5t);
         WS_ACC(24, n0t, n1t); WS_ACC(25, n1t, n2t); WS_ACC(26, n2t, n3t); WS_ACC(27, n3t, n4t); WS_ACC(28, n4t, n5t); WS_ACC(29, 0, 1);

@@ -46,6 +46,8 @@ static bool prof_active(int id, cudaStream_t st) {
     return true;
 }
 
+bool prof_enabled() { return g_prof_id > 0; }
+
 void prof_begin(int id, cudaStream_t st) {
     if (!prof_active(id, st)) return;
     cudaEventRecord(g_prof[g_prof_used].a, st);

@@ -144,12 +144,12 @@ def test_denoiser_matches_golden(name):
         assert eh < TOL and ex < TOL, (name, t_str, eh, ex)
 
 
-def _full_size_case(arch, cfgs):
+def _full_size_case(arch, cfgs, n_lig=None, n_pockets=3):
     """Shipped hyper-parameters (20-keypoint models), seeded weights, 6 complexes of mixed size."""
     from oracle import params as P
     from keypoint_diffusion_b200 import synthetic
     cfg = cfgs[f"{arch}_20kp"]
-    n_lig = [20, 8, 35, 20, 13, 27]
+    n_lig = n_lig or [20, 8, 35, 20, 13, 27]
     if arch == "egnn":
         d = cfg["dynamics"]
         rec_nf = cfg["rec_encoder"]["out_n_node_feat"]
@@ -173,11 +173,11 @@ def _full_size_case(arch, cfgs):
                   n_message_gvps=d["n_message_gvps"], n_update_gvps=d["n_update_gvps"],
                   n_noise_gvps=d["n_noise_gvps"], graph_cutoffs=cfg["graph"]["graph_cutoffs"])
         vs = d["vector_size"]
-    pockets = [synthetic.keypoint_pocket(i, 20, rec_nf, vs, cfg["graph"]["graph_cutoffs"]["kk"]) for i in range(3)]
+    pockets = [synthetic.keypoint_pocket(i, 20, rec_nf, vs, cfg["graph"]["graph_cutoffs"]["kk"]) for i in range(n_pockets)]
     x_l, h_l = synthetic.ligand_noise_state(n_lig, 10, seed=5)
     kp_x, kp_h, kp_v, ks, kd, off = [], [], [], [], [], 0
     for i in range(len(n_lig)):
-        pk = pockets[i % 3]
+        pk = pockets[i % n_pockets]
         kp_x.append(pk.kp_x); kp_h.append(pk.kp_h)
         if vs:
             kp_v.append(pk.kp_v)

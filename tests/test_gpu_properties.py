@@ -95,7 +95,7 @@ def _baseline_case(arch, n_ligands, dev):
     from test_gpu_parity import _full_size_case, build_model, device_inputs
     from keypoint_diffusion_b200 import ops
     cfgs = yaml.safe_load(open(GOLDEN / "shipped_configs.yml"))
-    sd, kw, rec_nf, inputs = _full_size_case(arch, cfgs, n_lig=[20] * n_ligands)
+    sd, kw, rec_nf, inputs = _full_size_case(arch, cfgs, n_lig=[20] * n_ligands, n_pockets=1)
     model = build_model(arch, sd, kw, 10, rec_nf, dev)
     gp = ops.GraphParams.from_module(kw["ll_k"], kw["kl_k"], kw["graph_cutoffs"])
     return model, gp, inputs, device_inputs
