@@ -279,6 +279,9 @@ int kpd_sampler_run(kpd_sampler* s, float* x_kp, const float* h_kp, const float*
 int kpd_sampler_edge_stats(kpd_sampler* s, double* out);
 /* kernels launched per reverse step by the captured sequence (for bench.py's gpu_launches) */
 int32_t kpd_sampler_launches_per_step(const kpd_sampler* s);
+/* Offset added to the ligand-atom index of the noise counter (seed, step, atom, channel): lets a caller sample one batch
+ * as several sub-batches (own samplers, own streams) and draw exactly the noise of the undivided batch. */
+int kpd_sampler_set_atom_offset(kpd_sampler* s, int32_t first_atom);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics (tools/tc_phase_times.py, tools/eg_phase_times.py, tools/ws_trace.py): in-kernel phase timers of the
@@ -289,6 +292,9 @@ int32_t kpd_sampler_launches_per_step(const kpd_sampler* s);
 int kpd_debug_ws_times(unsigned long long* out64);
 int kpd_debug_eg_times(unsigned long long* out16);
 int kpd_debug_ws_trace(unsigned long long* out, int32_t cap, int32_t* count);
+/* Launch timeline of the GVP convs (library built with -DKPD_TIMELINE, else returns 0 slots): out = [256][3] =
+ * (first CTA start ns, last CTA end ns, working CTAs) per slot 8 * conv + edge type (or 4 + node type). */
+int kpd_debug_timeline(unsigned long long* out, int32_t reset);
 
 #ifdef __cplusplus
 }

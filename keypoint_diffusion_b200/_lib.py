@@ -8,7 +8,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libkpdiff_b200.so"
+LIB_PATH = Path(os.environ["KPD_LIB"]) if os.environ.get("KPD_LIB") else _HERE / "libkpdiff_b200.so"   # KPD_LIB: an instrumented build (tools/)
 
 TILE_EDGES = 64
 
@@ -76,6 +76,7 @@ def _load():
         "kpd_debug_ws_times": (I, [P]),
         "kpd_debug_eg_times": (I, [P]),
         "kpd_debug_ws_trace": (I, [P, I, P]),
+        "kpd_debug_timeline": (I, [P, I]),
         "kpd_egnn_dims": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "kpd_egnn_workspace_bytes": (L, [P, C.POINTER(KpdBatch), I, I, I]),
         "kpd_egnn_forward": (I, [P, C.POINTER(KpdBatch), P, P, P, P, P, P, I, C.POINTER(KpdCsr),
@@ -99,6 +100,7 @@ def _load():
         "kpd_sampler_destroy": (None, [P]),
         "kpd_sampler_run": (I, [P, P, P, P, P, P, P, P, U64, I, P]),
         "kpd_sampler_launches_per_step": (I, [P]),
+        "kpd_sampler_set_atom_offset": (I, [P, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

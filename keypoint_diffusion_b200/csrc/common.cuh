@@ -229,7 +229,8 @@ struct RunParams {        // lives in device memory so that a captured graph can
     const float* noise;   // NULL or [(T+1)][n_lig][3+F], slot 0 = initial draw
     uint64_t seed;
     int T;
-    int pad;
+    int atom_offset;      // added to the atom index of the Philox counter: a batch sampled as several sub-batches draws
+                          // the same noise as when it is sampled whole (kpd_sampler_set_atom_offset)
 };
 int launch_ddpm_step(const kpd_batch* b, float* x_lig, float* h_lig, float* x_kp, const float* eps_x,
                      const float* eps_h, int F, const float* coef, const int* step_ptr, const float* noise_x,

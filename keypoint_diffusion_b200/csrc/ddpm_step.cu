@@ -51,8 +51,10 @@ ddpm_step_kernel(kpd_batch b, float* __restrict__ x_lig, float* __restrict__ h_l
     const int k0 = b.kp_ptr[c], nk = b.kp_ptr[c + 1] - k0;
     const int s = *step_ptr;
     const float a = coef[4 * s], vt = coef[4 * s + 1], sg = coef[4 * s + 2];
+    int aoff = 0;
     if (rp) {
         seed = rp->seed;
+        aoff = rp->atom_offset;
         if (rp->noise) {
             const float* slot = rp->noise + (size_t)(1 + (rp->T - 1 - s)) * b.n_lig * (3 + F);
             noise_x = slot;
@@ -65,13 +67,13 @@ ddpm_step_kernel(kpd_batch b, float* __restrict__ x_lig, float* __restrict__ h_l
     // mu = z/alpha_t|s - var_terms*eps ; z_s = mu + sigma*noise   (ligand_diffuser.py:522-533)
     for (int i = threadIdx.x; i < nl * 3; i += blockDim.x) {
         const int idx = 3 * l0 + i;
-        const float nz = noise_x ? noise_x[idx] : philox_normal(seed, s, l0 + i / 3, i % 3);
+        const float nz = noise_x ? noise_x[idx] : philox_normal(seed, s, aoff + l0 + i / 3, i % 3);
         const float mu = __fsub_rn(__fdiv_rn(x_lig[idx], a), __fmul_rn(vt, eps_x[idx]));
         x_lig[idx] = __fadd_rn(mu, __fmul_rn(sg, nz));
     }
     for (int i = threadIdx.x; i < nl * F; i += blockDim.x) {
         const int idx = F * l0 + i;
-        const float nz = noise_h ? noise_h[idx] : philox_normal(seed, s, l0 + i / F, 3 + i % F);
+        const float nz = noise_h ? noise_h[idx] : philox_normal(seed, s, aoff + l0 + i / F, 3 + i % F);
         const float mu = __fsub_rn(__fdiv_rn(h_lig[idx], a), __fmul_rn(vt, eps_h[idx]));
         h_lig[idx] = __fadd_rn(mu, __fmul_rn(sg, nz));
     }
@@ -143,11 +145,12 @@ __global__ void randn_init_kernel(float* x_lig, float* h_lig, int n_lig, int F, 
     const int W = 3 + F;
     if (i >= n_lig * W) return;
     const float* noise = nullptr;
-    if (rp) { seed = rp->seed; noise = rp->noise; }
+    int aoff = 0;
+    if (rp) { seed = rp->seed; noise = rp->noise; aoff = rp->atom_offset; }
     const int atom = i / W, ch = i % W;
     float v;
     if (noise) v = ch < 3 ? noise[3 * atom + ch] : noise[(size_t)3 * n_lig + (size_t)F * atom + (ch - 3)];
-    else v = philox_normal(seed, -1, atom, ch);
+    else v = philox_normal(seed, -1, aoff + atom, ch);
     if (ch < 3) x_lig[3 * atom + ch] = v;
     else h_lig[F * atom + (ch - 3)] = v;
 }

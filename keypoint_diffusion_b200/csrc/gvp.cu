@@ -188,8 +188,21 @@ struct GvpEtypeArgs {
     float* sm; float* vm; float* part;
 };
 
+// launch timeline (only with -DKPD_TIMELINE): per slot the start of CTA 0 of the LAST launch, the latest CTA end
+// (globaltimer, ns) and the number of working CTAs summed over launches; slot = 8 * conv + edge type (or 4 + node type); see kpd_debug_timeline
+#ifdef KPD_TIMELINE
+__device__ unsigned long long g_tl[3 * 256];
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TL_BEGIN(slot) do { if (threadIdx.x == 0 && (slot) >= 0) { if (blockIdx.x == 0) g_tl[3 * (slot)] = tl_now(); atomicAdd(&g_tl[3 * (slot) + 2], 1ull); } } while (0)
+#define TL_END(slot) do { if (threadIdx.x == 0 && (slot) >= 0) atomicMax(&g_tl[3 * (slot) + 1], tl_now()); } while (0)
+#else
+#define TL_BEGIN(slot) do { } while (0)
+#define TL_END(slot) do { } while (0)
+#endif
+
 struct GvpEdgeLaunch {
     GvpEtypeArgs e[4];
+    int tl_slot;
     int Sdim, Vdim, n_msg, lds, pw, rbf_dim, kch;
     float rbf_step, rbf_sigma;
 };
@@ -264,7 +277,7 @@ struct GvpNodeArgs {
     const float *mln_w, *mln_b, *uln_w, *uln_b;
 };
 
-struct GvpNodeLaunch { GvpNodeArgs nt[2]; };
+struct GvpNodeLaunch { GvpNodeArgs nt[2]; int tl_slot; };
 
 __global__ void __launch_bounds__(NT, 1) gvp_node_kernel(const GvpNodeLaunch L) {
     const GvpNodeArgs& a = L.nt[blockIdx.y];
@@ -372,21 +385,32 @@ using namespace kpd;
 
 // launch with thread-block clusters of `cl` CTAs along x (grid.x is rounded up to a multiple of cl)
 template <typename Arg>
-static void launch_clustered(void (*kernel)(Arg), dim3 grid, int threads, size_t smem, cudaStream_t st, int cl, const Arg& arg) {
+static void launch_clustered(void (*kernel)(Arg), dim3 grid, int threads, size_t smem, cudaStream_t st, int cl, const Arg& arg,
+                             bool high_priority = false) {
     grid.x = (grid.x + cl - 1) / cl * cl;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cl > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cl;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (high_priority) {        // explicit, so that a captured kernel node carries it whatever the stream's priority
+        int pr_lo = 0, pr_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+        attr[na].id = cudaLaunchAttributePriority;
+        attr[na].val.priority = pr_hi;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = cl > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     cudaLaunchKernelEx(&cfg, kernel, arg);
 }
 
@@ -635,6 +659,25 @@ extern "C" int kpd_debug_ws_trace(unsigned long long* out, int32_t cap, int32_t*
 #endif
 }
 
+// launch timeline of the GVP convs (only with -DKPD_TIMELINE): out = [256][3] (first CTA start ns, last CTA end ns,
+// working CTAs); reset != 0 clears it afterwards.  Returns the number of slots (0 when not compiled in).
+extern "C" int kpd_debug_timeline(unsigned long long* out, int32_t reset) {
+#ifdef KPD_TIMELINE
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out) e = cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 3 * 256);
+    if (e == cudaSuccess && reset) {
+        static unsigned long long z[3 * 256];
+        for (int i = 0; i < 256; ++i) { z[3 * i] = ~0ull; z[3 * i + 1] = 0; z[3 * i + 2] = 0; }
+        e = cudaMemcpyToSymbol(g_tl, z, sizeof(z));
+    }
+    KPD_REQUIRE(e == cudaSuccess, "kpd_debug_timeline: %s", cudaGetErrorString(e));
+    return 256;
+#else
+    (void)out; (void)reset;
+    return 0;
+#endif
+}
+
 // same for the warp-specialised kernels (gvp_ws.inl)
 extern "C" int kpd_debug_ws_times(unsigned long long* out64) {
     KPD_REQUIRE(out64, "kpd_debug_ws_times: null argument");
@@ -775,8 +818,8 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
     };
     auto launch_node_ws = [&](const GvpNodeLaunch& NL, int max_n, int n_dst, cudaStream_t s_) -> int {
-        if (m->mode == 1) launch_clustered(gvp_node_ws_kernel<WsBf16N>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsBf16N::NT, m->smem_ws1n, s_, WsBf16N::CL, NL);
-        else launch_clustered(gvp_node_ws_kernel<WsSplit>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, NL);
+        if (m->mode == 1) launch_clustered(gvp_node_ws_kernel<WsBf16N>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsBf16N::NT, m->smem_ws1n, s_, WsBf16N::CL, NL, dag);
+        else launch_clustered(gvp_node_ws_kernel<WsSplit>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, NL, dag);
         return check_launch("gvp_node_ws_kernel");
     };
 
@@ -795,6 +838,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         if (dag) {
             for (int e = 0; e < W.n_et; ++e) {
                 GvpEdgeLaunch Le = L;
+                Le.tl_slot = 8 * l + e;
                 fill_edge(Le, 0, e, W, cur);
                 KPD_CU(cudaStreamWaitEvent(es[e], m->ev_node[src_nt[e]], 0));
                 KPD_TRY(launch_edge_ws(Le, cdiv(caps[e] > 0 ? caps[e] : 1, edge_rows), 1, es[e]));
@@ -806,6 +850,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
                 GvpNodeLaunch NL;
                 memset(&NL, 0, sizeof(NL));
                 fill_node(NL, 0, nt, W, cur, nxt);
+                NL.tl_slot = 8 * l + 4 + nt;
                 for (int k = 0; k < 2; ++k) KPD_CU(cudaStreamWaitEvent(ns[nt], m->ev_edge[2 * nt + k], 0));
                 KPD_TRY(launch_node_ws(NL, N[nt], 1, ns[nt]));
                 KPD_CU(cudaEventRecord(m->ev_node[nt], ns[nt]));
@@ -817,6 +862,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             continue;
         }
         int max_tiles = 1, tiles_tc = 1;
+        L.tl_slot = 8 * l;
         for (int e = 0; e < W.n_et; ++e) {
             fill_edge(L, e, e, W, cur);
             const int c1 = caps[e] > 0 ? caps[e] : 1;
@@ -834,6 +880,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         {
             GvpNodeLaunch NL;
             memset(&NL, 0, sizeof(NL));
+            NL.tl_slot = 8 * l + 4;
             int max_n = 0;
             for (int nt = 0; nt < W.n_dst; ++nt) {
                 fill_node(NL, nt, nt, W, cur, nxt);

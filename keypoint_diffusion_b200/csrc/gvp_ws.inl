@@ -907,6 +907,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
     const bool dead = tile_begin >= E;                              // (CTA pairs) this CTA only lends its half of the weights
     const int n = min(C::R, E - tile_begin);
     extern __shared__ __align__(128) unsigned char smem_ws[];
+    TL_BEGIN(L.tl_slot);
     TC_T(e0);
     ws::Sm m = ws::carve<C>(smem_ws, L.kch);
     if (C::CL == 2) {
@@ -1050,6 +1051,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
     }
     if (ASYNC && warp < C::NW && dead) tmem = ws::simt_join<C>(m);     // (unreachable without clusters; keeps barrier 3 balanced)
     ws::teardown<C>(tmem);
+    TL_END(L.tl_slot);
 }
 
 // ------------------------------------------------------------------ node kernel
@@ -1243,6 +1245,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
     const int n = min(NODE_ROWS, a.n - n0);
     constexpr int RPW = NODE_ROWS / C::NW;     // rows per warp in the scalar phases (row = warp + NW * j)
     extern __shared__ __align__(128) unsigned char smem_ws[];
+    TL_BEGIN(L.tl_slot + (int)blockIdx.y);
     TC_T(n0t);
     ws::Sm m = ws::carve<C>(smem_ws, a.kch);
     const uint32_t tmem = ws::setup<C>(m, a.kch);
@@ -1457,6 +1460,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         WS_ACC(24, n0t, n1t); WS_ACC(25, n1t, n2t); WS_ACC(26, n2t, n3t); WS_ACC(27, n3t, n4t); WS_ACC(28, n4t, n5t); WS_ACC(29, 0, 1);
     }
     ws::teardown<C>(tmem);
+    TL_END(L.tl_slot + (int)blockIdx.y);
 }
 
 // NoisePredictionBlock (models/dynamics_gvp.py:38-44): noise GVPs + Linear(64 -> atom_nf); eps_x = vectors.squeeze(1)

@@ -35,6 +35,7 @@ struct kpd_sampler {
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     int launches_per_step;
+    int atom_offset;
 };
 
 static int64_t model_ws_bytes(const kpd_sampler_config* cfg, const void* model, const kpd_batch* b, int cap_ll,
@@ -166,6 +167,14 @@ extern "C" int kpd_sampler_edge_stats(kpd_sampler* s, double* out) {
 
 extern "C" int32_t kpd_sampler_launches_per_step(const kpd_sampler* s) { return s ? s->launches_per_step : 0; }
 
+// A batch may be sampled as several sub-batches on their own streams (their kernels fill each other's idle SMs); with
+// the sub-batch's first global ligand-atom index as offset the generated noise does not depend on the split.
+extern "C" int kpd_sampler_set_atom_offset(kpd_sampler* s, int32_t first_atom) {
+    KPD_REQUIRE(s && first_atom >= 0, "kpd_sampler_set_atom_offset: bad argument");
+    s->atom_offset = first_atom;
+    return 0;
+}
+
 static int capture(kpd_sampler* s) {
     cudaError_t e = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
     KPD_REQUIRE(e == cudaSuccess, "sampler: begin capture: %s", cudaGetErrorString(e));
@@ -174,7 +183,9 @@ static int capture(kpd_sampler* s) {
     e = cudaStreamEndCapture(s->stream, &s->graph);
     if (rc != 0) return rc;
     KPD_REQUIRE(e == cudaSuccess, "sampler: end capture: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&s->exec, s->graph, 0);
+    // per-node priorities: the denoisers mark their critical-path kernels (kpd_gvp_forward) and those must be dispatched
+    // ahead of already-queued CTAs of lower-priority kernels, whatever the priority of the launching stream
+    e = cudaGraphInstantiateWithFlags(&s->exec, s->graph, cudaGraphInstantiateFlagUseNodePriority);
     KPD_REQUIRE(e == cudaSuccess, "sampler: graph instantiate: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -197,7 +208,7 @@ extern "C" int kpd_sampler_run(kpd_sampler* s, float* x_kp, const float* h_kp, c
     if (s->v_width) CU(cudaMemcpyAsync(s->v_kp, v_kp, sizeof(float) * (size_t)s->v_width * b.n_kp, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(s->init_lig_pos, init_lig_pos, sizeof(float) * 3 * b.B, cudaMemcpyDeviceToDevice, st));
     RunParams rp;
-    rp.noise = noise; rp.seed = seed; rp.T = s->cfg.T; rp.pad = 0;
+    rp.noise = noise; rp.seed = seed; rp.T = s->cfg.T; rp.atom_offset = s->atom_offset;
     int counter0[4] = {s->cfg.T, s->cfg.T, 0, 0};
     // small pageable H2D copies: staged by the runtime before the call returns
     CU(cudaMemcpyAsync(s->rp, &rp, sizeof(rp), cudaMemcpyHostToDevice, st));

@@ -5,6 +5,7 @@ models/ligand_diffuser.py:24-538; the 1000-step loop of sample_from_encoded_rece
 replayed CUDA graph inside libkpdiff_b200.so (ops.Sampler).  Training (`forward`, losses) is
 out of scope (sampling only) and raises NotImplementedError.
 """
+import os
 from math import ceil
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
@@ -18,6 +19,8 @@ from .n_nodes_dist import LigandSizeDistribution
 from .receptor_encoder import ReceptorEncoder, ReceptorEncoderGVP
 from .schedule import PredefinedNoiseSchedule, alpha, coefficient_table, sigma, sigma_and_alpha_t_given_s
 from .utils import copy_graph, get_batch_idxs
+
+DEFAULT_SUB_BATCHES = 2
 
 
 class FixedReceptorEncoder(nn.Module):
@@ -75,6 +78,7 @@ class KeypointDiffusion(nn.Module):
             self.rec_encoder = FixedReceptorEncoder(rec_encoder_config['vector_size'] if architecture == 'gvp' else None)
         object.__setattr__(self, "_samplers", {})
         object.__setattr__(self, "_coef", {})
+        object.__setattr__(self, "last_launches_per_step", 0)
 
     # ------------------------------------------------------------------ training (out of scope)
     def forward(self, complex_graphs, interface_points=None):
@@ -156,10 +160,50 @@ class KeypointDiffusion(nn.Module):
                                               lig_feat_norm_constant=float(self.lig_feat_norm_constant))
         return self._samplers[key]
 
+    def _sub_samplers(self, g, n_sub, steps_per_graph, use_cuda_graph):
+        """The batch cut into n_sub contiguous groups of complexes, each with its own captured loop (ops.Sampler) and its
+        own stream.  Complexes are independent (no cross-complex term anywhere in the loop), so the groups' kernels may
+        run concurrently: a fused edge kernel of one group is only a few waves of long-running CTAs, and the CTAs of the
+        other groups fill the SMs its tail leaves idle.  Noise is keyed by the GLOBAL atom index, so the split does not
+        change what is drawn."""
+        batch, kk = self._layout(g)
+        model = self.dynamics.device_model(g.device)
+        key = ("sub", id(batch), id(kk), id(model), n_sub, steps_per_graph, use_cuda_graph, getattr(model, "precision", "fp32"))
+        if key not in self._samplers:
+            if len(self._samplers) > 3:
+                self._samplers.clear()
+            B = batch.B
+            ks, kd = g.edges(form="uv", etype="kk")
+            ks, kd = ks.cpu().long(), kd.cpu().long()
+            kp_ptr = batch.kp_ptr.cpu().long()
+            lig_ptr = batch.lig_ptr.cpu().long()
+            bounds = [round(i * B / n_sub) for i in range(n_sub + 1)]
+            subs = []
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                sb = ops.DeviceBatch(batch.lig_n[a:b], batch.kp_n[a:b], g.device)
+                k0, k1, l0, l1 = int(kp_ptr[a]), int(kp_ptr[b]), int(lig_ptr[a]), int(lig_ptr[b])
+                m = (kd >= k0) & (kd < k1)
+                skk = ops.Csr.from_edges(ks[m] - k0, kd[m] - k0, sb.n_kp, g.device)
+                smp = ops.Sampler(model, sb, self.dynamics.graph_params(), skk, self.coef_table(g.device), self.n_timesteps,
+                                  self.n_lig_features, steps_per_graph=steps_per_graph, use_cuda_graph=use_cuda_graph,
+                                  lig_feat_norm_constant=float(self.lig_feat_norm_constant), atom_offset=l0)
+                subs.append((smp, (a, b), (k0, k1), (l0, l1), torch.cuda.Stream(device=g.device)))
+            self._samplers[key] = subs
+        return self._samplers[key]
+
+    @staticmethod
+    def default_sub_batches(n_complexes: int) -> int:
+        """How many concurrently sampled groups a batch is cut into when the caller does not say (measured on B200,
+        DESIGN.md section 4.4); KPD_SUB_BATCHES overrides."""
+        env = os.environ.get("KPD_SUB_BATCHES")
+        if env:
+            return max(1, min(int(env), n_complexes))
+        return max(1, min(DEFAULT_SUB_BATCHES, n_complexes // 16))
+
     @torch.no_grad()
     def sample_from_encoded_receptors(self, g, visualize=False, init_lig_pos: torch.Tensor = None, noise=None,
                                       seed: Optional[int] = None, steps_per_graph: int = 50, use_cuda_graph: bool = True,
-                                      return_device_tensors: bool = False):
+                                      return_device_tensors: bool = False, sub_batches: Optional[int] = None):
         """Returns (lig_pos, lig_feat): one CPU tensor per complex, as the reference does.  ``g`` may
         live on the CPU (pinned or not): its keypoint tensors are uploaded here, which is the
         host->device boundary of the path (reference test.py:152-161)."""
@@ -178,11 +222,38 @@ class KeypointDiffusion(nn.Module):
                 raise ValueError("init_lig_pos is required when the graph has no 'rec' nodes (fixed encoder; "
                                  "the reference would take a mean over zero nodes here, SURVEY N7)")
             init_pos = hetero.readout_nodes(g, feat='x_0', op='mean', ntype='rec')
-        sampler = self._sampler(g, steps_per_graph, use_cuda_graph)
         kp = g.nodes['kp'].data
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # follows torch.manual_seed like the reference
-        x_lig, h_lig, x_kp = sampler.run(kp['x_0'], kp['h_0'], kp.get('v_0'), init_pos, noise=noise, seed=seed)
+        n_sub = self.default_sub_batches(batch_size) if sub_batches is None else max(1, min(int(sub_batches), batch_size))
+        if noise is not None:
+            n_sub = 1          # injected noise (parity runs) is laid out for the undivided batch
+        if n_sub == 1:
+            sampler = self._sampler(g, steps_per_graph, use_cuda_graph)
+            x_lig, h_lig, x_kp = sampler.run(kp['x_0'], kp['h_0'], kp.get('v_0'), init_pos, noise=noise, seed=seed)
+            object.__setattr__(self, "last_launches_per_step", sampler.launches_per_step)
+        else:
+            subs = self._sub_samplers(g, n_sub, steps_per_graph, use_cuda_graph)
+            cur = torch.cuda.current_stream(dev)
+            kx, kh, kv = kp['x_0'].float().contiguous(), kp['h_0'].float().contiguous(), kp.get('v_0')
+            kv = kv.float().contiguous() if kv is not None else None
+            init_pos = init_pos.float().contiguous()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            parts = []
+            for smp, (a, b), (k0, k1), _, st in subs:
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    out = smp.run(kx[k0:k1], kh[k0:k1], kv[k0:k1] if kv is not None else None, init_pos[a:b], seed=seed)
+                for t in out:
+                    t.record_stream(cur)
+                parts.append(out)
+            for *_, st in subs:
+                cur.wait_stream(st)
+            x_lig = torch.cat([p[0] for p in parts])
+            h_lig = torch.cat([p[1] for p in parts])
+            x_kp = torch.cat([p[2] for p in parts])
+            object.__setattr__(self, "last_launches_per_step", sum(smp.launches_per_step for smp, *_ in subs))
         g.nodes['lig'].data['x_0'], g.nodes['lig'].data['h_0'], g.nodes['kp'].data['x_0'] = x_lig, h_lig, x_kp
         if return_device_tensors:
             return x_lig, h_lig

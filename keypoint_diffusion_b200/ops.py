@@ -348,7 +348,7 @@ class Sampler:
 
     def __init__(self, model: _Model, batch: DeviceBatch, gp: GraphParams, kk: Optional[Csr], coef: torch.Tensor,
                  T: int, atom_nf: int, steps_per_graph: int = 50, use_cuda_graph: bool = True,
-                 lig_feat_norm_constant: float = 1.0):
+                 lig_feat_norm_constant: float = 1.0, atom_offset: int = 0):
         self.model, self.batch, self.gp, self.kk, self.coef = model, batch, gp, kk, coef
         _require_cuda(coef)
         self.T, self.atom_nf = int(T), int(atom_nf)
@@ -367,6 +367,8 @@ class Sampler:
         check(lib.kpd_sampler_create(C.byref(self.cfg), model.handle, C.byref(batch.c), C.byref(self._gpc),
                                      C.byref(kk.c) if kk is not None else None, int(self.has_lk), ptr(coef), cap_ll,
                                      cap_kl, ptr(self.ws), n, C.byref(self.handle)), "kpd_sampler_create")
+        if atom_offset:     # this sampler holds a slice of a larger batch: keep the noise of the undivided batch
+            check(lib.kpd_sampler_set_atom_offset(self.handle, int(atom_offset)), "kpd_sampler_set_atom_offset")
 
     def __del__(self):
         if getattr(self, "handle", None) and self.handle.value and lib is not None:

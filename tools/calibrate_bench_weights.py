@@ -30,7 +30,7 @@ for wl, scales in (("gvp_20kp", [1, -1, 30, -30, 100, -100, 300, -300]), ("egnn_
                     p.mul_(sc)
         g = HeteroBatch.from_pockets([pocket], [n_atoms] * B, 10).to(dev)
         x, h = model.sample_from_encoded_receptors(g, init_lig_pos=torch.zeros(B, 3, device=dev), seed=7,
-                                                   return_device_tensors=True)
+                                                   return_device_tensors=True, sub_batches=1)
         torch.cuda.synchronize()
         s = next(iter(model._samplers.values()))
         st = (C.c_double * 4)()
