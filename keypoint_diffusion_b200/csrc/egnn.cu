@@ -562,7 +562,8 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             WL.kch = 2 * cdiv(H, 16);
             for (int e = 0; e < m->n_et; ++e)
                 for (int br = 0; br < 2; ++br) WL.t[e].W2P[br] = W.W2P[e][br];
-            egnn_edge_ws_kernel<<<dim3(max_tiles, m->n_et), egws::NT, m->edge_smem_ws, st>>>(WL);
+            for (int e = 0; e < 4; ++e) WL.tile_off[e + 1] = WL.tile_off[e] + (e < m->n_et ? cdiv(caps[e] > 0 ? caps[e] : 1, egws::R) : 0);
+            egnn_edge_ws_kernel<<<dim3(WL.tile_off[4]), egws::NT, m->edge_smem_ws, st>>>(WL);
             KPD_TRY(check_launch("egnn_edge_ws_kernel"));
         } else {
             egnn_edge_kernel<<<dim3(max_tiles, m->n_et), NT, m->edge_smem, st>>>(L);

@@ -88,13 +88,19 @@ struct EgnnWsLaunch {
     EgnnEdgeLaunch L;
     EgnnWsEtype t[4];
     int kch;
+    int tile_off[5];            // 1-D grid: CTAs [tile_off[e], tile_off[e+1]) are the tiles of edge type e (at capacity)
 };
 
 __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_constant__ EgnnWsLaunch W) {
     using namespace egws;
     const EgnnEdgeLaunch& L = W.L;
-    const EgnnEtypeArgs& a = L.e[blockIdx.y];
-    const int tile_begin = blockIdx.x * R;
+    // each edge type gets exactly the tiles its capacity needs (a 2-D grid sized by the largest type would launch
+    // ~2x as many CTAs that only find out they are empty)
+    int et = 0;
+    while (et < 3 && (int)blockIdx.x >= W.tile_off[et + 1]) ++et;
+    const int bx = (int)blockIdx.x - W.tile_off[et];
+    const EgnnEtypeArgs& a = L.e[et];
+    const int tile_begin = bx * R;
     // this thread's edge, fetched together with the edge count (arrays are sized at capacity: the speculative read is
     // in bounds; rows past the end are re-read from the tile's last edge below)
     int my_s = 0, my_d = 0;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                     const uint32_t st = it % C::STAGES;
                     if (it >= (uint32_t)C::STAGES) tc::mbar_wait(&m.empty[st], ((it / C::STAGES) - 1) & 1);
                     tc::mbar_arrive_expect_tx(&m.full[st], slab);
-                    tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, W.t[blockIdx.y].W2P[br] + (size_t)j * (slab / 16), slab, &m.full[st]);
+                    tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, W.t[et].W2P[br] + (size_t)j * (slab / 16), slab, &m.full[st]);
                 }
         }
     } else if (warp == NW) {
@@ -366,8 +372,8 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             gt[2 + 2 * br] = clock64();
             // segmented reduction by destination (copy_e + sum, :177-185)
             const int nseg = m.seg[R + 1];
-            float* part0 = a.part + ((size_t)blockIdx.x * 2 + 0) * L.pw;
-            float* part1 = a.part + ((size_t)blockIdx.x * 2 + 1) * L.pw;
+            float* part0 = a.part + ((size_t)bx * 2 + 0) * L.pw;
+            float* part1 = a.part + ((size_t)bx * 2 + 1) * L.pw;
             if (br == 0) {
                 // one warp per group of segments, one lane per 8-column chunk: 16-byte reads of the hi and lo planes
                 // (bank-conflict free thanks to the +16 B chunk stride), 32-byte coalesced stores

@@ -20,7 +20,7 @@ from .receptor_encoder import ReceptorEncoder, ReceptorEncoderGVP
 from .schedule import PredefinedNoiseSchedule, alpha, coefficient_table, sigma, sigma_and_alpha_t_given_s
 from .utils import copy_graph, get_batch_idxs
 
-DEFAULT_SUB_BATCHES = 2
+DEFAULT_SUB_BATCHES = 4
 
 
 class FixedReceptorEncoder(nn.Module):
