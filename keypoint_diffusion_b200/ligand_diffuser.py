@@ -20,7 +20,7 @@ from .receptor_encoder import ReceptorEncoder, ReceptorEncoderGVP
 from .schedule import PredefinedNoiseSchedule, alpha, coefficient_table, sigma, sigma_and_alpha_t_given_s
 from .utils import copy_graph, get_batch_idxs
 
-DEFAULT_SUB_BATCHES = 4
+DEFAULT_SUB_BATCHES = {"gvp": 4, "egnn": 2}      # measured on B200: profiles/r01_sweep_sub_batches_*.txt
 
 
 class FixedReceptorEncoder(nn.Module):
@@ -191,14 +191,13 @@ class KeypointDiffusion(nn.Module):
             self._samplers[key] = subs
         return self._samplers[key]
 
-    @staticmethod
-    def default_sub_batches(n_complexes: int) -> int:
+    def default_sub_batches(self, n_complexes: int) -> int:
         """How many concurrently sampled groups a batch is cut into when the caller does not say (measured on B200,
         DESIGN.md section 4.4); KPD_SUB_BATCHES overrides."""
         env = os.environ.get("KPD_SUB_BATCHES")
         if env:
             return max(1, min(int(env), n_complexes))
-        return max(1, min(DEFAULT_SUB_BATCHES, n_complexes // 16))
+        return max(1, min(DEFAULT_SUB_BATCHES[self.architecture], n_complexes // 16))
 
     @torch.no_grad()
     def sample_from_encoded_receptors(self, g, visualize=False, init_lig_pos: torch.Tensor = None, noise=None,
