@@ -18,7 +18,7 @@ from .dynamics import LigRecDynamics, LigRecDynamicsGVP
 from .n_nodes_dist import LigandSizeDistribution
 from .receptor_encoder import ReceptorEncoder, ReceptorEncoderGVP
 from .schedule import PredefinedNoiseSchedule, alpha, coefficient_table, sigma, sigma_and_alpha_t_given_s
-from .utils import copy_graph, get_batch_idxs
+from .utils import copy_graph, get_batch_idxs, split_bounds
 
 DEFAULT_SUB_BATCHES = {"gvp": 4, "egnn": 2}      # measured on B200: profiles/r01_sweep_sub_batches_*.txt
 
@@ -177,7 +177,7 @@ class KeypointDiffusion(nn.Module):
             ks, kd = ks.cpu().long(), kd.cpu().long()
             kp_ptr = batch.kp_ptr.cpu().long()
             lig_ptr = batch.lig_ptr.cpu().long()
-            bounds = [round(i * B / n_sub) for i in range(n_sub + 1)]
+            bounds = split_bounds(B, n_sub)
             subs = []
             for a, b in zip(bounds[:-1], bounds[1:]):
                 sb = ops.DeviceBatch(batch.lig_n[a:b], batch.kp_n[a:b], g.device)

@@ -68,3 +68,10 @@ def decode_ligands(lig_pos: List[torch.Tensor], lig_feat: List[torch.Tensor], li
         idx = torch.argmax(feat, dim=1).tolist()
         out.append((pos, [lig_elements[i] for i in idx]))
     return out
+
+
+def split_bounds(n_complexes: int, n_groups: int):
+    """Boundaries of n_groups contiguous, near-equal groups of complexes: [b_0 = 0, ..., b_n = n_complexes].
+    Used by KeypointDiffusion._sub_samplers (a batch sampled as concurrent sub-batches)."""
+    n_groups = max(1, min(int(n_groups), int(n_complexes)))
+    return [round(i * n_complexes / n_groups) for i in range(n_groups + 1)]

@@ -116,3 +116,25 @@ def test_output_decode_matches_reference_format():
     assert [d[1] for d in dec] == [["N", "Cl"], ["O"]]
     txt = write_xyz_file(dec[0][0], dec[0][1])
     assert txt == "2\n\nN 0.000 1.000 2.000\nCl 1.235 -2.000 3.500\n"
+
+
+def test_sub_batch_partition_and_default_count(monkeypatch):
+    """Host logic of the concurrent sub-batch sampling: contiguous near-equal groups that cover the batch exactly;
+    default group count per architecture, never fewer than 16 complexes per group; KPD_SUB_BATCHES overrides."""
+    from keypoint_diffusion_b200 import model_from_config
+    from keypoint_diffusion_b200.utils import split_bounds
+    import os
+    for B in (1, 2, 3, 16, 33, 100, 1024):
+        for n in (1, 2, 3, 4, 7):
+            b = split_bounds(B, n)
+            assert b[0] == 0 and b[-1] == B and all(y > x for x, y in zip(b[:-1], b[1:]))
+            sizes = [y - x for x, y in zip(b[:-1], b[1:])]
+            assert len(sizes) == min(n, B) and max(sizes) - min(sizes) <= 1
+    os.chdir(ROOT)
+    monkeypatch.delenv("KPD_SUB_BATCHES", raising=False)
+    cfgs = _cfgs()
+    gvp, egnn = model_from_config(cfgs["gvp_20kp"]), model_from_config(cfgs["egnn_20kp"])
+    assert [gvp.default_sub_batches(B) for B in (1, 10, 31, 32, 64, 100, 4096)] == [1, 1, 1, 2, 4, 4, 4]
+    assert [egnn.default_sub_batches(B) for B in (10, 32, 100, 800)] == [1, 2, 2, 2]
+    monkeypatch.setenv("KPD_SUB_BATCHES", "3")
+    assert gvp.default_sub_batches(100) == 3 and gvp.default_sub_batches(2) == 2
