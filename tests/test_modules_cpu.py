@@ -47,6 +47,8 @@ def test_constructor_errors_match_reference(monkeypatch):
         KeypointDiffusion(10, 128, Path("/nonexistent"))
     with pytest.raises(NotImplementedError):
         LigRecDynamicsGVP(10, 128, no_cg=True)
+    with pytest.raises(NotImplementedError):      # dead and broken in the reference, no shipped config enables it
+        KeypointDiffusion(10, 128, d, use_fake_atoms=True)
 
 
 def test_no_cpu_fallback(monkeypatch):
