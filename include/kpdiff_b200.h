@@ -207,6 +207,13 @@ int kpd_gvp_set_mode(kpd_gvp_model* m, int32_t mode);
 int64_t kpd_gvp_workspace_bytes(const kpd_gvp_model* m, const kpd_batch* batch,
                                 int32_t cap_ll, int32_t cap_kl, int32_t cap_kk);
 
+/* Stream semantics: the call is ordered on `stream` like any kernel launch (everything it does starts after prior work
+ * on `stream` and is complete before later work on `stream`), and it may be captured into a CUDA graph.  In the
+ * tensor-core modes the convs are issued as a dependency graph over auxiliary streams owned by the model (forked from
+ * and joined back to `stream` by events inside the call; KPD_GVP_SERIAL=1 at model creation keeps everything on
+ * `stream`).  A graph captured from it should be instantiated with cudaGraphInstantiateFlagUseNodePriority (the
+ * node kernels carry a launch priority).  One call at a time per model handle from the host's point of view (the
+ * model owns the events); concurrent execution of several captured graphs of the same model is fine. */
 int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* batch,
                     const float* h_lig, const float* x_lig, const float* h_kp, const float* x_kp,
                     const float* v_kp, const float* t_ptr, int32_t t_per_complex,
