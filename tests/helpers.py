@@ -49,3 +49,23 @@ def rel_err(a, b):
 def edge_set(ei):
     """A sorted list of (src, dst) pairs for exact set comparison."""
     return sorted(zip(ei[0].tolist(), ei[1].tolist()))
+
+
+def err_report(a, b):
+    """Three views of the error of `a` against the reference `b` ([N, C] tensors):
+      norm  max|a-b| / max|b|                       -- the headline bar (north_star's 1e-4 "relative")
+      rms   rms(a-b) / rms(b)                       -- the typical element
+      chan  max over channels c of max_i|a-b|[:,c] / max_i|b|[:,c]
+                                                    -- a small-magnitude channel cannot hide behind a large one
+    """
+    a = a.double().reshape(b.shape[0], -1)
+    b = b.double().reshape(b.shape[0], -1)
+    d = (a - b).abs()
+    norm = float(d.max() / b.abs().max().clamp(min=1e-30))
+    rms = float(d.pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-30))
+    chan = float((d.max(0).values / b.abs().max(0).values.clamp(min=1e-30)).max())
+    return {"norm": norm, "rms": rms, "chan": chan}
+
+
+def fmt_err(r):
+    return f"norm {r['norm']:.2e} rms {r['rms']:.2e} per-channel {r['chan']:.2e}"
