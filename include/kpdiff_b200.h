@@ -290,6 +290,10 @@ int32_t kpd_sampler_launches_per_step(const kpd_sampler* s);
  * as several sub-batches (own samplers, own streams) and draw exactly the noise of the undivided batch. */
 int kpd_sampler_set_atom_offset(kpd_sampler* s, int32_t first_atom);
 
+/* Output decode, the step right behind the path (reference test.py:199-203: torch.argmax(lig_feat, dim=1) on the
+ * host, then dataset.lig_atom_idx_to_element): atom_type[i] = argmax_c h_lig[i, c], lowest index on ties. */
+int kpd_decode_atom_types(const float* h_lig, int32_t n_lig, int32_t atom_nf, int32_t* atom_type, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Diagnostics (tools/tc_phase_times.py, tools/eg_phase_times.py, tools/ws_trace.py): in-kernel phase timers of the
  * warp-specialised kernels, in SM cycles summed over CTAs; each call synchronises the device, copies the counters

@@ -101,6 +101,7 @@ def _load():
         "kpd_sampler_run": (I, [P, P, P, P, P, P, P, P, U64, I, P]),
         "kpd_sampler_launches_per_step": (I, [P]),
         "kpd_sampler_set_atom_offset": (I, [P, I]),
+        "kpd_decode_atom_types": (I, [P, I, I, P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

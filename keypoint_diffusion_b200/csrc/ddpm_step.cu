@@ -172,6 +172,21 @@ int launch_scale(float* x, int n, float s, cudaStream_t st) {
     return check_launch("scale_kernel");
 }
 
+// atom type of every generated atom = argmax over its feature channels, lowest index on ties (reference test.py:199-203:
+// torch.argmax(lig_feat, dim=1), then dataset.lig_atom_idx_to_element); NaN-free inputs assumed, like the reference
+__global__ void decode_atom_types_kernel(const float* __restrict__ h, int n, int F, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* row = h + (size_t)i * F;
+    float best = row[0];
+    int arg = 0;
+    for (int c = 1; c < F; ++c) {
+        const float v = row[c];
+        if (v > best) { best = v; arg = c; }
+    }
+    out[i] = arg;
+}
+
 // s = --counter; step = s; t_cur = coef[4 s + 3]   (ligand_diffuser.py:404-408)
 __global__ void step_prologue_kernel(int* counter, int* step, float* t_cur, const float* coef) {
     const int s = *counter - 1;
@@ -214,4 +229,11 @@ extern "C" int kpd_shift_by_complex(float* x, const int32_t* node_batch, int32_t
 extern "C" int kpd_randn_init(float* x_lig, float* h_lig, int32_t n_lig, int32_t atom_nf, uint64_t seed, void* stream) {
     KPD_REQUIRE(x_lig && h_lig, "kpd_randn_init: null argument");
     return launch_randn_init(x_lig, h_lig, n_lig, atom_nf, seed, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kpd_decode_atom_types(const float* h_lig, int32_t n_lig, int32_t atom_nf, int32_t* atom_type, void* stream) {
+    KPD_REQUIRE(h_lig && atom_type && atom_nf >= 1 && n_lig >= 0, "kpd_decode_atom_types: bad argument");
+    if (n_lig == 0) return 0;
+    decode_atom_types_kernel<<<kpd::cdiv(n_lig, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h_lig, n_lig, atom_nf, atom_type);
+    return kpd::check_launch("decode_atom_types_kernel");
 }

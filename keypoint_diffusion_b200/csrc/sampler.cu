@@ -157,11 +157,14 @@ extern "C" void kpd_sampler_destroy(kpd_sampler* s) {
 extern "C" int kpd_sampler_edge_stats(kpd_sampler* s, double* out) {
     KPD_REQUIRE(s && out, "kpd_sampler_edge_stats: null argument");
     long long h[4] = {0, 0, 0, 0};
+    int e_kk = 0;
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (e == cudaSuccess) e = cudaMemcpy(h, s->edge_accum, sizeof(h), cudaMemcpyDeviceToHost);
+    // the kk edge count lives on the device like every other (rowptr[n_dst]); cap is only the capacity of the arrays
+    if (e == cudaSuccess && s->has_lk) e = cudaMemcpy(&e_kk, s->kk.rowptr + s->kk.n_dst, sizeof(int), cudaMemcpyDeviceToHost);
     KPD_REQUIRE(e == cudaSuccess, "kpd_sampler_edge_stats: %s", cudaGetErrorString(e));
     const double n = h[2] > 0 ? (double)h[2] : 1.0;
-    out[0] = h[0] / n; out[1] = h[1] / n; out[2] = s->has_lk ? (double)s->kk.cap : 0.0; out[3] = (double)h[2];
+    out[0] = h[0] / n; out[1] = h[1] / n; out[2] = s->has_lk ? (double)e_kk : 0.0; out[3] = (double)h[2];
     return 0;
 }
 

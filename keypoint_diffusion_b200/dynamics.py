@@ -23,8 +23,10 @@ class _DeviceState:
         self.batch = None
         self.batch_key = None
         self.kk = None
-        self.kk_key = None
+        self.kk_key = None          # content hash of the kk edge list the CSR was built from
+        self.kk_ref = None          # (src, dst, versions): strong refs, so identity checks cannot be fooled by address reuse
         self.graphs = None
+        self.warned_fp32 = False
 
 
 class _DynamicsBase(ParamTree):
@@ -47,13 +49,36 @@ class _DynamicsBase(ParamTree):
             st.batch = ops.DeviceBatch(key[0], key[1], dev)
             st.batch_key = key
             st.graphs = None
-            st.kk_key = None
+            st.kk_key = st.kk_ref = None
         ks, kd = g.edges(form="uv", etype="kk")
-        kkey = (ks.data_ptr(), kd.data_ptr(), int(ks.numel()))
-        if st.kk_key != kkey:
-            st.kk = ops.Csr.from_edges(ks, kd, st.batch.n_kp, dev)
-            st.kk_key = kkey
+        ref = st.kk_ref
+        if ref is None or ref[0] is not ks or ref[1] is not kd or ref[2] != (ks._version, kd._version):
+            # a different (or edited) edge list: key the CSR on its CONTENT -- the kk graph depends on the receptor
+            # geometry, and raw addresses are recycled by the caching allocator between diffusion batches
+            ks_c, kd_c = ks.to("cpu", torch.int64).contiguous(), kd.to("cpu", torch.int64).contiguous()
+            kkey = (int(ks_c.numel()), hash(ks_c.numpy().tobytes()), hash(kd_c.numpy().tobytes()))
+            if st.kk_key != kkey or st.kk is None:
+                st.kk = ops.Csr.from_edges(ks_c, kd_c, st.batch.n_kp, dev)
+                st.kk_key = kkey
+            st.kk_ref = (ks, kd, (ks._version, kd._version))
         return st.batch, st.kk
+
+    def layout_key(self):
+        """Content key of the current layout (complex sizes, device, kk edge list): what captured samplers are cached on."""
+        return (self._st.batch_key, self._st.kk_key)
+
+    def _resolve_precision(self, model):
+        """The requested tensor-core mode, or fp32 SIMT when this width has no tensor-core tiles -- said out loud once:
+        the SIMT kernels are ~6x slower."""
+        if model.tc_blob2 is not None:
+            return self.precision
+        if self.precision != "fp32" and not self._st.warned_fp32:
+            import warnings
+            warnings.warn(f"{type(self).__name__}: no tensor-core tiles for this hidden width; precision={self.precision!r} "
+                          f"falls back to the fp32 SIMT kernels (still CUDA, several times slower)", RuntimeWarning,
+                          stacklevel=3)
+            self._st.warned_fp32 = True
+        return "fp32"
 
     def _graphs(self, batch, with_lk):
         st = self._st
@@ -111,7 +136,7 @@ class LigRecDynamics(_DynamicsBase):
                                      message_norm=self.message_norm, device=device,
                                      z_effective=self.message_norm_effective)
             st.model_key = key
-        want = self.precision if st.model.tc_blob2 is not None else "fp32"
+        want = self._resolve_precision(st.model)
         if st.model.precision != want:
             st.model.set_precision(want)
         return st.model
@@ -171,7 +196,7 @@ class LigRecDynamicsGVP(_DynamicsBase):
                                     n_update_gvps=self.n_update_gvps, n_noise_gvps=self.n_noise_gvps,
                                     message_norm=self.message_norm, device=device)
             st.model_key = key
-        want = self.precision if st.model.tc_blob2 is not None else "fp32"
+        want = self._resolve_precision(st.model)
         if st.model.precision != want:
             st.model.set_precision(want)
         return st.model

@@ -214,6 +214,50 @@ def batch(graphs: List[HeteroBatch]) -> HeteroBatch:
     return out
 
 
+def expand_complexes(enc: HeteroBatch, pocket_idx: torch.Tensor, n_lig_atoms: torch.Tensor, atom_nf: int = None) -> HeteroBatch:
+    """One batched graph with a complex per entry of pocket_idx: complex c = the encoded pocket enc[pocket_idx[c]]
+    (its keypoint data and kk edges) with n_lig_atoms[c] zero-filled ligand atoms.
+
+    The device-side replacement of the reference's per-complex host loop -- utils.copy_graph (utils.py:103-156) called
+    once per receptor and dgl.batch per diffusion batch (ligand_diffuser.py:292-313): there every copy deep-clones
+    every tensor of its pocket on the host (seconds at thousands of complexes); here the whole batch is a handful of
+    index computations (cumsum / repeat_interleave / gather) on the device the encoded pockets live on, with no Python
+    loop over complexes.  'rec' nodes are not carried over (nothing behind the encoder reads them; callers pass
+    init_lig_pos)."""
+    dev = enc.device
+    pocket_idx = pocket_idx.to(dev, torch.long)
+    n_lig = n_lig_atoms.to(dev, torch.long)
+    C = int(pocket_idx.numel())
+    kp_n_p = enc.batch_num_nodes("kp").to(dev, torch.long)
+    kp_off_p = torch.cumsum(kp_n_p, 0) - kp_n_p
+    kp_n_c = kp_n_p[pocket_idx]
+    kp_off_c = torch.cumsum(kp_n_c, 0) - kp_n_c
+    K = int(kp_n_c.sum())
+    # row gather: complex c takes rows kp_off_p[p_c] + [0, kp_n_c[c])
+    shift = torch.repeat_interleave(kp_off_p[pocket_idx] - kp_off_c, kp_n_c, output_size=K)
+    rows = shift + torch.arange(K, device=dev)
+    kp_data = {k: v.index_select(0, rows) for k, v in enc.nodes["kp"].data.items()}
+    # kk edges: complex c takes the edges of pocket p_c, renumbered from the pocket's rows to the complex's rows
+    ks, kd = enc.edges(form="uv", etype="kk")
+    e_n_p = enc.batch_num_edges("kk").to(dev, torch.long)
+    e_off_p = torch.cumsum(e_n_p, 0) - e_n_p
+    e_n_c = e_n_p[pocket_idx]
+    e_off_c = torch.cumsum(e_n_c, 0) - e_n_c
+    E = int(e_n_c.sum())
+    eshift = torch.repeat_interleave(e_off_p[pocket_idx] - e_off_c, e_n_c, output_size=E)
+    eidx = eshift + torch.arange(E, device=dev)
+    renum = torch.repeat_interleave(kp_off_c - kp_off_p[pocket_idx], e_n_c, output_size=E)
+    new_s, new_d = ks.index_select(0, eidx) + renum, kd.index_select(0, eidx) + renum
+    N_l = int(n_lig.sum())
+    lig_ref = enc.nodes["lig"].data
+    F = atom_nf if atom_nf is not None else (lig_ref["h_0"].shape[1] if "h_0" in lig_ref else 0)
+    nd = {"kp": kp_data,
+          "lig": {"x_0": torch.zeros(N_l, 3, device=dev), "h_0": torch.zeros(N_l, F, device=dev)},     # utils.py:142-144
+          "rec": {"x_0": torch.zeros(0, 3, device=dev), "h_0": torch.zeros(0, 1, device=dev)}}
+    return HeteroBatch({"kp": kp_n_c, "lig": n_lig, "rec": torch.zeros(C, dtype=torch.long, device=dev)}, nd,
+                       {("kp", "kk", "kp"): (new_s, new_d)}, {("kp", "kk", "kp"): e_n_c})
+
+
 def unbatch(g: HeteroBatch) -> List[HeteroBatch]:
     B = g.batch_size
     out = []

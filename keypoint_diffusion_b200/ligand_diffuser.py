@@ -18,7 +18,7 @@ from .dynamics import LigRecDynamics, LigRecDynamicsGVP
 from .n_nodes_dist import LigandSizeDistribution
 from .receptor_encoder import ReceptorEncoder, ReceptorEncoderGVP
 from .schedule import PredefinedNoiseSchedule, alpha, coefficient_table, sigma, sigma_and_alpha_t_given_s
-from .utils import copy_graph, get_batch_idxs, split_bounds
+from .utils import get_batch_idxs, split_bounds
 
 DEFAULT_SUB_BATCHES = {"gvp": 4, "egnn": 2}      # measured on B200: profiles/r01_sweep_sub_batches_*.txt
 
@@ -79,6 +79,8 @@ class KeypointDiffusion(nn.Module):
         object.__setattr__(self, "_samplers", {})
         object.__setattr__(self, "_coef", {})
         object.__setattr__(self, "last_launches_per_step", 0)
+        object.__setattr__(self, "_streams", {})
+        object.__setattr__(self, "cold_captures", 0)       # capacity buckets captured so far (a cold call each)
 
     # ------------------------------------------------------------------ training (out of scope)
     def forward(self, complex_graphs, interface_points=None):
@@ -131,9 +133,17 @@ class KeypointDiffusion(nn.Module):
 
     # ------------------------------------------------------------------ one reverse step (reference :497-538)
     @torch.no_grad()
-    def sample_p_zs_given_zt(self, s: torch.Tensor, t: torch.Tensor, g, batch_idxs=None, noise=None, seed: int = 0):
+    def sample_p_zs_given_zt(self, s: torch.Tensor, t: torch.Tensor, g, batch_idxs=None, noise=None,
+                             seed: Optional[int] = None):
         """Mutates lig x_0/h_0 and kp x_0 of g in place and returns g.  ``noise=(pos_noise, feat_noise)``
-        injects the Gaussian draws (parity); otherwise Philox keyed by (seed, step, atom, channel)."""
+        injects the Gaussian draws (parity); otherwise Philox keyed by (seed, step, atom, channel).  With seed=None
+        (default) a fresh seed is drawn from torch's global generator on every call, so a caller driving the
+        reference-style per-step loop gets new noise per step, per batch and per run, and torch.manual_seed makes it
+        reproducible -- like the reference's torch.randn draws (ligand_diffuser.py:520-527).  An explicit seed is
+        deterministic: same (seed, step, atom, channel) -> same draw."""
+        if seed is None and noise is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seed = 0 if seed is None else seed
         batch, _ = self._layout(g)
         eps_h, eps_x = self.dynamics(g, t, batch_idxs)
         s_int = int(torch.round(s.flatten()[0] * self.n_timesteps).item())
@@ -147,13 +157,26 @@ class KeypointDiffusion(nn.Module):
         return g
 
     # ------------------------------------------------------------------ the loop (reference :342-469)
+    MAX_CACHED_SAMPLERS = 24
+
+    def _cache_get(self, key):
+        """Captured samplers are cached on the CONTENT of what they were captured for (complex sizes, kk edge list,
+        parameter versions, mode) -- never on object ids, which CPython and the caching allocator recycle -- and evicted
+        least-recently-used, one at a time (a wipe would destroy captured graphs mid-workload)."""
+        hit = self._samplers.pop(key, None)
+        if hit is not None:
+            self._samplers[key] = hit           # re-insert: most recently used last
+            return hit
+        while len(self._samplers) >= self.MAX_CACHED_SAMPLERS:
+            self._samplers.pop(next(iter(self._samplers)))
+        return None
+
     def _sampler(self, g, steps_per_graph, use_cuda_graph) -> ops.Sampler:
         batch, kk = self._layout(g)
         model = self.dynamics.device_model(g.device)
-        key = (id(batch), id(kk), id(model), steps_per_graph, use_cuda_graph, getattr(model, "precision", "fp32"))
-        if key not in self._samplers:
-            if len(self._samplers) > 3:
-                self._samplers.clear()
+        key = ("one", self.dynamics.layout_key(), self.dynamics._st.model_key, steps_per_graph, use_cuda_graph,
+               getattr(model, "precision", "fp32"))
+        if self._cache_get(key) is None:
             self._samplers[key] = ops.Sampler(model, batch, self.dynamics.graph_params(), kk, self.coef_table(g.device),
                                               self.n_timesteps, self.n_lig_features, steps_per_graph=steps_per_graph,
                                               use_cuda_graph=use_cuda_graph,
@@ -168,10 +191,9 @@ class KeypointDiffusion(nn.Module):
         change what is drawn."""
         batch, kk = self._layout(g)
         model = self.dynamics.device_model(g.device)
-        key = ("sub", id(batch), id(kk), id(model), n_sub, steps_per_graph, use_cuda_graph, getattr(model, "precision", "fp32"))
-        if key not in self._samplers:
-            if len(self._samplers) > 3:
-                self._samplers.clear()
+        key = ("sub", self.dynamics.layout_key(), self.dynamics._st.model_key, n_sub, steps_per_graph, use_cuda_graph,
+               getattr(model, "precision", "fp32"))
+        if self._cache_get(key) is None:
             B = batch.B
             ks, kd = g.edges(form="uv", etype="kk")
             ks, kd = ks.cpu().long(), kd.cpu().long()
@@ -199,34 +221,124 @@ class KeypointDiffusion(nn.Module):
             return max(1, min(int(env), n_complexes))
         return max(1, min(DEFAULT_SUB_BATCHES[self.architecture], n_complexes // 16))
 
+    def _capacity_sampler(self, instance: int, plan: "ops.CapacityPlan", device, steps_per_graph, use_cuda_graph):
+        """The captured loop of capacity bucket plan.key (created on first use, then shared by every batch that lands in
+        the bucket -- whatever its per-complex sizes, pockets or kk graph).  Groups of one call that run concurrently
+        and share a bucket take distinct instances 0, 1, ... of it."""
+        model = self.dynamics.device_model(device)
+        key = ("cap", instance, plan.key, self.dynamics._st.model_key, steps_per_graph, use_cuda_graph,
+               getattr(model, "precision", "fp32"), self.n_timesteps)
+        hit = self._cache_get(key)
+        if hit is None:
+            kp_width = self.n_kp_feat
+            v_width = self.dynamics.vector_size if self.architecture == "gvp" else 0
+            hit = ops.CapacitySampler(model, plan, self.dynamics.graph_params(), self.coef_table(device), self.n_timesteps,
+                                      self.n_lig_features, kp_width, v_width, steps_per_graph=steps_per_graph,
+                                      use_cuda_graph=use_cuda_graph,
+                                      lig_feat_norm_constant=float(self.lig_feat_norm_constant))
+            self._samplers[key] = hit
+            object.__setattr__(self, "cold_captures", self.cold_captures + 1)
+        return hit
+
     @torch.no_grad()
     def sample_from_encoded_receptors(self, g, visualize=False, init_lig_pos: torch.Tensor = None, noise=None,
                                       seed: Optional[int] = None, steps_per_graph: int = 50, use_cuda_graph: bool = True,
-                                      return_device_tensors: bool = False, sub_batches: Optional[int] = None):
-        """Returns (lig_pos, lig_feat): one CPU tensor per complex, as the reference does.  ``g`` may
-        live on the CPU (pinned or not): its keypoint tensors are uploaded here, which is the
-        host->device boundary of the path (reference test.py:152-161)."""
+                                      return_device_tensors: bool = False, sub_batches: Optional[int] = None,
+                                      decode: bool = False, capacity: bool = True):
+        """Returns (lig_pos, lig_feat): one CPU tensor per complex, as the reference does (:342-469).  ``g`` may live
+        on the CPU (pinned or not): its keypoint tensors are uploaded here, straight into the sampler's buffers -- the
+        host->device boundary of the path (reference test.py:152-161).
+
+        The batch is sampled by capacity-bucketed captured loops (ops.plan_capacity / ops.CapacitySampler): a new
+        tuple of ligand sizes, another pocket or another kk graph re-uses the CUDA graphs captured for its bucket
+        instead of re-capturing, so the reference's real entry points -- random sizes per call, :490-495 -- stay warm.
+        ``capacity=False`` selects samplers captured for the exact layout (kept for A/B tests).  ``decode=True`` also
+        returns the atom types (argmax over the feature channels, computed on the device: test.py:199-203)."""
         if visualize:
             raise NotImplementedError("visualize=True (a per-step CPU copy of the whole graph) is a debug feature "
                                       "outside the throughput path")
         dev = torch.device("cuda", torch.cuda.current_device()) if g.device.type != "cuda" else g.device
-        if g.device.type != "cuda":
-            g = g.to(dev)
         batch_size = g.batch_size
         if init_lig_pos is not None:
             assert init_lig_pos.shape == (batch_size, 3)
-            init_pos = init_lig_pos.to(dev, torch.float32, non_blocking=True)
+            init_pos = init_lig_pos
         else:
             if g.num_nodes('rec') == 0:
                 raise ValueError("init_lig_pos is required when the graph has no 'rec' nodes (fixed encoder; "
                                  "the reference would take a mean over zero nodes here, SURVEY N7)")
             init_pos = hetero.readout_nodes(g, feat='x_0', op='mean', ntype='rec')
-        kp = g.nodes['kp'].data
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # follows torch.manual_seed like the reference
         n_sub = self.default_sub_batches(batch_size) if sub_batches is None else max(1, min(int(sub_batches), batch_size))
         if noise is not None:
             n_sub = 1          # injected noise (parity runs) is laid out for the undivided batch
+        if not capacity:
+            return self._sample_exact_layout(g, dev, init_pos, noise, seed, steps_per_graph, use_cuda_graph,
+                                             return_device_tensors, n_sub)
+        kp = g.nodes['kp'].data
+        lig_n = g.batch_num_nodes('lig').tolist()
+        kp_n = g.batch_num_nodes('kp').tolist()
+        ks, kd = g.edges(form="uv", etype="kk")
+        kk_n = g.batch_num_edges('kk').tolist()
+        grouped = sum(kk_n) == int(ks.numel())          # kk edges grouped by complex (dgl.batch / hetero.batch order)
+        lig_ptr = [0]
+        kp_ptr = [0]
+        kk_ptr = [0]
+        for b in range(batch_size):
+            lig_ptr.append(lig_ptr[-1] + lig_n[b]); kp_ptr.append(kp_ptr[-1] + kp_n[b]); kk_ptr.append(kk_ptr[-1] + kk_n[b])
+        bounds = split_bounds(batch_size, n_sub)
+        gp = self.dynamics.graph_params()
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        parts, used, launches, taken = [], [], 0, {}
+        kv = kp.get('v_0')
+        for slot, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            k0, k1, l0 = kp_ptr[a], kp_ptr[b], lig_ptr[a]
+            if grouped:
+                gs, gd = ks[kk_ptr[a]:kk_ptr[b]] - k0, kd[kk_ptr[a]:kk_ptr[b]] - k0
+            else:
+                m = (kd >= k0) & (kd < k1)
+                gs, gd = ks[m] - k0, kd[m] - k0
+            plan = ops.plan_capacity(lig_n[a:b], kp_n[a:b], int(gs.numel()), gp)
+            inst = taken.get(plan.key, 0)
+            taken[plan.key] = inst + 1
+            smp = self._capacity_sampler(inst, plan, dev, steps_per_graph, use_cuda_graph)
+            if n_sub > 1 and (slot, str(dev)) not in self._streams:
+                self._streams[(slot, str(dev))] = torch.cuda.Stream(device=dev)
+            st = self._streams[(slot, str(dev))] if n_sub > 1 else cur
+            if n_sub > 1:
+                st.wait_event(ready)
+            with torch.cuda.stream(st):
+                out = smp.run(plan, kp['x_0'][k0:k1], kp['h_0'][k0:k1], kv[k0:k1] if kv is not None else None, gs, gd,
+                              init_pos[a:b], seed=seed, atom_offset=l0, noise=noise, decode=decode)
+            if n_sub > 1:
+                for t in out:
+                    t.record_stream(cur)
+                used.append(st)
+            parts.append(out)
+            launches += smp.sampler.launches_per_step
+        for st in used:
+            cur.wait_stream(st)
+        cat = (lambda i: parts[0][i]) if len(parts) == 1 else (lambda i: torch.cat([p[i] for p in parts]))
+        x_lig, h_lig, x_kp = cat(0), cat(1), cat(2)
+        atom_type = cat(3) if decode else None
+        object.__setattr__(self, "last_launches_per_step", launches)
+        if g.device.type == "cuda":
+            g.nodes['lig'].data['x_0'], g.nodes['lig'].data['h_0'], g.nodes['kp'].data['x_0'] = x_lig, h_lig, x_kp
+        if return_device_tensors:
+            return (x_lig, h_lig, atom_type) if decode else (x_lig, h_lig)
+        pos_cpu, feat_cpu = x_lig.cpu(), h_lig.cpu()                # device -> host boundary (reference :464)
+        res = (list(torch.split(pos_cpu, lig_n)), list(torch.split(feat_cpu, lig_n)))
+        return res + (list(torch.split(atom_type.cpu(), lig_n)),) if decode else res
+
+    def _sample_exact_layout(self, g, dev, init_pos, noise, seed, steps_per_graph, use_cuda_graph, return_device_tensors,
+                             n_sub):
+        """Samplers captured for the exact per-complex layout of g (one per distinct tuple of sizes)."""
+        if g.device.type != "cuda":
+            g = g.to(dev)
+        init_pos = init_pos.to(dev, torch.float32, non_blocking=True)
+        kp = g.nodes['kp'].data
         if n_sub == 1:
             sampler = self._sampler(g, steps_per_graph, use_cuda_graph)
             x_lig, h_lig, x_kp = sampler.run(kp['x_0'], kp['h_0'], kp.get('v_0'), init_pos, noise=noise, seed=seed)
@@ -257,51 +369,107 @@ class KeypointDiffusion(nn.Module):
         if return_device_tensors:
             return x_lig, h_lig
         sizes = g.batch_num_nodes('lig').tolist()
-        pos_cpu, feat_cpu = x_lig.cpu(), h_lig.cpu()                # device -> host boundary (reference :464)
+        pos_cpu, feat_cpu = x_lig.cpu(), h_lig.cpu()
         return list(torch.split(pos_cpu, sizes)), list(torch.split(feat_cpu, sizes))
 
     # ------------------------------------------------------------------ batch drivers (reference :270-340, :472-495)
     @torch.no_grad()
+    def _encode_all(self, ref_graphs: List, rec_enc_batch_size: int, encoded: bool):
+        """All receptors encoded and batched into ONE graph on the model's device, plus the per-receptor mean of the
+        'rec' positions (what sample_from_encoded_receptors falls back to for init_lig_pos, reference :359-360)."""
+        dev = self.gamma.gamma.device
+        if encoded:
+            enc = hetero.batch(ref_graphs)
+            enc = enc if enc.device == dev else enc.to(dev)
+        else:
+            # rec_enc_batch_size receptors per encoder pass (reference :277-287), on the device the weights live on
+            chunks = []
+            for b in range(ceil(len(ref_graphs) / rec_enc_batch_size)):
+                chunk = hetero.batch(ref_graphs[b * rec_enc_batch_size:(b + 1) * rec_enc_batch_size])
+                chunks.append(self.encode_receptors(chunk if chunk.device == dev else chunk.to(dev)))
+            enc = chunks[0] if len(chunks) == 1 else hetero.batch(chunks)
+        rec_mean = hetero.readout_nodes(enc, feat='x_0', op='mean', ntype='rec') if enc.num_nodes('rec') > 0 else None
+        return enc, rec_mean
+
+    @torch.no_grad()
     def _sample(self, ref_graphs: List, n_lig_atoms: List[List[int]], rec_enc_batch_size: int = 32,
                 diff_batch_size: int = 32, visualize=False, use_ref_lig_com: bool = False, encoded: bool = False,
-                init_lig_pos: Optional[List[torch.Tensor]] = None):
-        """ref_graphs: one single-complex graph per receptor.  ``encoded=True`` skips the receptor
-        encoder (graphs already hold kp nodes + kk edges).  init_lig_pos: optional [3] tensor per receptor."""
+                init_lig_pos: Optional[List[torch.Tensor]] = None, noise: Optional[List[torch.Tensor]] = None,
+                complexes: Optional[List[int]] = None, **sampler_kw):
+        """ref_graphs: one single-complex graph per receptor (reference :270-340).  ``encoded=True`` skips the receptor
+        encoder (graphs already hold kp nodes + kk edges).  init_lig_pos: optional [3] tensor per receptor.
+        noise: optional injected Gaussian draws, one [T+1, n_lig*(3+F)] tensor per diffusion batch (parity runs).
+        complexes: optional subset (indices into the flattened receptor-major list of requested ligands) to sample --
+        what sample_sharded deals to this rank; the returned lists then hold only those.
+
+        The diffusion batches are assembled on the device (hetero.expand_complexes): no per-complex graph copies."""
         n_receptors = len(ref_graphs)
-        if encoded:
-            enc_graphs = ref_graphs
+        enc, rec_mean = self._encode_all(ref_graphs, rec_enc_batch_size, encoded)
+        dev = enc.device
+        pocket_of = [r for r in range(n_receptors) for _ in n_lig_atoms[r]]
+        sizes = [int(n) for r in range(n_receptors) for n in n_lig_atoms[r]]
+        todo = list(range(len(sizes))) if complexes is None else list(complexes)
+        if init_lig_pos is not None:
+            centers = torch.stack([c.reshape(3) for c in init_lig_pos]).to(dev, torch.float32)
+        elif use_ref_lig_com:
+            # copy_graph zero-fills the ligand before the mean is taken, so this is the origin (SURVEY N10)
+            centers = torch.zeros(n_receptors, 3, device=dev)
         else:
-            # encode the pockets rec_enc_batch_size at a time (reference :277-287), on the device the weights live on
-            dev = self.gamma.gamma.device
-            enc_graphs = []
-            for b in range(ceil(n_receptors / rec_enc_batch_size)):
-                chunk = hetero.batch(ref_graphs[b * rec_enc_batch_size:(b + 1) * rec_enc_batch_size])
-                enc_graphs.extend(hetero.unbatch(self.encode_receptors(chunk if chunk.device == dev else chunk.to(dev))))
-        graphs, centers = [], []
-        for rec_idx, ref_graph in enumerate(enc_graphs):
-            sizes = n_lig_atoms[rec_idx]
-            graphs.extend(copy_graph(ref_graph, n_copies=len(sizes), lig_atoms_per_copy=torch.tensor(sizes)))
-            if init_lig_pos is not None:
-                centers.extend([init_lig_pos[rec_idx].reshape(1, 3)] * len(sizes))
-        n_complexes = len(graphs)
+            centers = rec_mean
+        pocket_t = torch.tensor(pocket_of, dtype=torch.long, device=dev)
+        size_t = torch.tensor(sizes, dtype=torch.long, device=dev)
         lig_pos, lig_feat = [], []
-        for b in range(ceil(n_complexes / diff_batch_size)):
-            sl = slice(b * diff_batch_size, min((b + 1) * diff_batch_size, n_complexes))
-            bg = hetero.batch(graphs[sl])
-            if init_lig_pos is not None:
-                center = torch.cat(centers[sl])
-            elif use_ref_lig_com:
-                # copy_graph zero-fills ligand data, so this is the origin -- as in the reference (SURVEY N10)
-                center = hetero.readout_nodes(bg, feat='x_0', op='mean', ntype='lig')
-            else:
-                center = None
-            p, f = self.sample_from_encoded_receptors(bg, visualize=visualize, init_lig_pos=center)
+        for b in range(ceil(len(todo) / diff_batch_size)):
+            idx = torch.tensor(todo[b * diff_batch_size:(b + 1) * diff_batch_size], dtype=torch.long, device=dev)
+            bg = hetero.expand_complexes(enc, pocket_t[idx], size_t[idx], self.n_lig_features)
+            if centers is None:
+                raise ValueError("init_lig_pos is required when the graphs have no 'rec' nodes (SURVEY N7)")
+            p, f = self.sample_from_encoded_receptors(bg, visualize=visualize, init_lig_pos=centers[pocket_t[idx]],
+                                                      noise=None if noise is None else noise[b], **sampler_kw)
             lig_pos.extend(p)
             lig_feat.extend(f)
+        if complexes is not None:
+            return lig_pos, lig_feat
         samples, end = [], 0
         for rec_idx in range(n_receptors):
             start, end = end, end + len(n_lig_atoms[rec_idx])
             samples.append({'positions': lig_pos[start:end], 'features': lig_feat[start:end]})
+        return samples
+
+    @torch.no_grad()
+    def sample_sharded(self, ref_graphs: List, n_lig_atoms: List[List[int]], rec_enc_batch_size: int = 32,
+                       diff_batch_size: int = 128, group=None, **kw):
+        """_sample over every rank of the process group (one process per GPU): the requested (receptor, ligand size)
+        pairs are dealt to the ranks by estimated cost (dist.shard_complexes), each rank samples its share with its own
+        captured loops and no per-step communication, and ONE final all_gather (NCCL over NVLink; gloo in the CPU
+        tests) brings coordinates + atom features back, so every rank returns the complete, receptor-major result of
+        ``_sample``.  The reference's equivalent is a slurm array of independent single-GPU processes
+        (gen_test_commands.py:36-40, test.py:143-184).  Noise follows this rank's torch generator / ``seed``."""
+        import torch.distributed as dist
+        from . import dist as kdist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        sizes = [int(n) for r in range(len(ref_graphs)) for n in n_lig_atoms[r]]
+        kp_n = [int(g.num_nodes('kp')) or int(g.num_nodes('rec')) for g in ref_graphs]
+        kp_of = [kp_n[r] for r in range(len(ref_graphs)) for _ in n_lig_atoms[r]]
+        shards = kdist.shard_complexes(sizes, kp_of, world)
+        mine = shards[rank]
+        pos, feat = self._sample(ref_graphs, n_lig_atoms, rec_enc_batch_size, diff_batch_size, complexes=mine, **kw)
+        dev = self.gamma.gamma.device
+        F = self.n_lig_features
+        x = torch.cat(pos).to(dev) if pos else torch.zeros(0, 3, device=dev)
+        h = torch.cat(feat).to(dev) if feat else torch.zeros(0, F, device=dev)
+        xs, hs, all_sizes = kdist.gather_ligands(x, h, [sizes[i] for i in mine], group=group)
+        out_pos, out_feat = [None] * len(sizes), [None] * len(sizes)
+        for r in range(world):
+            px = torch.split(xs[r].cpu(), all_sizes[r])
+            ph = torch.split(hs[r].cpu(), all_sizes[r])
+            for j, i in enumerate(shards[r]):
+                out_pos[i], out_feat[i] = px[j], ph[j]
+        samples, end = [], 0
+        for rec_idx in range(len(ref_graphs)):
+            start, end = end, end + len(n_lig_atoms[rec_idx])
+            samples.append({'positions': out_pos[start:end], 'features': out_feat[start:end]})
         return samples
 
     @torch.no_grad()

@@ -34,7 +34,7 @@ class DeviceBatch:
     """Node layout of a batch of complexes (replaces the DGL batch bookkeeping read by the hot
     path: g.batch_size, g.batch_num_nodes, utils.get_batch_idxs -- reference utils.py:81-170)."""
 
-    def __init__(self, lig_n: Sequence[int], kp_n: Sequence[int], device):
+    def __init__(self, lig_n: Sequence[int], kp_n: Sequence[int], device, max_lig: int = 0, max_kp: int = 0):
         lig_n = [int(v) for v in lig_n]
         kp_n = [int(v) for v in kp_n]
         if len(lig_n) != len(kp_n) or not lig_n:
@@ -54,8 +54,31 @@ class DeviceBatch:
         self.kp_ptr = kp.to(self.device)
         self.lig_batch = ar.repeat_interleave(ln).to(self.device)
         self.kp_batch = ar.repeat_interleave(kn).to(self.device)
-        self.c = KpdBatch(self.B, self.n_lig, self.n_kp, max(lig_n), max(kp_n), self.lig_ptr.data_ptr(),
-                          self.kp_ptr.data_ptr(), self.lig_batch.data_ptr(), self.kp_batch.data_ptr())
+        self.c = KpdBatch(self.B, self.n_lig, self.n_kp, max(max(lig_n), int(max_lig or 0)), max(max(kp_n), int(max_kp or 0)),
+                          self.lig_ptr.data_ptr(), self.kp_ptr.data_ptr(), self.lig_batch.data_ptr(),
+                          self.kp_batch.data_ptr())
+
+    def set_layout(self, lig_n: Sequence[int], kp_n: Sequence[int]):
+        """Overwrite the per-complex sizes IN PLACE (same device arrays, same addresses): the number of complexes and
+        the node totals must stay what this object was created with, and no complex may exceed max_lig / max_kp.  This
+        is what lets a captured sampler (whose kernels hold these addresses and the totals) run a different batch."""
+        lig_n = [int(v) for v in lig_n]
+        kp_n = [int(v) for v in kp_n]
+        if (len(lig_n) != self.B or len(kp_n) != self.B or sum(lig_n) != self.n_lig or sum(kp_n) != self.n_kp
+                or max(lig_n) > self.c.max_lig or max(kp_n) > self.c.max_kp or min(lig_n) < 1 or min(kp_n) < 1):
+            raise ValueError("set_layout: the new layout does not fit this batch's fixed totals / maxima")
+        if lig_n == self.lig_n and kp_n == self.kp_n:
+            return
+        self.lig_n, self.kp_n = lig_n, kp_n
+        ln = torch.tensor(lig_n, dtype=torch.int64)
+        kn = torch.tensor(kp_n, dtype=torch.int64)
+        lp = torch.zeros(self.B + 1, dtype=torch.int32); lp[1:] = torch.cumsum(ln, 0)
+        kp = torch.zeros(self.B + 1, dtype=torch.int32); kp[1:] = torch.cumsum(kn, 0)
+        ar = torch.arange(self.B, dtype=torch.int32)
+        self.lig_ptr.copy_(lp, non_blocking=True)
+        self.kp_ptr.copy_(kp, non_blocking=True)
+        self.lig_batch.copy_(ar.repeat_interleave(ln), non_blocking=True)
+        self.kp_batch.copy_(ar.repeat_interleave(kn), non_blocking=True)
 
     def edge_capacity(self, gp: "GraphParams") -> Tuple[int, int]:
         """(cap_ll, cap_kl): the most edges any configuration of this batch can produce."""
@@ -110,6 +133,26 @@ class Csr:
         rp[1:] = torch.cumsum(torch.bincount(dst, minlength=n_dst), 0)
         out.rowptr.copy_(rp.to(torch.int32))
         return out
+
+    def fill_from_edges(self, src: torch.Tensor, dst: torch.Tensor):
+        """Rewrite this CSR IN PLACE from global (src, dst) index lists, with device ops only (stable sort by
+        destination, bincount, cumsum): no host round trip, addresses unchanged, so a captured sampler that holds this
+        CSR sees the new graph.  At most `cap` edges."""
+        n = int(src.numel())
+        if n > self.cap:
+            raise ValueError(f"fill_from_edges: {n} edges exceed the capacity {self.cap}")
+        dev = self.rowptr.device
+        if n == 0:
+            self.rowptr.zero_()
+            return self
+        src = src.to(dev, non_blocking=True)
+        dst = dst.to(dev, non_blocking=True)
+        order = torch.sort(dst, stable=True).indices
+        self.src[:n] = src[order].to(torch.int32)
+        self.dst[:n] = dst[order].to(torch.int32)
+        self.rowptr[0] = 0
+        self.rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=self.n_dst), 0).to(torch.int32)
+        return self
 
     def edges(self) -> torch.Tensor:
         """[2, E] int64 (src; dst) on the CPU -- synchronises; for tests and debugging only."""
@@ -243,8 +286,11 @@ class EgnnModel(_Model):
         caps = (graphs.ll.cap, graphs.kl.cap, kk.cap if kk is not None else 1)
         ws = self._workspace(batch, caps)
         per_complex = int(t.numel() == batch.B and batch.B > 1)
-        check(lib.kpd_egnn_forward(self.handle, C.byref(batch.c), ptr(_f32(h_lig)), ptr(_f32(x_lig)), ptr(_f32(h_kp)),
-                                   ptr(_f32(x_kp)), ptr(kp_feat_enc), ptr(_f32(t)), per_complex,
+        # converted copies are bound to locals so they outlive the launch (a temporary would go back to the caching
+        # allocator inside the argument list and two arguments could alias)
+        h_lig, x_lig, h_kp, x_kp, t = _f32(h_lig), _f32(x_lig), _f32(h_kp), _f32(x_kp), _f32(t)
+        check(lib.kpd_egnn_forward(self.handle, C.byref(batch.c), ptr(h_lig), ptr(x_lig), ptr(h_kp),
+                                   ptr(x_kp), ptr(kp_feat_enc), ptr(t), per_complex,
                                    C.byref(graphs.ll.c), C.byref(graphs.kl.c),
                                    C.byref(graphs.lk.c) if graphs.lk is not None else None,
                                    C.byref(kk.c) if kk is not None else None, ptr(eps_h), ptr(eps_x), ptr(ws),
@@ -317,8 +363,9 @@ class GvpModel(_Model):
         caps = (graphs.ll.cap, graphs.kl.cap, kk.cap if kk is not None else 1)
         ws = self._workspace(batch, caps)
         per_complex = int(t.numel() == batch.B and batch.B > 1)
-        check(lib.kpd_gvp_forward(self.handle, C.byref(batch.c), ptr(_f32(h_lig)), ptr(_f32(x_lig)), ptr(_f32(h_kp)),
-                                  ptr(_f32(x_kp)), ptr(_f32(v_kp)), ptr(_f32(t)), per_complex, C.byref(graphs.ll.c),
+        h_lig, x_lig, h_kp, x_kp, v_kp, t = _f32(h_lig), _f32(x_lig), _f32(h_kp), _f32(x_kp), _f32(v_kp), _f32(t)
+        check(lib.kpd_gvp_forward(self.handle, C.byref(batch.c), ptr(h_lig), ptr(x_lig), ptr(h_kp),
+                                  ptr(x_kp), ptr(v_kp), ptr(t), per_complex, C.byref(graphs.ll.c),
                                   C.byref(graphs.kl.c), C.byref(graphs.lk.c) if graphs.lk is not None else None,
                                   C.byref(kk.c) if kk is not None else None, ptr(eps_h), ptr(eps_x), ptr(ws),
                                   _stream()), "kpd_gvp_forward")
@@ -332,6 +379,18 @@ def ddpm_step(batch: DeviceBatch, x_lig, h_lig, x_kp, eps_x, eps_h, coef, step: 
     check(lib.kpd_ddpm_step(C.byref(batch.c), ptr(x_lig), ptr(h_lig), ptr(x_kp), ptr(eps_x), ptr(eps_h),
                             h_lig.shape[1], ptr(coef), ptr(step), ptr(noise_x), ptr(noise_h), int(seed), _stream()),
           "kpd_ddpm_step")
+
+
+def decode_atom_types(h_lig: torch.Tensor) -> torch.Tensor:
+    """int32 [n] = argmax over the feature channels of every atom (lowest index wins ties, like torch.argmax on the
+    CPU), on the device through kpd_decode_atom_types -- what the reference computes on the host right after sampling
+    (test.py:199-203: ``torch.argmax(feat, dim=1)`` then ``lig_atom_idx_to_element``)."""
+    _require_cuda(h_lig)
+    h_lig = _f32(h_lig)
+    out = torch.empty(h_lig.shape[0], dtype=torch.int32, device=h_lig.device)
+    check(lib.kpd_decode_atom_types(ptr(h_lig), h_lig.shape[0], h_lig.shape[1], ptr(out), _stream()),
+          "kpd_decode_atom_types")
+    return out
 
 
 def remove_com(batch: DeviceBatch, x_lig, x_kp, which: str):
@@ -348,7 +407,7 @@ class Sampler:
 
     def __init__(self, model: _Model, batch: DeviceBatch, gp: GraphParams, kk: Optional[Csr], coef: torch.Tensor,
                  T: int, atom_nf: int, steps_per_graph: int = 50, use_cuda_graph: bool = True,
-                 lig_feat_norm_constant: float = 1.0, atom_offset: int = 0):
+                 lig_feat_norm_constant: float = 1.0, atom_offset: int = 0, caps: Optional[Tuple[int, int]] = None):
         self.model, self.batch, self.gp, self.kk, self.coef = model, batch, gp, kk, coef
         _require_cuda(coef)
         self.T, self.atom_nf = int(T), int(atom_nf)
@@ -356,7 +415,7 @@ class Sampler:
         steps_per_graph = max(1, min(int(steps_per_graph), self.T))
         self.cfg = KpdSamplerConfig(model.arch, self.T, self.atom_nf, steps_per_graph, int(bool(use_cuda_graph)),
                                     float(lig_feat_norm_constant))
-        cap_ll, cap_kl = batch.edge_capacity(gp)
+        cap_ll, cap_kl = caps if caps is not None else batch.edge_capacity(gp)
         cap_kk = kk.cap if kk is not None else 1
         n = int(lib.kpd_sampler_workspace_bytes(C.byref(self.cfg), model.handle, C.byref(batch.c), cap_ll, cap_kl, cap_kk))
         if n < 0:
@@ -375,8 +434,10 @@ class Sampler:
             lib.kpd_sampler_destroy(self.handle)
             self.handle = C.c_void_p()
 
-    def run(self, x_kp, h_kp, v_kp, init_lig_pos, noise=None, seed=0, n_steps=None):
-        """Returns (x_lig [n_lig,3], h_lig [n_lig,F], x_kp) on the device, in the input frame."""
+    def run(self, x_kp, h_kp, v_kp, init_lig_pos, noise=None, seed=0, n_steps=None, decode=False):
+        """Returns (x_lig [n_lig,3], h_lig [n_lig,F], x_kp) on the device, in the input frame; with decode=True also
+        the atom type of every generated atom (int32 [n_lig] = argmax over the feature channels, the first step of
+        the reference's output handling, test.py:199-203), written by a kernel enqueued behind the loop."""
         _require_cuda(x_kp, h_kp, init_lig_pos)
         b = self.batch
         x_kp = _f32(x_kp).clone()
@@ -386,11 +447,154 @@ class Sampler:
         if noise is not None:
             _require_cuda(noise)
             assert noise.shape == (self.T + 1, b.n_lig * (3 + self.atom_nf)) and noise.dtype == torch.float32
-        check(lib.kpd_sampler_run(self.handle, ptr(x_kp), ptr(_f32(h_kp)), ptr(_f32(v_kp)) if v_kp is not None else None,
-                                  ptr(_f32(init_lig_pos)), ptr(x_lig), ptr(h_lig), ptr(noise), int(seed), n_steps,
+        h_kp, init_lig_pos = _f32(h_kp), _f32(init_lig_pos)
+        v_kp = _f32(v_kp) if v_kp is not None else None
+        check(lib.kpd_sampler_run(self.handle, ptr(x_kp), ptr(h_kp), ptr(v_kp) if v_kp is not None else None,
+                                  ptr(init_lig_pos), ptr(x_lig), ptr(h_lig), ptr(noise), int(seed), n_steps,
                                   _stream()), "kpd_sampler_run")
+        if decode:
+            return x_lig, h_lig, x_kp, decode_atom_types(h_lig)
         return x_lig, h_lig, x_kp
 
     @property
     def launches_per_step(self):
         return int(lib.kpd_sampler_launches_per_step(self.handle))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Capacity-based sampling: capture once per capacity bucket, run any batch that fits.
+#
+# A captured loop (Sampler) bakes in three kinds of constants: the addresses of its buffers, the node totals
+# (B, n_lig, n_kp -> grids, workspace carving) and the edge capacities.  The per-complex structure, on the other
+# hand, is DATA: lig_ptr / kp_ptr / lig_batch / kp_batch and the kk CSR are device arrays the kernels read.  So a
+# sampler captured for totals (B, N, K) runs ANY batch whose padded layout has exactly those totals: the real
+# complexes come first (their global atom indices, hence their Philox noise, and their tile boundaries are those of
+# the unpadded batch), followed by a few filler complexes that absorb the spare atoms / keypoints.  Complexes are
+# independent (no cross-complex term anywhere in the loop), so the fillers cannot influence the real ones; their
+# results are dropped.  Totals are rounded up to coarse granules, so that the sizes drawn by
+# LigandSizeDistribution.sample (reference n_nodes_dist.py:42-60; a new draw per call in
+# ligand_diffuser.py:490-495) land in a handful of buckets.
+
+def _round_up(v: int, g: int) -> int:
+    return (int(v) + g - 1) // g * g
+
+
+def _pow2_floor(v: int) -> int:
+    g = 1
+    while g * 2 <= v:
+        g *= 2
+    return g
+
+
+def _geometric_bucket(v: int, lo: int = 512) -> int:
+    """The smallest value of {lo, 1.5 lo, 2 lo, 3 lo, 4 lo, ...} that is >= v."""
+    b = lo
+    while True:
+        if v <= b:
+            return b
+        if v <= b + b // 2:
+            return b + b // 2
+        b *= 2
+
+
+@dataclass(frozen=True)
+class CapacityPlan:
+    key: Tuple                       # (B, N, K, max_lig, max_kp, cap_ll, cap_kl, cap_kk)
+    lig_n: Tuple[int, ...]           # padded layout: real complexes first, then fillers
+    kp_n: Tuple[int, ...]
+    n_real: int                      # real complexes
+    n_lig_real: int
+    n_kp_real: int
+
+
+def plan_capacity(lig_n: Sequence[int], kp_n: Sequence[int], n_kk_edges: int, gp: "GraphParams") -> CapacityPlan:
+    """Capacity bucket + padded layout for a batch (see the comment above).  The bucket is coarse on purpose: node
+    totals round up to a granule of ~1/6 of the total (<= ~8 % filler work on average), per-complex maxima to 64 / 8,
+    and the edge capacities are functions of the node totals wherever a bound exists, so that ligand sizes drawn
+    afresh for every call (LigandSizeDistribution.sample) fall into a few buckets."""
+    lig_n = [int(v) for v in lig_n]
+    kp_n = [int(v) for v in kp_n]
+    B_r, N_r, K_r = len(lig_n), sum(lig_n), sum(kp_n)
+    max_lig, max_kp = _round_up(max(lig_n), 64), _round_up(max(kp_n), 8)
+    gN, gK = max(8, _pow2_floor(N_r // 6)), max(8, _pow2_floor(K_r // 6))
+    N, K = _round_up(N_r + 1, gN), _round_up(K_r + 1, gK)
+    while True:
+        f_min = max(-(-(N - N_r) // max_lig), -(-(K - K_r) // max_kp), 1)
+        B = _round_up(B_r + f_min, 8)
+        f = B - B_r
+        if f <= N - N_r and f <= K - K_r:
+            break
+        if f > N - N_r:
+            N += gN
+        if f > K - K_r:
+            K += gK
+
+    def spread(total, parts):
+        q, r = divmod(total, parts)
+        return [q + (1 if i < r else 0) for i in range(parts)]
+
+    lig_p = lig_n + spread(N - N_r, f)
+    kp_p = kp_n + spread(K - K_r, f)
+    ll_lim = gp.ll_k if gp.ll_k > 0 else gp.ll_cap
+    kl_lim = gp.kl_k if gp.kl_k > 0 else gp.kl_cap
+    need_ll = max(sum(n * min(n - 1, ll_lim) for n in lig_p), 1)
+    need_kl = max(sum(k * min(n, kl_lim) for n, k in zip(lig_p, kp_p)), 1)
+    if gp.ll_k > 0:
+        cap_ll = N * gp.ll_k
+    else:                                   # radius graph: ~(mean n + var/mean) edges per atom; two levels, then exact
+        cap_ll = next((c for c in (32 * N, 64 * N) if c >= need_ll), _geometric_bucket(need_ll))
+    bound_kl = K * min(max_lig, kl_lim)
+    cap_kl = bound_kl if bound_kl <= 4 * need_kl else _geometric_bucket(need_kl)
+    cap_kk = _geometric_bucket(max(int(n_kk_edges), 1))
+    return CapacityPlan((B, N, K, max_lig, max_kp, cap_ll, cap_kl, cap_kk), tuple(lig_p), tuple(kp_p), B_r, N_r, K_r)
+
+
+class CapacitySampler:
+    """A captured reverse-diffusion loop for one capacity bucket (see plan_capacity): owns its layout arrays, kk CSR and
+    input buffers; run() rewrites their CONTENTS for the batch at hand and replays the same CUDA graphs."""
+
+    def __init__(self, model: _Model, plan: CapacityPlan, gp: GraphParams, coef: torch.Tensor, T: int, atom_nf: int,
+                 kp_width: int, v_width: int, steps_per_graph: int = 50, use_cuda_graph: bool = True,
+                 lig_feat_norm_constant: float = 1.0):
+        B, N, K, max_lig, max_kp, cap_ll, cap_kl, cap_kk = plan.key
+        dev = model.device
+        self.key, self.model, self.atom_nf, self.T = plan.key, model, int(atom_nf), int(T)
+        self.batch = DeviceBatch(plan.lig_n, plan.kp_n, dev, max_lig=max_lig, max_kp=max_kp)
+        self.has_lk = bool(model.update_kp_feat if model.arch == 0 else model.update_kp)
+        self.kk = Csr(K, cap_kk, dev)
+        self.x_kp = torch.zeros(K, 3, dtype=torch.float32, device=dev)
+        self.h_kp = torch.zeros(K, kp_width, dtype=torch.float32, device=dev)
+        self.v_kp = torch.zeros(K, v_width, 3, dtype=torch.float32, device=dev) if v_width else None
+        self.init_pos = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+        self.sampler = Sampler(model, self.batch, gp, self.kk, coef, T, atom_nf, steps_per_graph=steps_per_graph,
+                               use_cuda_graph=use_cuda_graph, lig_feat_norm_constant=lig_feat_norm_constant,
+                               caps=(cap_ll, cap_kl))
+        self.runs = 0
+
+    def run(self, plan: CapacityPlan, x_kp, h_kp, v_kp, kk_src, kk_dst, init_pos, seed: int, atom_offset: int = 0,
+            noise: Optional[torch.Tensor] = None, decode: bool = False):
+        """x_kp/h_kp/v_kp: the REAL keypoint rows (host or device tensors; pinned host tensors are uploaded straight
+        into the capacity buffers); kk_src/kk_dst: kk edges in this batch's own keypoint numbering; init_pos [B_real,3].
+        -> (x_lig [N_real,3], h_lig [N_real,F], x_kp [K_real,3][, atom_type int32 [N_real]]) on the device."""
+        if plan.key != self.key:
+            raise ValueError("CapacitySampler.run: the plan belongs to another capacity bucket")
+        B_r, N_r, K_r = plan.n_real, plan.n_lig_real, plan.n_kp_real
+        self.batch.set_layout(plan.lig_n, plan.kp_n)
+        self.x_kp[:K_r].copy_(x_kp, non_blocking=True)
+        self.h_kp[:K_r].copy_(h_kp, non_blocking=True)
+        if self.v_kp is not None:
+            self.v_kp[:K_r].copy_(v_kp, non_blocking=True)
+        self.init_pos[:B_r].copy_(init_pos, non_blocking=True)
+        if self.has_lk:
+            self.kk.fill_from_edges(kk_src, kk_dst)
+        check(lib.kpd_sampler_set_atom_offset(self.sampler.handle, int(atom_offset)), "kpd_sampler_set_atom_offset")
+        if noise is not None:            # injected draws are laid out for the real atoms: re-lay them for the padded total
+            N, F = self.batch.n_lig, self.atom_nf
+            pad = torch.zeros(noise.shape[0], N * (3 + F), dtype=torch.float32, device=noise.device)
+            pad[:, : N_r * 3] = noise[:, : N_r * 3]
+            pad[:, N * 3: N * 3 + N_r * F] = noise[:, N_r * 3:]
+            noise = pad
+        out = self.sampler.run(self.x_kp, self.h_kp, self.v_kp, self.init_pos, noise=noise, seed=seed, decode=decode)
+        self.runs += 1
+        res = (out[0][:N_r], out[1][:N_r], out[2][:K_r])
+        return res + (out[3][:N_r],) if decode else res

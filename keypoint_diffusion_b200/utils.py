@@ -58,12 +58,17 @@ def write_xyz_file(coords, atom_types, filename=None):
         f.write(out)
 
 
-def decode_ligands(lig_pos: List[torch.Tensor], lig_feat: List[torch.Tensor], lig_elements: List[str]) -> List[Tuple]:
+def decode_ligands(lig_pos: List[torch.Tensor], lig_feat: List[torch.Tensor], lig_elements: List[str],
+                   atom_types: List[torch.Tensor] = None) -> List[Tuple]:
     """What the reference does with the sampler's output before molecule building (test.py:199-203): the atom type
     of every generated atom is the argmax over its feature channels, mapped through the dataset's ``lig_elements``
     (``dataset.lig_atom_idx_to_element``).  Returns one (positions [n,3], element symbols) pair per ligand; bond
     perception / sanitisation (OpenBabel, RDKit) stay with the caller."""
     out = []
+    if atom_types is not None:        # already decoded on the device (sample_from_encoded_receptors(decode=True))
+        for pos, idx in zip(lig_pos, atom_types):
+            out.append((pos, [lig_elements[int(i)] for i in idx.tolist()]))
+        return out
     for pos, feat in zip(lig_pos, lig_feat):
         idx = torch.argmax(feat, dim=1).tolist()
         out.append((pos, [lig_elements[i] for i in idx]))

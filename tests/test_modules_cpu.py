@@ -140,3 +140,67 @@ def test_sub_batch_partition_and_default_count(monkeypatch):
     assert [egnn.default_sub_batches(B) for B in (10, 32, 100, 800)] == [1, 2, 2, 2]
     monkeypatch.setenv("KPD_SUB_BATCHES", "3")
     assert gvp.default_sub_batches(100) == 3 and gvp.default_sub_batches(2) == 2
+
+
+def test_expand_complexes_equals_copy_graph_then_batch():
+    """Device-side batch assembly (hetero.expand_complexes) builds exactly the batch the reference's host loop builds
+    (utils.copy_graph per receptor + dgl.batch per diffusion batch, ligand_diffuser.py:292-313)."""
+    from keypoint_diffusion_b200 import HeteroBatch, hetero, synthetic, utils
+    pk = [synthetic.keypoint_pocket(i, 6 + i, 12, 4) for i in range(3)]
+    encs = [HeteroBatch.from_pockets([p], [1], 10) for p in pk]
+    enc = hetero.batch(encs)
+    pocket_idx, n_lig = torch.tensor([0, 0, 2, 1, 2]), torch.tensor([5, 3, 7, 4, 6])
+    g = hetero.expand_complexes(enc, pocket_idx, n_lig, 10)
+    copies = []
+    for c in range(5):
+        copies.extend(utils.copy_graph(encs[int(pocket_idx[c])], 1, torch.tensor([int(n_lig[c])])))
+    r = hetero.batch(copies)
+    for k in ("x_0", "h_0", "v_0"):
+        assert torch.equal(g.nodes["kp"].data[k], r.nodes["kp"].data[k]), k
+    assert torch.equal(torch.stack(g.edges(form="uv", etype="kk")), torch.stack(r.edges(form="uv", etype="kk")))
+    for nt in ("kp", "lig"):
+        assert torch.equal(g.batch_num_nodes(nt), r.batch_num_nodes(nt))
+    assert torch.equal(g.batch_num_edges("kk"), r.batch_num_edges("kk"))
+    assert torch.equal(g.nodes["lig"].data["h_0"], r.nodes["lig"].data["h_0"])        # zero-filled (utils.py:142-144)
+    assert g.batch_size == 5 and g.num_nodes("rec") == 0
+
+
+def test_capacity_plan_properties():
+    """plan_capacity: real complexes first and unchanged, fillers inside the per-complex maxima, totals and edge
+    capacities cover the padded layout, and freshly drawn ligand sizes land in a handful of buckets."""
+    from keypoint_diffusion_b200 import ops
+    from keypoint_diffusion_b200.n_nodes_dist import LigandSizeDistribution
+    from keypoint_diffusion_b200.utils import split_bounds
+    g = torch.Generator().manual_seed(0)
+    for gp in (ops.GraphParams(ll_r=6.0, kl_k=7), ops.GraphParams(ll_k=4, kl_k=0, kl_r=8.0), ops.GraphParams(ll_r=5.0, kl_k=5)):
+        for trial in range(40):
+            B = int(torch.randint(1, 70, (1,), generator=g))
+            lig = torch.randint(1, 61, (B,), generator=g).tolist()
+            kp = torch.randint(1, 50, (B,), generator=g).tolist() if trial % 2 else [20] * B
+            n_kk = int(torch.randint(0, 400 * B, (1,), generator=g))
+            p = ops.plan_capacity(lig, kp, n_kk, gp)
+            Bc, N, K, ml, mk, cll, ckl, ckk = p.key
+            assert list(p.lig_n[:B]) == lig and list(p.kp_n[:B]) == kp and p.n_real == B
+            assert len(p.lig_n) == len(p.kp_n) == Bc and sum(p.lig_n) == N and sum(p.kp_n) == K
+            assert Bc > B and min(p.lig_n) >= 1 and min(p.kp_n) >= 1 and max(p.lig_n) <= ml and max(p.kp_n) <= mk
+            ll_lim = gp.ll_k if gp.ll_k > 0 else gp.ll_cap
+            kl_lim = gp.kl_k if gp.kl_k > 0 else gp.kl_cap
+            assert cll >= sum(n * min(n - 1, ll_lim) for n in p.lig_n)
+            assert ckl >= sum(k * min(n, kl_lim) for n, k in zip(p.lig_n, p.kp_n))
+            assert ckk >= max(n_kk, 1)
+            assert N <= 1.34 * sum(lig) + 72 and K <= 1.34 * sum(kp) + 72            # bounded filler work
+            assert ops.plan_capacity(lig, kp, n_kk, gp).key == p.key
+    # the reference's real entry point draws new sizes per call (ligand_diffuser.py:490-495): few distinct buckets
+    dist = LigandSizeDistribution(ROOT / "data" / "bindingmoad_processed")
+    torch.manual_seed(1)
+    gp = ops.GraphParams(ll_r=6.0, kl_k=7)
+    keys, waste = set(), []
+    for _ in range(60):
+        sizes = dist.sample(torch.tensor([336]), 100)[0].tolist()
+        bd = split_bounds(100, 4)
+        for a, b in zip(bd[:-1], bd[1:]):
+            p = ops.plan_capacity(sizes[a:b], [20] * (b - a), 322 * (b - a), gp)
+            keys.add(p.key)
+            waste.append((p.key[1] + p.key[2]) / (p.n_lig_real + p.n_kp_real) - 1.0)
+    assert len(keys) <= 8, sorted(keys)
+    assert sum(waste) / len(waste) < 0.10
