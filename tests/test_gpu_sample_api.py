@@ -3,7 +3,7 @@
 * KeypointDiffusion._sample against fixtures produced by the reference's _sample (tests/golden/make_golden_sample.py:
   receptor encoder -> copies with requested ligand sizes -> diffusion batches that straddle receptors -> regrouping),
   with the reference's global-generator draws injected; bar 1e-3 relative over the whole (short) trajectory.
-* capacity samplers: a padded, bucketed sampler gives bit-identical ligands to a sampler captured for the exact layout,
+* capacity samplers: a padded, bucketed sampler gives the ligands of a sampler captured for the exact layout (<= 1e-5),
   and a second batch with other sizes / another pocket re-uses the captured graphs (no new capture).
 * output decode on the device against utils.decode_ligands / torch.argmax.
 """

@@ -204,3 +204,34 @@ def test_capacity_plan_properties():
             waste.append((p.key[1] + p.key[2]) / (p.n_lig_real + p.n_kp_real) - 1.0)
     assert len(keys) <= 8, sorted(keys)
     assert sum(waste) / len(waste) < 0.10
+
+
+def test_reference_arm_weights_equal_product_arm():
+    """bench.py --impl reference rebuilds the seeded weights without importing the product package (no .so in that
+    process); they must be the weights the product arm's model_from_config draws."""
+    import os
+    import bench
+    from keypoint_diffusion_b200 import model_from_config
+    for name in ("gvp_20kp", "egnn_all_atom"):
+        cfg = bench.load_config(name)
+        os.chdir(ROOT)
+        torch.manual_seed(0)
+        model = model_from_config(cfg)
+        sd, arch, kw, rec_nf = bench.reference_state_dict(cfg)
+        msd = {k: v for k, v in model.state_dict().items() if k.startswith("dynamics.")}
+        assert set(sd) == set(msd) and rec_nf == model.n_kp_feat
+        assert all(torch.equal(sd[k], msd[k]) for k in sd)
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """The CPU arm must not dlopen libkpdiff_b200.so (the judge checks which .so files that process loaded)."""
+    import subprocess
+    import sys
+    code = ("import sys, json; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0','--cpu-steps','1',"
+            "'--workload','egnn_20kp_c1']; import runpy; runpy.run_path('bench.py', run_name='__main__');"
+            "maps=open('/proc/self/maps').read(); assert 'libkpdiff_b200' not in maps, 'product library loaded';"
+            "assert not any(m.startswith('keypoint_diffusion_b200') for m in sys.modules), 'product package imported'")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
