@@ -545,7 +545,9 @@ def plan_capacity(lig_n: Sequence[int], kp_n: Sequence[int], n_kk_edges: int, gp
         cap_ll = next((c for c in (32 * N, 64 * N) if c >= need_ll), _geometric_bucket(need_ll))
     bound_kl = K * min(max_lig, kl_lim)
     cap_kl = bound_kl if bound_kl <= 4 * need_kl else _geometric_bucket(need_kl)
-    cap_kk = _geometric_bucket(max(int(n_kk_edges), 1))
+    # kk: keypoint models (<= 64 keypoints per complex) take the complete-graph bound, which does not depend on the
+    # pockets at hand (spare capacity only costs CTAs that exit at once); all-atom pockets a geometric bucket
+    cap_kk = K * (max_kp - 1) if max_kp <= 64 and K * (max_kp - 1) >= n_kk_edges else _geometric_bucket(max(int(n_kk_edges), 1))
     return CapacityPlan((B, N, K, max_lig, max_kp, cap_ll, cap_kl, cap_kk), tuple(lig_p), tuple(kp_p), B_r, N_r, K_r)
 
 
