@@ -42,7 +42,8 @@ struct GvpW {
     const uint4* WfP;   // bf16 mode: to_feats_out weight as tcgen05 k-step slabs (pack_tc_weight)
     const uint4* WgP;   // bf16 mode: gates weight, rows padded to 16
     const uint4* WfP2;  // bf16x3 mode: the same two weights as interleaved (hi, lo) k-step slabs
-    const uint4* WgP2;
+    const uint4* WgP2;  //   gates weight as mma.sync B fragments (pack.pack_gates_frag) ...
+    const uint4* WgP2c; //   ... followed by the same weight as (hi, lo) tcgen05 k-step slabs (the KS edge kernel)
     const float* wsmP;  // tensor-core modes: shared-memory image of Wh, Wu, bf, bg (pack.pack_gvp_small)
     const float* wsmP2;
     int vin, vout, hd, fin, fout, ldf, sigmoid_gate;
@@ -428,7 +429,9 @@ struct kpd_gvp_model {
     std::vector<GvpLayerW> layers;
     GvpW head[MAXG];
     const float* WoT; const float* bo;
-    size_t smem, smem_node, smem_ws1, smem_ws2, smem_ws1n;
+    size_t smem, smem_node, smem_ws1, smem_ws2, smem_ws1n, smem_ks;
+    bool edge_ks;       // bf16x3: the edge kernel keeps (hi, lo) planes of 128-row tiles (WsKS); KPD_GVP_EDGE=stack selects the
+                        // 64-row stacked-operand kernel (WsSplit) instead
     bool edge_pair;     // bf16x3: the edge kernel runs as CTA pairs (message GVP weights pair-packed, pack.pack_gvp_tc)
     int kch;           // k-chunks of the bf16 tile (tensor-core mode)
     int mode;          // 0 = fp32 SIMT, 1 = bf16 tcgen05, 2 = bf16x3 tcgen05 (split operands, fp32-grade)
@@ -506,7 +509,7 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         g.vin = vin; g.vout = vout; g.hd = vin > vout ? vin : vout; g.fin = fin; g.fout = fout;
         g.ldf = (fout + 3) & ~3; g.sigmoid_gate = sig;
         g.Wh = P(); g.Wu = P(); g.WfT = P(); g.bf = P(); g.WgT = P(); g.bg = P();
-        g.WfP = nullptr; g.WgP = nullptr; g.WfP2 = nullptr; g.WgP2 = nullptr; g.wsmP = nullptr; g.wsmP2 = nullptr;
+        g.WfP = nullptr; g.WgP = nullptr; g.WfP2 = nullptr; g.WgP2 = nullptr; g.WgP2c = nullptr; g.wsmP = nullptr; g.wsmP2 = nullptr;
         g.xfirst = vin > vout && sig ? 1 : 0;
         return g;
     };
@@ -556,6 +559,8 @@ extern "C" int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, cons
         m->edge_pair = false;
 #endif
         m->smem_ws1n = ws::smem_bytes<WsBf16N>(m->kch);
+        m->smem_ks = ws::smem_bytes<WsKS>(m->kch);
+        { const char* e = getenv("KPD_GVP_EDGE"); m->edge_ks = !(e && e[0] == 's') && m->smem_ks <= 227 * 1024 && !m->edge_pair; }
         m->mode = 0;
         m->tc_ready = false;
         m->tc2_ready = false;
@@ -619,11 +624,18 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
         const uint4* wg = reinterpret_cast<const uint4*>(base + byte_offsets[3 * i + 1]);
         const float* ws_img = reinterpret_cast<const float*>(base + byte_offsets[3 * i + 2]);
         if (nsplit == 1) { m->all_gvps[i]->WfP = wf; m->all_gvps[i]->WgP = wg; m->all_gvps[i]->wsmP = ws_img; }
-        else { m->all_gvps[i]->WfP2 = wf; m->all_gvps[i]->WgP2 = wg; m->all_gvps[i]->wsmP2 = ws_img; }
+        else {
+            GvpW* gw = m->all_gvps[i];
+            gw->WfP2 = wf; gw->WgP2 = wg; gw->wsmP2 = ws_img;
+            // the (hi, lo) slab image of the gates weight follows its fragment image: both are 2 planes x 512 B per k-step
+            const int ksg = ((gw->fout + 15) & ~15) >> 4;
+            gw->WgP2c = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(wg) + (size_t)ksg * 1024);
+        }
     }
     if (nsplit == 2) {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplitPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess && m->edge_ks) e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ks);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws2);
@@ -762,7 +774,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     const int src_nt[4] = {0, 1, 0, 1}, dst_nt[4] = {0, 0, 1, 1};
     const float* X[2] = {x_lig, x_kp};
     const int norm_mode = m->cfg.norm_mode;
-    const int edge_rows = m->mode == 1 ? WsBf16::R : m->mode == 2 ? WsSplit::R : TE;
+    const int edge_rows = m->mode == 1 ? WsBf16::R : m->mode == 2 ? (m->edge_ks ? WsKS::R : WsSplit::R) : TE;
 
     // Tensor-core modes run the convs as a DEPENDENCY GRAPH instead of a chain of launches: one edge launch per edge
     // type, one node launch per node type, each waiting only for what it reads --
@@ -797,6 +809,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
     };
     auto launch_edge_ws = [&](const GvpEdgeLaunch& L, int tiles, int n_et, cudaStream_t s_) -> int {
         if (m->mode == 1) launch_clustered(gvp_edge_ws_kernel<WsBf16>, dim3(tiles, n_et), WsBf16::NT, m->smem_ws1, s_, WsBf16::CL, L);
+        else if (m->edge_ks) launch_clustered(gvp_edge_ws_kernel<WsKS>, dim3(tiles, n_et), WsKS::NT, m->smem_ks, s_, 1, L);
         else if (m->edge_pair) launch_clustered(gvp_edge_ws_kernel<WsSplitPair>, dim3(tiles, n_et), WsSplitPair::NT, m->smem_ws2, s_, 2, L);
         else launch_clustered(gvp_edge_ws_kernel<WsSplit>, dim3(tiles, n_et), WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, L);
         return check_launch("gvp_edge_ws_kernel");

@@ -65,34 +65,42 @@ struct Sm {
     bool solo;
 };
 
-// bytes of the A operand (all MMA_M rows)
+// bytes of one A operand (all MMA_M rows); KS keeps two of them (hi plane, lo plane)
 template <class C>
 __host__ __device__ inline size_t plane_bytes(int kch) { return ((size_t)kch * C::KCS + 127) & ~(size_t)127; }
+template <class C>
+__host__ __device__ inline size_t planes_bytes(int kch) { return (C::KS ? 2 : 1) * plane_bytes<C>(kch); }
+// per-row staging of the gates between epilogue 1 / the gates GEMM and epilogue 2 (floats per tile row): STACK keeps
+// the per-column-group partial sums of the mma.sync gates, the bf16 mode the finished gates; KS reads its gates from
+// TMEM directly in the vector-fragment layout (no staging)
+template <class C>
+constexpr int GATE_FLOATS = C::KS ? 0 : (C::STACK ? C::NCG * 16 : GATE_LD);
 
 
 // Stages of the weight ring.  The ring is latency-bound (a slab is re-requested when its MMA has completed and lands
 // ~1350 cycles later), so the k-step rate is (MMA completion + copy latency) / stages: as deep as shared memory allows.
 template <class C>
-constexpr int GST = C::NS == 1 ? 10 : 6;
+constexpr int GST = C::NS == 1 ? 10 : C::KS ? 3 : 6;
 
 template <class C>
 static size_t smem_bytes(int kch) {
-    return plane_bytes<C>(kch) + (size_t)GST<C> * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * (C::WSM_W + 2 * C::WSM_B) +
-           sizeof(float) * (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * GST<C> + 12) + 16 + 128;
+    return planes_bytes<C>(kch) + (size_t)GST<C> * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * (C::WSM_W + 2 * C::WSM_B) +
+           sizeof(float) * GATE_FLOATS<C> * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * GST<C> + 12) + 16 + 128;
 }
 
 template <class C>
 __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     Sm m;
     m.A[0] = smem;
-    m.A[1] = smem + (C::NS - 1) * 256;            // lo rows: 2 row groups after their hi rows
-    m.ring = smem + plane_bytes<C>(kch);
+    // lo rows: STACK two row groups after their hi rows (same operand); KS a plane of their own
+    m.A[1] = C::KS ? smem + plane_bytes<C>(kch) : smem + (C::NS - 1) * 256;
+    m.ring = smem + planes_bytes<C>(kch);
     m.Wg[0] = m.ring + GST<C> * C::SLAB;
     m.Wg[1] = m.Wg[0] + C::WG_BYTES;
     m.wsm = reinterpret_cast<float*>(m.Wg[0] + C::WGB * C::WG_BYTES);
     m.bias = m.wsm + C::WSM_W;
     m.gate = m.bias + 2 * C::WSM_B;
-    m.src_s = reinterpret_cast<int*>(m.gate + (C::NS == 2 ? C::NCG * 16 : GATE_LD) * C::R);
+    m.src_s = reinterpret_cast<int*>(m.gate + GATE_FLOATS<C> * C::R);
     m.dst_s = m.src_s + C::R;
     m.seg = m.dst_s + C::R;            // [R + 8]
     m.rp = m.seg + C::R + 8;           // [2R]
@@ -123,8 +131,8 @@ __device__ __forceinline__ void init_barriers(Sm& m) {      // one thread
     // one more arrival: the peer's forwarding threads (relay(), forward_ready()); everything else stays per CTA
     const uint32_t extra = (C::CL == 2 && m.rank == 0 && !m.solo) ? 1u : 0u;
     for (int i = 0; i < GST<C>; ++i) { tc::mbar_init(&m.full[i], (C::CL == 2 && m.rank == 0) ? 2 : 1); tc::mbar_init(&m.empty[i], 1); }
-    // wg_empty: NS = 1 the tcgen05 gates GEMM commits it; NS = 2 every SIMT warp arrives after its mma.sync gates
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], C::NS == 2 ? C::NW : 1); }
+    // wg_empty: NS = 1 the tcgen05 gates GEMM commits it; STACK every SIMT warp arrives after its mma.sync gates
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&m.wg_full[i], 1); tc::mbar_init(&m.wg_empty[i], C::STACK ? C::NW : 1); }
     tc::mbar_init(m.feats_ready, C::NW + extra);
     tc::mbar_init(m.tail_ready, C::NWV + extra);
     tc::mbar_init(m.acc_done, 1);
@@ -146,7 +154,7 @@ __device__ __forceinline__ uint32_t setup(Sm& m, int kch) {
         else { tc::tmem_alloc(m.tmem_slot, TMEM_COLS); tc::tmem_relinquish(); }
     }
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const int nz = (int)(plane_bytes<C>(kch) / 16);
+    const int nz = (int)(planes_bytes<C>(kch) / 16);
     for (int i = tid; i < nz; i += C::NT) reinterpret_cast<uint4*>(m.A[0])[i] = z;
     tc::fence_proxy_async();
     tc::fence_before_sync();
@@ -196,7 +204,7 @@ __device__ __forceinline__ void teardown(uint32_t tmem) {
 // j = first halves of all column groups, then second halves, then the |Vh| tail.  Otherwise j = i.
 template <class C>
 __device__ __forceinline__ int kstep_at(int i, int ksm, bool chained) {
-    if (C::NS != 2 || !chained || i >= ksm) return i;
+    if (!C::STACK || !chained || i >= ksm) return i;
     constexpr int kpg = (256 / C::NCG) / 16, kph = kpg / 2;      // k-steps per column group / per half
     int n0 = (ksm / kpg) * kph + min(ksm % kpg, kph);            // k-steps that lie in first halves
     const bool second = i >= n0;
@@ -222,7 +230,7 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
         const GvpW& w = gv[g];
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksg = NBf >> 4;
         const uint32_t slab = C::NS * 2 * (NBf / 8) * 128;
-        const int b = g % C::WGB;
+        [[maybe_unused]] const int b = g % (C::WGB > 0 ? C::WGB : 1);
         const uint4* WfP = C::NS == 2 ? w.WfP2 : w.WfP;
         if (!dead) {
             // shared-memory image of this GVP's small fp32 weights: Wh | Wu into the single buffer once the vector warps
@@ -254,7 +262,14 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
 #endif
         }
         // the gates weight is needed only after this GVP's feats GEMM: queue it behind the slabs
-        if (!dead) {
+        if constexpr (C::KS) {
+            // KS: no buffer of its own -- the whole gates weight (hi | lo k-step slabs, <= 16 KB) is one more ring slot
+            const uint32_t st = it % GST<C>;
+            if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
+            tc::mbar_arrive_expect_tx(&m.full[st], (uint32_t)(2 * ksg * 512));
+            tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, w.WgP2c, (uint32_t)(2 * ksg * 512), &m.full[st]);
+            ++it;
+        } else if (!dead) {
             if (g >= C::WGB) tc::mbar_wait(&m.wg_empty[b], ((g / C::WGB) - 1) & 1);   // gates MMA g-WGB has consumed the buffer
             tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
             tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
@@ -294,8 +309,8 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 2 * C::MMA_M : C::MMA_M, NBf);
         const uint32_t b_k = PAIR ? (NBf / 16) * 128 : (NBf / 8) * 128, slab1 = 2 * b_k;    // (pair: N / 2 rows per CTA)
         // bf16x3: two accumulators, so that the next GVP's k-steps can start while epilogue 1 still reads this one
-        const uint32_t acc = tmem + ((C::NS == 2 && (g & 1)) ? 256u : 0u);
-        const bool chained = C::NS == 2 && g > 0;
+        const uint32_t acc = tmem + ((C::STACK && (g & 1)) ? 256u : 0u);
+        const bool chained = C::STACK && g > 0;
         const int n_first = first_half_ksteps<C>(ksm);
         if (chained) { wait_ready<C>(m.half_ready, (g - 1) & 1); tc::fence_after_sync(); }
         for (int i = 0; i < ksf; ++i, ++it) {
@@ -321,10 +336,16 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
             if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
             else tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
-            if (C::NS == 2) {       // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
+            if (C::STACK) {         // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
                 const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
                 if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b1, idesc, 1u);
                 else tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
+            }
+            if constexpr (C::KS) {  // + A_lo x W_hi + A_hi x W_lo into the same accumulator
+                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
+                tc::mma_bf16_ss(acc, a1, b0, idesc, 1u);
+                tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
             }
             if (PAIR) tc::mma_commit_pair(&m.empty[st], 3);       // frees the slot in both CTAs
             else tc::mma_commit(&m.empty[st]);
@@ -332,8 +353,8 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         if (PAIR) tc::mma_commit_pair(m.acc_done, 3);
         else tc::mma_commit(m.acc_done);
         WS_TRACE(4);
-        if constexpr (C::NS == 2) {
-            // bf16x3: the gates GEMM runs on the warp-level tensor cores straight from the epilogue registers
+        if constexpr (C::STACK) {
+            // stacked bf16x3: the gates GEMM runs on the warp-level tensor cores straight from the epilogue registers
             // (gates_mma); the next GVP's k-steps wait for epilogue 1 half by half (above)
             continue;
         }
@@ -341,13 +362,17 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         // k-steps over the first halves run on the tensor core while the second halves are still being produced
         constexpr int cpw = 256 / C::NCG, hb = cpw / 2;
         const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
-        const uint32_t wg = tc::smem_u32(m.Wg[0] + (g % C::WGB) * C::WG_BYTES);
+        // KS: the gates weight sits in the next ring slot (produce()); otherwise in its own buffer
+        const uint32_t gst = it % GST<C>;
+        const uint32_t wg = C::KS ? tc::smem_u32(m.ring + (size_t)gst * C::SLAB)
+                                  : tc::smem_u32(m.Wg[0] + (g % (C::WGB > 0 ? C::WGB : 1)) * C::WG_BYTES);
         uint32_t gacc = 0u;
         for (int half = 0; half < 2; ++half) {
             if (half == 0) {
                 tc::mbar_wait(m.half_ready, g & 1);
                 tc::fence_after_sync();
-                tc::mbar_wait(&m.wg_full[g % C::WGB], (g / C::WGB) & 1);
+                if constexpr (C::KS) tc::mbar_wait(&m.full[gst], (it / GST<C>) & 1);
+                else tc::mbar_wait(&m.wg_full[g % (C::WGB > 0 ? C::WGB : 1)], (g / (C::WGB > 0 ? C::WGB : 1)) & 1);
             } else {
                 // epilogue 1 of this GVP done: feats_out is in A, the accumulator columns are free again
                 tc::mbar_wait(m.feats_ready, (g + 1) & 1);
@@ -360,14 +385,17 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
                 const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
                 tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, gacc);
                 gacc = 1u;
-                if (C::NS == 2) {       // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                if constexpr (C::KS) {  // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                    const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
                     const uint64_t b1 = tc::make_smem_desc(wg + j * 1024 + 512, 256, 128);
+                    tc::mma_bf16_ss(tmem + GATE_COL, a1, b0, idg, 1u);
                     tc::mma_bf16_ss(tmem + GATE_COL, a0, b1, idg, 1u);
                 }
             }
         }
         tc::mma_commit(m.gates_done);
-        tc::mma_commit(&m.wg_empty[g % C::WGB]);
+        if constexpr (C::KS) { tc::mma_commit(&m.empty[gst]); ++it; }
+        else tc::mma_commit(&m.wg_empty[g % (C::WGB > 0 ? C::WGB : 1)]);
         WS_TRACE(6);
     }
 #ifdef KPD_WS_TRACE
@@ -478,7 +506,9 @@ template <class C>
 __device__ __forceinline__ Lane lane_geometry() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Lane L;
-    L.row = 8 * warp + (lane >> 2);
+    // KS: warp w owns the 8 rows [32 (w % 4) + 8 (w / 4), + 8) -- inside the TMEM lane quarter the warp may read, so that
+    // epilogue 2 can take its gates straight from TMEM in this fragment layout (gates_from_tmem)
+    L.row = C::KS ? 32 * (warp & 3) + 8 * (warp >> 2) + (lane >> 2) : 8 * warp + (lane >> 2);
     L.t = lane & 3;
     L.rowoff = row_off<C>(L.row);
     return L;
@@ -704,7 +734,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const int q = warp & 3, cg = warp >> 2;
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
     const bool valid_e = C::R == 128 ? true : lane < 16;
-    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + ((C::NS == 2 && (gi & 1)) ? 256u : 0u);
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + ((C::STACK && (gi & 1)) ? 256u : 0u);
     TC_T(t2);
     WS_TRACE(12);
     tc::mbar_wait(m.acc_done, gi & 1);
@@ -716,10 +746,10 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         const int row0 = C::R == 128 ? 32 * q : 16 * q;
         [[maybe_unused]] uint32_t fr8[4][8];
         [[maybe_unused]] uint32_t fr4[4][4];
-        if constexpr (C::NS == 2) {                          // the gates weight fragments of this GVP have landed
+        if constexpr (C::STACK) {                            // the gates weight fragments of this GVP have landed
             tc::mbar_wait(&m.wg_full[gi % C::WGB], (gi / C::WGB) & 1);
         }
-        const uint32_t* wgf = reinterpret_cast<const uint32_t*>(m.Wg[0] + (gi % C::WGB) * C::WG_BYTES);
+        [[maybe_unused]] const uint32_t* wgf = reinterpret_cast<const uint32_t*>(m.Wg[0] + (gi % (C::WGB > 0 ? C::WGB : 1)) * C::WG_BYTES);
         const int wg_lo = ((NBf >> 4) * 512) / 4;            // words between the hi and the lo fragment image
         const int cend = row0 < rows_valid ? min(NBf, cg * cpw + cpw) : 0;   // warps of empty row quarters skip
 #pragma unroll
@@ -765,7 +795,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
             if (half == 0) publish_mma<C>(m, m.half_ready);
         }
     }
-    if constexpr (C::NS == 2) {
+    if constexpr (C::STACK) {
         // partial gates of this warp (its 16 rows x its feats_out columns) -> shared memory; the buffer of the gates
         // weight is free again
         const int ra = 16 * q + (lane >> 2);
@@ -783,7 +813,37 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     TC_T(t4);
     WS_TRACE(14);
     // d. epilogue 2: vectors_out = act(gating) * Vu   (gvp.py:105-111)
-    if constexpr (C::NS == 2) {
+    if constexpr (C::KS) {
+        // the gates accumulator (TMEM columns GATE_COL .. GATE_COL + 16) read with the 16x256b shape: lane (g, t) gets
+        // rows g and g + 8 of a 16-lane window, columns 8 j + 2 t + e -- exactly the channels its vector fragment holds;
+        // no staging through shared memory, no SIMT-wide barrier
+        tc::mbar_wait(m.gates_done, gi & 1);
+        tc::fence_after_sync();
+        TC_T(t5);
+        {
+            const int sub = warp >> 2;                       // which 8 rows of the warp's TMEM lane quarter
+            uint32_t gv[8];
+            tc::tmem_ld_16x256b_x2(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + GATE_COL, gv);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int u = 8 * j + 2 * L.t;
+                float a0 = __uint_as_float((sub & 1) ? gv[4 * j + 2] : gv[4 * j + 0]) + bg_s[u];
+                float a1 = __uint_as_float((sub & 1) ? gv[4 * j + 3] : gv[4 * j + 1]) + bg_s[u + 1];
+                if (g.sigmoid_gate) { a0 = sigmoid_acc(a0); a1 = sigmoid_acc(a1); }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * a0; v.x[c][j][1] = vu[c][j][1] * a1; }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v.x[c][2][0] = v.x[c][2][1] = 0.f;
+        }
+        tc::fence_before_sync();            // the next gates GEMM overwrites these TMEM columns (ordered through half_ready)
+        TC_T(t6);
+        WS_ACC(tb + 0, t0, t1); WS_ACC(tb + 1, t1, t2); WS_ACC(tb + 2, t2, t3); WS_ACC(tb + 3, t3, t4); WS_ACC(tb + 4, t4, t5);
+        WS_ACC(tb + 5, t5, t6); WS_ACC(tb + 6, 0, 1);
+        return;
+    }
+    if constexpr (C::STACK) {
         TC_T(t5);
         simt_bar<C>();
         if (vecw) {
@@ -822,7 +882,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         for (int i = 0; i < CG; ++i) {
             const int u = cg * CG + i;
             float a = __uint_as_float(gv[i]);
-            if (C::NS == 2) a += __shfl_xor_sync(0xffffffffu, a, 16);     // hi rows (lanes 0-15) + lo rows (lanes 16-31)
+            if (C::STACK) a += __shfl_xor_sync(0xffffffffu, a, 16);     // hi rows (lanes 0-15) + lo rows (lanes 16-31)
             a += bg_s[u];
             if (g.sigmoid_gate) a = act_sigmoid<C::NS>(a);
             if (valid_e) m.gate[row_e * GATE_LD + u] = a;
@@ -887,6 +947,9 @@ using WsSplit = ws::Cfg<64, 2, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;
 // bf16x3 edge kernel as CTA pairs (cta_group::2): two neighbouring 64-row tiles share every weight slab, each SM
 // holding (and reading) half of it
 using WsSplitPair = ws::Cfg<64, 2, 2, KPD_WS_SPLIT_XWARPS>;
+// bf16x3 edge kernel, default: (hi, lo) PLANES of a 128-row tile, three MMAs per k-step into one accumulator
+// (ws_common.cuh: Cfg::KS); all 16 SIMT warps own vector rows
+using WsKS = ws::Cfg<128, 2, 1, 0, true>;
 using WsBf16N = ws::Cfg<64, 1, KPD_WS_CLUSTER, KPD_WS_SPLIT_XWARPS>;    // bf16 operands, 64-row MMA tiles (M = 64): node / head kernels
 
 // ------------------------------------------------------------------ edge kernel
@@ -968,7 +1031,10 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         if (ASYNC) {        // only the k-chunks behind the gathered scalars need zeros (rbf / |Vh| columns and K padding)
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             const int c0 = Sd >> 3, per = C::KCS / 16;
-            for (int i = tid; i < (L.kch - c0) * per; i += C::NT_SIMT) reinterpret_cast<uint4*>(m.A[0] + (size_t)c0 * C::KCS)[i] = z;
+            for (int i = tid; i < (L.kch - c0) * per; i += C::NT_SIMT) {
+                reinterpret_cast<uint4*>(m.A[0] + (size_t)c0 * C::KCS)[i] = z;
+                if (C::KS) reinterpret_cast<uint4*>(m.A[1] + (size_t)c0 * C::KCS)[i] = z;
+            }
         }
         ws::build_segments<C>(m, n);             // (its barriers also order the zero fill before the rbf stores)
         if (vecw) {
@@ -1005,6 +1071,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             // (bank-conflict free thanks to the +16 B chunk stride), 32-byte coalesced stores
             if (lane < (Sd >> 3)) {
                 const unsigned char* p0 = m.A[0] + (size_t)lane * C::KCS;
+                [[maybe_unused]] const unsigned char* p1 = m.A[1] + (size_t)lane * C::KCS;
                 for (int sg = warp; sg < nseg; sg += C::NW) {
                     const int ra = m.seg[sg], rb = m.seg[sg + 1];
                     float acc[8];
@@ -1017,7 +1084,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
                                       __uint_as_float(wh.y & 0xffff0000u), __uint_as_float(wh.z << 16), __uint_as_float(wh.z & 0xffff0000u),
                                       __uint_as_float(wh.w << 16), __uint_as_float(wh.w & 0xffff0000u)};
                         if (C::NS == 2) {
-                            const uint4 wl = *reinterpret_cast<const uint4*>(p0 + ro + 256);
+                            const uint4 wl = *reinterpret_cast<const uint4*>(p1 + ro);
                             x[0] += __uint_as_float(wl.x << 16); x[1] += __uint_as_float(wl.x & 0xffff0000u);
                             x[2] += __uint_as_float(wl.y << 16); x[3] += __uint_as_float(wl.y & 0xffff0000u);
                             x[4] += __uint_as_float(wl.z << 16); x[5] += __uint_as_float(wl.z & 0xffff0000u);

@@ -23,34 +23,43 @@ constexpr int WH_LD = 36, WU_LD = 20;
 constexpr int WH_SZ = 12 * WH_LD * 2, WU_SZ = 12 * WU_LD * 2;
 template <int NS> constexpr int wsm_floats() { return NS * (WH_SZ + WU_SZ) + 256 + 16; }   // (hi[, lo]) Wh | Wu | bf | bg
 
-template <int R_, int NS_, int CL_, int NWX_ = 0>
+// NS = 2 ("bf16x3", split (hi, lo) bf16 operands) comes in two layouts:
+//   STACK (KS_ = false): the hi and lo rows of 64 tile rows stacked along M into one 128-row A operand; two MMAs per
+//         k-step ([A_hi; A_lo] x W_hi, x W_lo) give all FOUR hi/lo products, the epilogue adds the two accumulator rows;
+//   KS    (KS_ = true):  hi and lo PLANES of a 128-row tile, three MMAs per k-step (A_hi W_hi + A_lo W_hi + A_hi W_lo:
+//         the lo x lo product is below the fp32 rounding of the sum) into ONE accumulator -- a weight slab streamed
+//         from L2 serves 128 tile rows instead of 64 (the slab stream is what bounds the k-step rate),
+//         3 instead of 4 tensor-core MACs per algorithmic MAC, half the TMEM read traffic per tile row.
+template <int R_, int NS_, int CL_, int NWX_ = 0, bool KS_ = false>
 struct Cfg {
     static constexpr int R = R_, NS = NS_;
+    static constexpr bool KS = KS_ && NS_ == 2;
+    static constexpr bool STACK = NS_ == 2 && !KS_;
     static constexpr int CL = CL_;                   // CTAs per cluster: neighbouring tiles share ONE weight stream (multicast)
     static constexpr int NWV = R / 8;                // vector-owning SIMT warps: 8 tile rows each (mma.sync fragments)
     static constexpr int NW = NWV + NWX_;            // all SIMT warps; the NWX extra ones only help with the epilogues,
                                                      // gathers and reductions (more warps in flight per SM quadrant)
     static constexpr int NT_SIMT = 32 * NW;
     static constexpr int NT = NT_SIMT + 64;
-    static constexpr int MMA_M = R * NS;             // NS = 2 stacks the hi and lo rows of a tile into ONE 128-row A operand
+    static constexpr int MMA_M = STACK ? 2 * R : R;  // STACK: the hi and lo rows of a tile form ONE 128-row A operand
     static constexpr int KCS = (MMA_M / 8) * 128 + 16;   // bytes between k-chunks of A (+16: bank rotation for column walks)
     static constexpr int STAGES = NS == 1 ? 8 : 4;
     static constexpr int SLAB = NS * 8192;           // one ring stage: one k-step of a 256-row weight (hi [, lo])
     static constexpr int WG_BYTES = NS * 8192;       // gates weight: 16 k-steps x 512 B (hi [, lo])
-    static constexpr int WGB = NS == 1 ? 2 : 1;      // gates weight buffers
+    static constexpr int WGB = KS ? 0 : NS == 1 ? 2 : 1;   // gates weight buffers (KS: the gates weight travels through the ring)
     static constexpr int WSM = wsm_floats<NS>();
     static constexpr int WSM_W = NS * (WH_SZ + WU_SZ);   // its Wh | Wu part (dead after the Vu GEMM) ...
     static constexpr int WSM_B = 256 + 16;               // ... and its bias part bf | bg (live until epilogue 2)
     static constexpr int NCG = NW / 4;               // column groups of the epilogues (4 TMEM lane quarters x NCG)
 };
 
-// Byte offset of tile row r inside a k-chunk of A.  NS = 1: plain canonical rows.  NS = 2: MMA rows are ordered
+// Byte offset of tile row r inside a k-chunk of A.  NS = 1 and KS: plain canonical rows.  STACK: MMA rows are ordered
 // (16-row group q, plane, row % 16): TMEM lanes [32q, 32q+16) hold the hi rows and [32q+16, 32q+32) the lo rows of
 // tile rows [16q, 16q+16), so one warp reads both halves of a row's accumulator (16x256b loads) and adds them.
 // The lo row of r sits 256 bytes after its hi row.
 template <class C>
 __device__ __forceinline__ uint32_t row_off(int r) {
-    if (C::NS == 2) return (uint32_t)((4 * (r >> 4) + ((r >> 3) & 1)) * 128 + (r & 7) * 16);
+    if (C::STACK) return (uint32_t)((4 * (r >> 4) + ((r >> 3) & 1)) * 128 + (r & 7) * 16);
     return (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
 }
 

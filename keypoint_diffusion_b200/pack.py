@@ -313,7 +313,8 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
         # gates weight: tcgen05 slabs in the bf16 mode; mma.sync B fragments in the bf16x3 mode (the gates GEMM then
         # runs on the warp-level tensor cores straight from the epilogue registers)
         wg = sd[name + ".scalar_to_vector_gates.weight"]
-        add(pack_gates_frag(wg) if split else pack_tc_weight(wg, False))
+        # (split: followed by the (hi, lo) tcgen05 slabs of the same weight, which the KS edge kernel streams through its ring)
+        add(torch.cat([pack_gates_frag(wg), pack_tc_weight(wg, True)]) if split else pack_tc_weight(wg, False))
         # message GVP 0 of every edge type takes the unit x_diff as its first input vector channel
         xfirst = ".edge_message_fns." in name and name.endswith(".0")
         img = pack_gvp_small(sd[name + ".Wh"], sd[name + ".Wu"], sd[name + ".to_feats_out.0.bias"],
