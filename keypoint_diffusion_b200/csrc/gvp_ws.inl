@@ -43,6 +43,8 @@ __device__ int g_ws_trace_n;
 
 namespace ws {
 
+constexpr int WH_LD_KS = 28, WU_LD_KS = 20;          // fp32 [24][LD] images of Wh / Wu for vec_fma
+constexpr int WSM_KS_W = 24 * WH_LD_KS + 24 * WU_LD_KS;     // (== Cfg::WSM_W of the KS configuration)
 constexpr int VS_LD = 52;                                   // fp32 vector staging row (48 used)
 constexpr int GATE_LD = 20;                                 // gates staged as [R][20]
 constexpr uint32_t TMEM_COLS = 512;
@@ -80,11 +82,16 @@ constexpr int GATE_FLOATS = C::KS ? 0 : (C::STACK ? C::NCG * 16 : GATE_LD);
 // Stages of the weight ring.  The ring is latency-bound (a slab is re-requested when its MMA has completed and lands
 // ~1350 cycles later), so the k-step rate is (MMA completion + copy latency) / stages: as deep as shared memory allows.
 template <class C>
-constexpr int GST = C::NS == 1 ? 10 : C::KS ? 3 : 6;
+constexpr int GST = C::NS == 1 ? 10 : C::KS ? 4 : 6;
+// bytes of a ring slot: one k-step of a 256-row weight (hi [, lo]).  (KS with 8 KB slots -- the hi and the lo slab of a
+// k-step as separate copies, 6-7 slots -- was measured SLOWER, ~1000 instead of ~600 cycles per k-step: the cost of a
+// bulk copy is dominated by a per-copy term, not by its bytes.)
+template <class C>
+constexpr int SLOT = C::SLAB;
 
 template <class C>
 static size_t smem_bytes(int kch) {
-    return planes_bytes<C>(kch) + (size_t)GST<C> * C::SLAB + C::WGB * C::WG_BYTES + sizeof(float) * (C::WSM_W + 2 * C::WSM_B) +
+    return planes_bytes<C>(kch) + (size_t)GST<C> * SLOT<C> + C::WGB * C::WG_BYTES + sizeof(float) * (C::WSM_W + 2 * C::WSM_B) +
            sizeof(float) * GATE_FLOATS<C> * C::R + sizeof(int) * (5 * C::R + 8 + 8) + sizeof(uint64_t) * (2 * GST<C> + 12) + 16 + 128;
 }
 
@@ -95,7 +102,7 @@ __device__ __forceinline__ Sm carve(unsigned char* smem, int kch) {
     // lo rows: STACK two row groups after their hi rows (same operand); KS a plane of their own
     m.A[1] = C::KS ? smem + plane_bytes<C>(kch) : smem + (C::NS - 1) * 256;
     m.ring = smem + planes_bytes<C>(kch);
-    m.Wg[0] = m.ring + GST<C> * C::SLAB;
+    m.Wg[0] = m.ring + GST<C> * SLOT<C>;
     m.Wg[1] = m.Wg[0] + C::WG_BYTES;
     m.wsm = reinterpret_cast<float*>(m.Wg[0] + C::WGB * C::WG_BYTES);
     m.bias = m.wsm + C::WSM_W;
@@ -204,7 +211,7 @@ __device__ __forceinline__ void teardown(uint32_t tmem) {
 // j = first halves of all column groups, then second halves, then the |Vh| tail.  Otherwise j = i.
 template <class C>
 __device__ __forceinline__ int kstep_at(int i, int ksm, bool chained) {
-    if (!C::STACK || !chained || i >= ksm) return i;
+    if (!(C::STACK || C::KS) || !chained || i >= ksm) return i;
     constexpr int kpg = (256 / C::NCG) / 16, kph = kpg / 2;      // k-steps per column group / per half
     int n0 = (ksm / kpg) * kph + min(ksm % kpg, kph);            // k-steps that lie in first halves
     const bool second = i >= n0;
@@ -247,14 +254,14 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
             if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
             if (C::CL == 1) {
                 tc::mbar_arrive_expect_tx(&m.full[st], slab);
-                tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
+                tc::bulk_g2s(m.ring + (size_t)st * SLOT<C>, WfP + (size_t)j * (slab / 16), slab, &m.full[st]);
             } else {
                 // CTA pair: this CTA holds rows [rank * N/2, (rank + 1) * N/2) of the weight; pack.pack_tc_weight_pair
                 // stores the slab as [half][hi, lo][2 k-chunks][N/16 row groups x 128 B]: one contiguous copy per CTA
                 // (four 2 KB pieces of the single-CTA packing instead were 2.5x slower: measured)
                 const uint32_t half = C::NS * 2 * (NBf / 16) * 128;
                 tc::mbar_arrive_expect_tx(&m.full[st], half);
-                tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, reinterpret_cast<const unsigned char*>(WfP) + (size_t)j * slab + m.rank * half,
+                tc::bulk_g2s(m.ring + (size_t)st * SLOT<C>, reinterpret_cast<const unsigned char*>(WfP) + (size_t)j * slab + m.rank * half,
                              half, &m.full[st]);
             }
 #ifdef KPD_WS_TRACE
@@ -262,14 +269,7 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
 #endif
         }
         // the gates weight is needed only after this GVP's feats GEMM: queue it behind the slabs
-        if constexpr (C::KS) {
-            // KS: no buffer of its own -- the whole gates weight (hi | lo k-step slabs, <= 16 KB) is one more ring slot
-            const uint32_t st = it % GST<C>;
-            if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
-            tc::mbar_arrive_expect_tx(&m.full[st], (uint32_t)(2 * ksg * 512));
-            tc::bulk_g2s(m.ring + (size_t)st * C::SLAB, w.WgP2c, (uint32_t)(2 * ksg * 512), &m.full[st]);
-            ++it;
-        } else if (!dead) {
+        if (!dead) {
             if (g >= C::WGB) tc::mbar_wait(&m.wg_empty[b], ((g / C::WGB) - 1) & 1);   // gates MMA g-WGB has consumed the buffer
             tc::mbar_arrive_expect_tx(&m.wg_full[b], C::NS * ksg * 512);
             tc::bulk_g2s(m.Wg[0] + b * C::WG_BYTES, C::NS == 2 ? w.WgP2 : w.WgP, C::NS * ksg * 512, &m.wg_full[b]);
@@ -331,7 +331,7 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
 #ifdef KPD_WS_TRACE
             if (it < 64) tk[it] = clock64();
 #endif
-            const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
+            const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
             if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
@@ -340,12 +340,6 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
                 const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
                 if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b1, idesc, 1u);
                 else tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
-            }
-            if constexpr (C::KS) {  // + A_lo x W_hi + A_hi x W_lo into the same accumulator
-                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
-                const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
-                tc::mma_bf16_ss(acc, a1, b0, idesc, 1u);
-                tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
             }
             if (PAIR) tc::mma_commit_pair(&m.empty[st], 3);       // frees the slot in both CTAs
             else tc::mma_commit(&m.empty[st]);
@@ -362,17 +356,13 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         // k-steps over the first halves run on the tensor core while the second halves are still being produced
         constexpr int cpw = 256 / C::NCG, hb = cpw / 2;
         const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
-        // KS: the gates weight sits in the next ring slot (produce()); otherwise in its own buffer
-        const uint32_t gst = it % GST<C>;
-        const uint32_t wg = C::KS ? tc::smem_u32(m.ring + (size_t)gst * C::SLAB)
-                                  : tc::smem_u32(m.Wg[0] + (g % (C::WGB > 0 ? C::WGB : 1)) * C::WG_BYTES);
+        const uint32_t wg = tc::smem_u32(m.Wg[0] + (g % (C::WGB > 0 ? C::WGB : 1)) * C::WG_BYTES);
         uint32_t gacc = 0u;
         for (int half = 0; half < 2; ++half) {
             if (half == 0) {
                 tc::mbar_wait(m.half_ready, g & 1);
                 tc::fence_after_sync();
-                if constexpr (C::KS) tc::mbar_wait(&m.full[gst], (it / GST<C>) & 1);
-                else tc::mbar_wait(&m.wg_full[g % (C::WGB > 0 ? C::WGB : 1)], (g / (C::WGB > 0 ? C::WGB : 1)) & 1);
+                tc::mbar_wait(&m.wg_full[g % (C::WGB > 0 ? C::WGB : 1)], (g / (C::WGB > 0 ? C::WGB : 1)) & 1);
             } else {
                 // epilogue 1 of this GVP done: feats_out is in A, the accumulator columns are free again
                 tc::mbar_wait(m.feats_ready, (g + 1) & 1);
@@ -385,17 +375,10 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
                 const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
                 tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, gacc);
                 gacc = 1u;
-                if constexpr (C::KS) {  // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
-                    const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
-                    const uint64_t b1 = tc::make_smem_desc(wg + j * 1024 + 512, 256, 128);
-                    tc::mma_bf16_ss(tmem + GATE_COL, a1, b0, idg, 1u);
-                    tc::mma_bf16_ss(tmem + GATE_COL, a0, b1, idg, 1u);
-                }
             }
         }
         tc::mma_commit(m.gates_done);
-        if constexpr (C::KS) { tc::mma_commit(&m.empty[gst]); ++it; }
-        else tc::mma_commit(&m.wg_empty[g % (C::WGB > 0 ? C::WGB : 1)]);
+        tc::mma_commit(&m.wg_empty[g % (C::WGB > 0 ? C::WGB : 1)]);
         WS_TRACE(6);
     }
 #ifdef KPD_WS_TRACE
@@ -406,6 +389,179 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
         }
     }
 #endif
+}
+
+
+// ------------------------------------------------------------------ KS (hi / lo planes, 128-row tiles): producer + issuer
+// Ring order == consumption order (one FIFO of 8 KB slots):
+//   GVP 0:      [W_hi, W_lo] per k-step
+//   GVP g > 0:  gates weight of GVP g-1 | [W_hi | W_lo] of the k-steps over the FIRST halves of the column groups | the
+//               remaining k-steps (second halves, |Vh| tail)
+//   at the end: the last GVP's gates weight
+// (epilogue 1 rewrites A in two halves per column group; the k-steps that only need first halves are issued behind
+//  half_ready while the second halves are still being produced, into the OTHER accumulator.)
+// The gates weight image is packed with its first-half k-steps first (pack.pack_gates_ks); a gates accumulator lives
+// in columns [0, 16) of the accumulator its GVP has just drained.
+// KPD_KS_CHAIN=1: the next GVP's k-steps over the first halves of the column groups start behind half_ready (into the
+// other accumulator), the whole gates GEMM runs when epilogue 1 completes.  Measured SLOWER than the plain order below
+// (21.4k vs 16-19k cycles per GVP): the tensor pipe executes in issue order, so the gates GEMM -- which the SIMT warps
+// wait for -- queues behind the early k-steps, and the main GEMM is bound by the rate of the weight ring either way.
+#ifndef KPD_KS_CHAIN
+#define KPD_KS_CHAIN 0
+#endif
+template <class C>
+__device__ __forceinline__ bool gates_first_half(int j) { return ((16 * j) % (256 / C::NCG)) < (256 / C::NCG) / 2; }
+
+template <class C>
+__device__ __forceinline__ void produce_ks(const GvpW* gv, int n_gvps, Sm& m) {
+    uint32_t it = 0;
+    auto push = [&](const void* src, uint32_t bytes) {
+        const uint32_t st = it % GST<C>;
+        if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
+        tc::mbar_arrive_expect_tx(&m.full[st], bytes);
+        tc::bulk_g2s(m.ring + (size_t)st * SLOT<C>, src, bytes, &m.full[st]);
+        ++it;
+    };
+    auto gates_bytes = [&](const GvpW& w, int half) {      // k-steps of that half x (hi 512 B | lo 512 B)
+        const int ksg = ((w.fout + 15) & ~15) >> 4;
+        int n0 = 0;
+        for (int j = 0; j < ksg; ++j) n0 += gates_first_half<C>(j) ? 1 : 0;
+        return (uint32_t)((half == 0 ? n0 : ksg - n0) * 1024);
+    };
+    for (int g = 0; g <= n_gvps; ++g) {
+        if (g < n_gvps) {
+            // shared-memory image of this GVP's small fp32 weights (see produce())
+            const GvpW& w = gv[g];
+            if (g > 0) tc::mbar_wait(m.wsm_empty, (g - 1) & 1);
+            // (the plain fp32 image for vec_fma follows the fragment image of the other kernels: pack.pack_gvp_small_ks)
+            const float* img = w.wsmP2 + C::WSM;
+            tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)((WSM_KS_W + C::WSM_B) * sizeof(float)));
+            tc::bulk_g2s(m.wsm, img, WSM_KS_W * sizeof(float), m.wsm_full);
+            tc::bulk_g2s(m.bias + (g & 1) * C::WSM_B, img + WSM_KS_W, C::WSM_B * sizeof(float), m.wsm_full);
+        }
+        const int ksf = g < n_gvps ? (gv[g].fin + gv[g].hd + 15) >> 4 : 0;
+        const int ksm = g < n_gvps ? gv[g].fin >> 4 : 0;
+        const uint32_t plane = g < n_gvps ? (uint32_t)(2 * (((gv[g].fout + 15) & ~15) / 8) * 128) : 0u;   // bytes of one plane of a k-step
+        // the whole gates weight of GVP g-1 (<= 16 KB) is one ring slot AHEAD of this GVP's k-steps: the issuer holds it
+        // until epilogue 1 of GVP g-1 completes and runs the gates GEMM at once then, before the queued k-steps
+        if (g > 0) push(gv[g - 1].WgP2c, gates_bytes(gv[g - 1], 0) + gates_bytes(gv[g - 1], 1));
+        for (int i = 0; i < ksf; ++i) {
+            const int j = kstep_at<C>(i, ksm, KPD_KS_CHAIN && g > 0);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(gv[g].WfP2) + (size_t)j * 2 * plane;
+            push(src, 2 * plane);
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint32_t tmem) {
+    uint32_t it = 0;
+    auto take = [&]() -> uint32_t {             // next ring slot, once its copy has landed
+        const uint32_t st = it % GST<C>;
+        tc::mbar_wait(&m.full[st], (it / GST<C>) & 1);
+        tc::fence_after_sync();
+        return st;
+    };
+    auto release = [&](uint32_t st) { tc::mma_commit(&m.empty[st]); ++it; };
+    (void)release;
+    // gates GEMM of GVP gp over the slot `st` that holds its weight: feats_out (hi, lo planes) x Wg (hi, lo) into columns
+    // [0, 16) of the accumulator GVP gp has drained.  The weight image lists the k-steps over the first halves of the
+    // column groups first (pack.pack_gates_ks).
+    auto gates = [&](int gp, uint32_t st, int which) {          // which: 0 / 1 = the k-steps of that half only, 2 = all
+        const GvpW& w = gv[gp];
+        const int ksg = ((w.fout + 15) & ~15) >> 4;
+        const uint32_t wg = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
+        const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
+        const uint32_t gcol = tmem + ((gp & 1) ? 256u : 0u);
+        int k = 0;
+        for (int half = 0; half < 2; ++half)
+            for (int j = 0; j < ksg; ++j) {
+                if (gates_first_half<C>(j) != (half == 0)) continue;
+                if (which != 2 && which != half) { ++k; continue; }
+                const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                const uint64_t b0 = tc::make_smem_desc(wg + k * 1024, 256, 128);
+                const uint64_t b1 = tc::make_smem_desc(wg + k * 1024 + 512, 256, 128);
+                tc::mma_bf16_ss(gcol, a0, b0, idg, k == 0 ? 0u : 1u);
+                tc::mma_bf16_ss(gcol, a1, b0, idg, 1u);
+                tc::mma_bf16_ss(gcol, a0, b1, idg, 1u);     // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                ++k;
+            }
+        if (which == 0) return;
+        tc::mma_commit(m.gates_done);
+        tc::mma_commit(&m.empty[st]);
+    };
+    tc::mbar_wait(m.feats_ready, 0);
+    tc::fence_after_sync();
+    for (int g = 0; g < n_gvps; ++g) {
+        const GvpW& w = gv[g];
+        const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksm = w.fin >> 4;
+        const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NBf);
+        const uint32_t b_k = (NBf / 8) * 128;
+        const uint32_t acc = tmem + ((g & 1) ? 256u : 0u);
+        const bool chained = KPD_KS_CHAIN && g > 0;
+        const int n_first = chained ? first_half_ksteps<C>(ksm) : 0;
+        uint32_t gst = 0;
+        if (!KPD_KS_CHAIN && g > 0) {
+            // plain order: the gates GEMM of GVP g-1 progressively behind the two halves of its epilogue 1, then this GVP
+            gst = take();
+            ++it;
+            tc::mbar_wait(m.half_ready, (g - 1) & 1);
+            tc::fence_after_sync();
+            gates(g - 1, gst, 0);
+            tc::mbar_wait(m.feats_ready, g & 1);
+            tc::fence_after_sync();
+            gates(g - 1, gst, 1);
+        }
+        if (chained) {
+            gst = take();                       // the gates weight of GVP g-1: held until its epilogue 1 completes
+            ++it;
+            // first halves of epilogue 1 of GVP g-1 are in A, and out of its accumulator
+            tc::mbar_wait(m.half_ready, (g - 1) & 1);
+            tc::fence_after_sync();
+        }
+        bool g1 = !chained;                     // the previous GVP's gates GEMM issued
+        for (int i = 0; i < ksf; ++i) {
+            const int j = kstep_at<C>(i, ksm, chained);
+            // epilogue 1 of GVP g-1 done (all of its feats_out is in A): its remaining gates k-steps go first -- the SIMT
+            // warps wait for them --, then the k-steps of this GVP over the second halves
+            // (while the gates weight is held, the ring is one slot short and the producer may be waiting for THAT slot: so
+            // never block on the next slab before the gates are out -- watch both barriers)
+            while (!g1) {
+                if (i == n_first || tc::mbar_try_wait(m.feats_ready, g & 1)) {
+                    if (i == n_first) tc::mbar_wait(m.feats_ready, g & 1);
+                    tc::fence_after_sync();
+                    gates(g - 1, gst, 2);
+                    g1 = true;
+                } else if (tc::mbar_try_wait(&m.full[it % GST<C>], (it / GST<C>) & 1)) {
+                    break;
+                }
+            }
+            if (i == ksm) {         // (n_first <= ksm: the wait above has happened by now)
+                tc::mbar_wait(m.tail_ready, g & 1);
+                tc::fence_after_sync();
+            }
+            const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+            const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+            const uint32_t st = take();         // [W_hi | W_lo] of this k-step
+            const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
+            const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + 2 * b_k, b_k, 128);
+            tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);      // A_hi W_hi
+            tc::mma_bf16_ss(acc, a1, b0, idesc, 1u);                    // + A_lo W_hi
+            tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);                    // + A_hi W_lo (lo x lo is below the fp32 rounding of the sum)
+            release(st);
+        }
+        tc::mma_commit(m.acc_done);
+    }
+    // the last GVP's gates
+    const uint32_t gst = take();
+    ++it;
+    tc::mbar_wait(m.half_ready, (n_gvps - 1) & 1);
+    tc::fence_after_sync();
+    gates(n_gvps - 1, gst, 0);
+    tc::mbar_wait(m.feats_ready, n_gvps & 1);
+    tc::fence_after_sync();
+    gates(n_gvps - 1, gst, 1);
 }
 
 // CTA pairs: the peer's control thread tells the leader's MMA thread when the peer's half of a weight slab has landed
@@ -586,6 +742,67 @@ __device__ __forceinline__ void vec_gemm(const float (&A)[3][3][2], float (&D)[3
     }
 }
 
+// The same GEMM on the FP32 pipe (KS edge kernel).  The legacy warp-level tensor-core path shares the tensor cores with
+// tcgen05.mma and only gets the gaps of a busy UTCMMA stream: with the main GEMM of the chain running underneath, the
+// mma.sync vector GEMMs took 2-3x their stand-alone time (measured: Vh + Vu 10.8k instead of 4.4k cycles per GVP).  Here
+// every lane multiplies its own input channels (8 s + 2 t + e) into ALL eight outputs of a block, and a reduce-scatter
+// over the four lanes of a row (two shuffle rounds) leaves each lane with the outputs it owns (8 ob + 2 t + e) -- exact
+// fp32, no split operands.  W: plain fp32 [24][LD] in shared memory (pack.pack_gvp_small_ks; LD = 28 / 20 keeps the
+// four distinct rows a warp instruction reads on distinct banks).
+template <int LD, int NT>
+__device__ __forceinline__ void vec_fma(const float (&A)[3][3][2], float (&D)[3][NT][2], const float* __restrict__ W, int nks,
+                                        bool nt_last, int lane) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int ob = 0; ob < NT; ++ob) {
+        float acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
+        if (ob + 1 < NT || nt_last) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                if (s < nks) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float* wr = W + (8 * s + 2 * t + e) * LD + 8 * ob;
+                        const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float a = A[c][s][e];
+                            acc[c][0] = fmaf(a, w0.x, acc[c][0]); acc[c][1] = fmaf(a, w0.y, acc[c][1]);
+                            acc[c][2] = fmaf(a, w0.z, acc[c][2]); acc[c][3] = fmaf(a, w0.w, acc[c][3]);
+                            acc[c][4] = fmaf(a, w1.x, acc[c][4]); acc[c][5] = fmaf(a, w1.y, acc[c][5]);
+                            acc[c][6] = fmaf(a, w1.z, acc[c][6]); acc[c][7] = fmaf(a, w1.w, acc[c][7]);
+                        }
+                    }
+                }
+            }
+            // reduce-scatter over the four lanes of the row: lanes t = 0, 1 end up with outputs 0-3, lanes 2, 3 with 4-7 ...
+            const bool up = (t & 2) != 0, odd = (t & 1) != 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float keep[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float give = up ? acc[c][k] : acc[c][k + 4];
+                    keep[k] = (up ? acc[c][k + 4] : acc[c][k]) + __shfl_xor_sync(0xffffffffu, give, 2);
+                }
+                // ... then even lanes with the first pair of their four, odd lanes with the second
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float give = odd ? keep[k] : keep[k + 2];
+                    D[c][ob][k] = (odd ? keep[k + 2] : keep[k]) + __shfl_xor_sync(0xffffffffu, give, 1);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) D[c][ob][0] = D[c][ob][1] = 0.f;
+        }
+    }
+}
+
 // one 32-column chunk of epilogue 1: bias + SiLU -> bf16 plane(s) of A (static register indexing only)
 template <class C>
 __device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
@@ -690,7 +907,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                                          int rows_valid, int tb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* Wh_s = m.wsm;
-    const float* Wu_s = Wh_s + C::NS * WH_SZ;
+    const float* Wu_s = Wh_s + (C::KS ? 24 * WH_LD_KS : C::NS * WH_SZ);
     const float* bf_s = m.bias + (gi & 1) * C::WSM_B;
     const float* bg_s = bf_s + 256;
     const int NBf = (g.fout + 15) & ~15;
@@ -698,12 +915,15 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     TC_T(t0);
     WS_TRACE(10);
     tc::mbar_wait(m.wsm_full, gi & 1);
+    TC_T(t0b);
+    WS_ACC(tb + 7, t0, t0b);                 // (of the Vh phase: waiting for this GVP's small weights)
     float vh[3][3][2];
     float vu[3][2][2];
     [[maybe_unused]] float gD[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};     // bf16x3: this warp's partial gates
     const bool vecw = warp < C::NWV;          // (warp-uniform) this warp owns vector rows
     if (vecw) {
-    vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
+    if constexpr (C::KS) vec_fma<WH_LD_KS, 3>(v.x, vh, Wh_s, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
+    else vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const int h = 8 * j + 2 * L.t;
@@ -726,7 +946,8 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     WS_TRACE(11);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
     if (vecw) {
-        vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
+        if constexpr (C::KS) vec_fma<WU_LD_KS, 2>(vh, vu, Wu_s, g.hd > 16 ? 3 : 2, true, lane);
+        else vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(m.wsm_empty);     // Wh | Wu may be overwritten with the next GVP's
     }
@@ -734,7 +955,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const int q = warp & 3, cg = warp >> 2;
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
     const bool valid_e = C::R == 128 ? true : lane < 16;
-    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + ((C::STACK && (gi & 1)) ? 256u : 0u);
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (((C::STACK || C::KS) && (gi & 1)) ? 256u : 0u);
     TC_T(t2);
     WS_TRACE(12);
     tc::mbar_wait(m.acc_done, gi & 1);
@@ -823,7 +1044,8 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         {
             const int sub = warp >> 2;                       // which 8 rows of the warp's TMEM lane quarter
             uint32_t gv[8];
-            tc::tmem_ld_16x256b_x2(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + GATE_COL, gv);
+            // (the gates accumulator: columns [0, 16) of this GVP's own, drained, accumulator -- issue_ks())
+            tc::tmem_ld_16x256b_x2(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + ((gi & 1) ? 256u : 0u), gv);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -987,12 +1209,16 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         if (warp == C::NW) {
             if (lane == 0) {
                 if (C::CL == 2 && m.rank != 0) ws::relay<C>(a.msg, L.n_msg, m);
+                else if constexpr (C::KS) ws::issue_ks<C>(a.msg, L.n_msg, m, tmem);
                 else ws::issue<C>(a.msg, L.n_msg, m, tmem);
             } else if (lane == 1 && C::CL == 2 && m.rank != 0 && !dead) {
                 ws::forward_ready<C>(L.n_msg, m);
             }
         } else {
-            if (lane == 0) ws::produce<C>(a.msg, L.n_msg, m, dead);
+            if (lane == 0) {
+                if constexpr (C::KS) ws::produce_ks<C>(a.msg, L.n_msg, m);
+                else ws::produce<C>(a.msg, L.n_msg, m, dead);
+            }
         }
     } else if (!dead) {
         TC_T(e1);
@@ -1006,11 +1232,17 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             m.rp[2 * tid + 1] = __ldg(a.rowptr + my_d + 1);
         }
         ws::simt_bar<C>();
+        TC_T(ga);
         // s_src: 16-byte cp.async straight into the canonical bf16 plane(s); consecutive lanes = consecutive rows
         {
-            const int items = C::R * (Sd >> 3);
+            // consecutive lanes = consecutive 16-byte chunks of ONE source row: a warp instruction reads whole 32-byte
+            // sectors (rows dealt lane-by-lane fetched every sector twice: cp.async.cg goes to L2, 16 bytes at a time, and
+            // the gather was bound by L2 -> SM bandwidth); the shared-memory side stays conflict-free through the
+            // +16-byte rotation of the k-chunk stride
+            const int cpr = Sd >> 3;                 // chunks per row
+            const int items = C::R * cpr;
             for (int idx = tid; idx < items; idx += C::NT_SIMT) {
-                const int r = idx % C::R, kc = idx / C::R;
+                const int r = idx / cpr, kc = idx - r * cpr;
                 const uint32_t off = (uint32_t)(kc * C::KCS) + ws::row_off<C>(r);
                 const size_t g = (size_t)m.src_s[r] * Sd + 8 * kc;
                 cp_async16(m.A[0] + off, a.s_hi + g);
@@ -1018,6 +1250,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             }
             cp_async_commit();
         }
+        TC_T(ga1);
         // geometry + v_src -> registers (gvp.py:474-480), in flight together with the gather
         const ws::Lane Ln = ws::lane_geometry<C>();
         const bool vecw = warp < C::NWV;              // this warp owns 8 tile rows of vectors
@@ -1028,6 +1261,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             dx = a.xs[3 * sI] - a.xd[3 * dI]; dy = a.xs[3 * sI + 1] - a.xd[3 * dI + 1]; dz = a.xs[3 * sI + 2] - a.xd[3 * dI + 2];
             ws::vf_load(v, a.v_src + (size_t)sI * (Vd * 3), Vd, Ln.t);
         }
+        TC_T(ga2);
         if (ASYNC) {        // only the k-chunks behind the gathered scalars need zeros (rbf / |Vh| columns and K padding)
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             const int c0 = Sd >> 3, per = C::KCS / 16;
@@ -1036,7 +1270,10 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
                 if (C::KS) reinterpret_cast<uint4*>(m.A[1] + (size_t)c0 * C::KCS)[i] = z;
             }
         }
+        TC_T(ga3);
         ws::build_segments<C>(m, n);             // (its barriers also order the zero fill before the rbf stores)
+        TC_T(gb);
+        WS_ACC(40, ga, ga1); WS_ACC(41, ga1, ga2); WS_ACC(42, ga2, ga3); WS_ACC(43, ga3, gb);
         if (vecw) {
             const float dij = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-8f)) + 1e-8f;
             // the unit x_diff is the LAST input channel here (channel Vd; Wh is staged with its rows permuted to match)
@@ -1054,9 +1291,11 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
             }
         }
         if (ASYNC) tmem = ws::simt_join<C>(m);
+        TC_T(gc);
         cp_async_wait<0>();
         ws::publish_mma<C>(m, m.feats_ready);
         TC_T(e2);
+        WS_ACC(12, e1, ga); WS_ACC(14, ga, gb); WS_ACC(15, gb, gc);
         for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R, 0);
         TC_T(e3);
         // ---- deterministic segmented reduction by destination (all MMAs and bulk copies have completed)
@@ -1549,9 +1788,10 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
     } else if (!dead) {
         const ws::Lane Ln = ws::lane_geometry<C>();
         {
-            const int items = NODE_ROWS * (Sd >> 3);
+            const int cpr = Sd >> 3;                 // (lanes along a row: whole sectors per request, see the edge kernel)
+            const int items = NODE_ROWS * cpr;
             for (int idx = tid; idx < items; idx += C::NT_SIMT) {
-                const int r = idx % NODE_ROWS, kc = idx / NODE_ROWS;
+                const int r = idx / cpr, kc = idx - r * cpr;
                 const uint32_t off = (uint32_t)(kc * C::KCS) + ws::row_off<C>(r);
                 const size_t g = (size_t)(n0 + min(r, n - 1)) * Sd + 8 * kc;
                 cp_async16(m.A[0] + off, a.s_hi + g);

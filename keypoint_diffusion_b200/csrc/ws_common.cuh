@@ -48,7 +48,8 @@ struct Cfg {
     static constexpr int WG_BYTES = NS * 8192;       // gates weight: 16 k-steps x 512 B (hi [, lo])
     static constexpr int WGB = KS ? 0 : NS == 1 ? 2 : 1;   // gates weight buffers (KS: the gates weight travels through the ring)
     static constexpr int WSM = wsm_floats<NS>();
-    static constexpr int WSM_W = NS * (WH_SZ + WU_SZ);   // its Wh | Wu part (dead after the Vu GEMM) ...
+    // its Wh | Wu part (dead after the Vu GEMM); KS keeps plain fp32 [24][28] / [24][20] images instead (vec_fma) ...
+    static constexpr int WSM_W = KS ? 24 * 28 + 24 * 20 : NS * (WH_SZ + WU_SZ);
     static constexpr int WSM_B = 256 + 16;               // ... and its bias part bf | bg (live until epilogue 2)
     static constexpr int NCG = NW / 4;               // column groups of the epilogues (4 TMEM lane quarters x NCG)
 };

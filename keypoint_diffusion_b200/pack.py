@@ -314,13 +314,28 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
         # runs on the warp-level tensor cores straight from the epilogue registers)
         wg = sd[name + ".scalar_to_vector_gates.weight"]
         # (split: followed by the (hi, lo) tcgen05 slabs of the same weight, which the KS edge kernel streams through its ring)
-        add(torch.cat([pack_gates_frag(wg), pack_tc_weight(wg, True)]) if split else pack_tc_weight(wg, False))
+        add(torch.cat([pack_gates_frag(wg), pack_gates_ks(wg)]) if split else pack_tc_weight(wg, False))
         # message GVP 0 of every edge type takes the unit x_diff as its first input vector channel
         xfirst = ".edge_message_fns." in name and name.endswith(".0")
         img = pack_gvp_small(sd[name + ".Wh"], sd[name + ".Wu"], sd[name + ".to_feats_out.0.bias"],
                              sd[name + ".scalar_to_vector_gates.bias"], xfirst, split)
+        if split:       # followed by the plain fp32 image the KS edge kernel's FP32-pipe vector GEMMs read
+            img = torch.cat([img, pack_gvp_small_ks(sd[name + ".Wh"], sd[name + ".Wu"], sd[name + ".to_feats_out.0.bias"],
+                                                    sd[name + ".scalar_to_vector_gates.bias"], xfirst)])
         add(img.view(torch.bfloat16))                # fp32 image carried in the bf16 blob (two bf16 per float)
     return torch.cat(parts).to(device), offs
+
+
+def pack_gates_ks(wg: torch.Tensor, n_col_groups: int = 4) -> torch.Tensor:
+    """scalar_to_vector_gates.weight for the KS edge kernel (csrc/gvp_ws.inl issue_ks): the (hi, lo) tcgen05 k-step slabs
+    of pack_tc_weight(split=True) -- 1 KB per k-step -- reordered so that the k-steps over the FIRST halves of the epilogue's
+    column groups (256 / n_col_groups columns each) come first: the two parts travel through the weight ring separately,
+    the first as soon as epilogue 1 is half way."""
+    slabs = pack_tc_weight(wg, True).view(-1, 512)          # [ks][512 bf16 = 1 KB]
+    cpw = 256 // n_col_groups
+    first = [j for j in range(slabs.shape[0]) if (16 * j) % cpw < cpw // 2]
+    rest = [j for j in range(slabs.shape[0]) if j not in first]
+    return slabs[first + rest].reshape(-1)
 
 
 def pack_gates_frag(wg: torch.Tensor) -> torch.Tensor:
@@ -359,6 +374,27 @@ def _tf32_rna(x: torch.Tensor) -> torch.Tensor:
     b = x.contiguous().view(torch.int32)
     mag = (b & 0x7FFFFFFF) + 0x1000
     return ((mag & ~0x1FFF) | (b & -0x80000000)).view(torch.float32)
+
+
+_WH_LD_KS, _WU_LD_KS = 28, 20
+
+
+def pack_gvp_small_ks(Wh, Wu, bf, bg, xfirst: bool) -> torch.Tensor:
+    """The small weights of one GVP for the KS edge kernel (csrc/gvp_ws.inl vec_fma): Wh [vin, h] and Wu [h, vout] as plain
+    fp32 [24][28] / [24][20] images (zero padded), then the to_feats_out bias padded to 256 and the gates bias padded to 16.
+    xfirst: the kernel keeps the x_diff channel LAST, so Wh's rows are rotated (as in pack_gvp_small)."""
+    Wh, Wu = Wh.detach().float().cpu(), Wu.detach().float().cpu()
+    if xfirst:
+        Wh = torch.cat([Wh[1:], Wh[:1]])
+    ih = torch.zeros(24, _WH_LD_KS)
+    ih[:Wh.shape[0], :Wh.shape[1]] = Wh
+    iu = torch.zeros(24, _WU_LD_KS)
+    iu[:Wu.shape[0], :Wu.shape[1]] = Wu
+    b1 = torch.zeros(256)
+    b1[:bf.numel()] = bf.detach().float().cpu()
+    b2 = torch.zeros(16)
+    b2[:bg.numel()] = bg.detach().float().cpu()
+    return torch.cat([ih.reshape(-1), iu.reshape(-1), b1, b2])
 
 
 def pack_gvp_small(Wh, Wu, bf, bg, xfirst: bool, split: bool) -> torch.Tensor:

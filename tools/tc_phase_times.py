@@ -21,7 +21,12 @@ for kname, b in (("edge", 0), ("node", 16), ("head", 32)):
     print(f"{kname} kernel: gvp_simt calls {calls}")
     for n, v in zip(names, t[b:b + 6]):
         print(f"  {n:10s} {v / calls:9.0f} cycles/call  {100 * v / tot:5.1f}%")
-    print(f"  total      {tot / calls:9.0f} cycles/call")
+    print(f"  total      {tot / calls:9.0f} cycles/call   (of Vh+|Vh|: {t[b + 7] / calls:.0f} cycles waiting for the small weights)")
+ct_e = max(t[13], 1)
+print(f"edge gather breakdown: index staging {t[12] / ct_e:.0f} | gathers issued, geometry + vectors loaded, segments built "
+      f"{t[14] / ct_e:.0f} | rbf + control join {t[15] / ct_e:.0f} | waiting for the gathered rows {(t[9] - t[12] - t[14] - t[15]) / ct_e:.0f} cycles/CTA")
+print(f"   of the second: cp.async issue {t[40] / ct_e:.0f} | geometry + vector loads {t[41] / ct_e:.0f} | zero fill {t[42] / ct_e:.0f} | "
+      f"segment table {t[43] / ct_e:.0f}")
 for kname, b, en in (("edge", 8, ["setup", "gather", "gvp chain", "seg-reduce"]),
                      ("node", 24, ["setup", "phase 1a (scalars)", "phase 1b (vectors)", "gvp chain", "phase 3"])):
     ct = max(t[b + 5], 1)
