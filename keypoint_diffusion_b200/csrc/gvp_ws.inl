@@ -420,6 +420,7 @@ __device__ __forceinline__ void produce_ks(const GvpW* gv, int n_gvps, Sm& m) {
         if (it >= (uint32_t)GST<C>) tc::mbar_wait(&m.empty[st], ((it / GST<C>) - 1) & 1);
         tc::mbar_arrive_expect_tx(&m.full[st], bytes);
         tc::bulk_g2s(m.ring + (size_t)st * SLOT<C>, src, bytes, &m.full[st]);
+        WS_TRACE(100 + it);
         ++it;
     };
     auto gates_bytes = [&](const GvpW& w, int half) {      // k-steps of that half x (hi 512 B | lo 512 B)
@@ -487,6 +488,7 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
                 tc::mma_bf16_ss(gcol, a0, b1, idg, 1u);     // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
                 ++k;
             }
+        WS_TRACE(6 + which);
         if (which == 0) return;
         tc::mma_commit(m.gates_done);
         tc::mma_commit(&m.empty[st]);
@@ -538,12 +540,15 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
                 }
             }
             if (i == ksm) {         // (n_first <= ksm: the wait above has happened by now)
+                WS_TRACE(2);
                 tc::mbar_wait(m.tail_ready, g & 1);
                 tc::fence_after_sync();
+                WS_TRACE(3);
             }
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint32_t st = take();         // [W_hi | W_lo] of this k-step
+            WS_TRACE(200 + it);
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + 2 * b_k, b_k, 128);
             tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);      // A_hi W_hi
@@ -552,6 +557,7 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
             release(st);
         }
         tc::mma_commit(m.acc_done);
+        WS_TRACE(4);
     }
     // the last GVP's gates
     const uint32_t gst = take();

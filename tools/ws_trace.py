@@ -12,9 +12,12 @@ fn.restype = C.c_int
 buf = (C.c_ulonglong * (3 * 2048))()
 n = C.c_int32()
 fn(buf, 2048, C.byref(n))
-ev = sorted(((buf[3 * i + 2], buf[3 * i + 1], buf[3 * i]) for i in range(n.value)))
+ev = sorted(((buf[3 * i + 2], buf[3 * i + 1], buf[3 * i]) for i in range(n.value) if buf[3 * i + 2] > 0))
+# keep the first launch only (later launches -- other edge types, node kernels -- start much later)
+cut = next((k for k in range(1, len(ev)) if ev[k][0] - ev[k - 1][0] > 200000), len(ev))
+ev = ev[:cut]
 names = {1: "MMA: feats_ready(0) seen", 2: "MMA: main k-steps issued", 3: "MMA: tail_ready seen", 4: "MMA: acc_done committed",
-         5: "MMA: feats_ready(g+1) seen", 6: "MMA: gates committed", 10: "SIMT: GVP start", 11: "SIMT: |Vh| published",
+         5: "MMA: feats_ready(g+1) seen", 6: "MMA: gates issued (first halves)", 7: "MMA: gates issued (second halves)", 8: "MMA: gates issued (all)", 10: "SIMT: GVP start", 11: "SIMT: |Vh| published",
          12: "SIMT: Vu done, wait acc", 13: "SIMT: acc_done seen", 14: "SIMT: epi1 published", 15: "SIMT: gates_done seen",
          16: "SIMT: GVP end"}
 t0 = ev[0][0] if ev else 0
