@@ -466,13 +466,13 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
     auto release = [&](uint32_t st) { tc::mma_commit(&m.empty[st]); ++it; };
     (void)release;
     // gates GEMM of GVP gp over the slot `st` that holds its weight: feats_out (hi, lo planes) x Wg (hi, lo) into columns
-    // [0, 16) of the accumulator GVP gp has drained.  The weight image lists the k-steps over the first halves of the
+    // [0, 32) of the accumulator GVP gp has drained.  The weight image lists the k-steps over the first halves of the
     // column groups first (pack.pack_gates_ks).
     auto gates = [&](int gp, uint32_t st, int which) {          // which: 0 / 1 = the k-steps of that half only, 2 = all
         const GvpW& w = gv[gp];
         const int ksg = ((w.fout + 15) & ~15) >> 4;
         const uint32_t wg = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
-        const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
+        const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16), idg32 = tc::make_idesc_bf16(C::MMA_M, 32);
         const uint32_t gcol = tmem + ((gp & 1) ? 256u : 0u);
         int k = 0;
         for (int half = 0; half < 2; ++half)
@@ -481,11 +481,13 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
                 if (which != 2 && which != half) { ++k; continue; }
                 const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
                 const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
-                const uint64_t b0 = tc::make_smem_desc(wg + k * 1024, 256, 128);
-                const uint64_t b1 = tc::make_smem_desc(wg + k * 1024 + 512, 256, 128);
-                tc::mma_bf16_ss(gcol, a0, b0, idg, k == 0 ? 0u : 1u);
-                tc::mma_bf16_ss(gcol, a1, b0, idg, 1u);
-                tc::mma_bf16_ss(gcol, a0, b1, idg, 1u);     // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                // B = [Wg_hi ; Wg_lo] stacked along N (32 rows, pack.pack_gates_ks): A_hi x B gives hi x hi in columns
+                // [0, 16) and hi x lo in [16, 32) with ONE read of A_hi; A_lo x Wg_hi (the first 16 rows of the same image)
+                // adds to [0, 16).  Epilogue 2 sums the two column groups.  (These small MMAs are bound by the read of
+                // their A operand, ~70 cycles each: two per k-step instead of three.)
+                const uint64_t b32 = tc::make_smem_desc(wg + k * 1024, 512, 128);
+                tc::mma_bf16_ss(gcol, a0, b32, idg32, k == 0 ? 0u : 1u);
+                tc::mma_bf16_ss(gcol, a1, b32, idg, 1u);    // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
                 ++k;
             }
         WS_TRACE(6 + which);
@@ -1049,15 +1051,17 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         TC_T(t5);
         {
             const int sub = warp >> 2;                       // which 8 rows of the warp's TMEM lane quarter
-            uint32_t gv[8];
-            // (the gates accumulator: columns [0, 16) of this GVP's own, drained, accumulator -- issue_ks())
-            tc::tmem_ld_16x256b_x2(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + ((gi & 1) ? 256u : 0u), gv);
+            uint32_t gv[16];
+            // (the gates accumulator: columns [0, 32) of this GVP's own, drained, accumulator -- issue_ks(): hi x (hi + ...)
+            // products in [0, 16), the hi x lo products in [16, 32))
+            tc::tmem_ld_16x256b_x4(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + ((gi & 1) ? 256u : 0u), gv);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int u = 8 * j + 2 * L.t;
-                float a0 = __uint_as_float((sub & 1) ? gv[4 * j + 2] : gv[4 * j + 0]) + bg_s[u];
-                float a1 = __uint_as_float((sub & 1) ? gv[4 * j + 3] : gv[4 * j + 1]) + bg_s[u + 1];
+                const int o = (sub & 1) ? 2 : 0;
+                float a0 = __uint_as_float(gv[4 * j + o]) + __uint_as_float(gv[4 * (j + 2) + o]) + bg_s[u];
+                float a1 = __uint_as_float(gv[4 * j + o + 1]) + __uint_as_float(gv[4 * (j + 2) + o + 1]) + bg_s[u + 1];
                 if (g.sigmoid_gate) { a0 = sigmoid_acc(a0); a1 = sigmoid_acc(a1); }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * a0; v.x[c][j][1] = vu[c][j][1] * a1; }
@@ -1241,20 +1245,38 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         TC_T(ga);
         // s_src: 16-byte cp.async straight into the canonical bf16 plane(s); consecutive lanes = consecutive rows
         {
-            // consecutive lanes = consecutive 16-byte chunks of ONE source row: a warp instruction reads whole 32-byte
-            // sectors (rows dealt lane-by-lane fetched every sector twice: cp.async.cg goes to L2, 16 bytes at a time, and
-            // the gather was bound by L2 -> SM bandwidth); the shared-memory side stays conflict-free through the
-            // +16-byte rotation of the k-chunk stride
+            // 16-byte loads into registers + 16-byte shared-memory stores, a batch of GB rows-chunks (x hi, lo) in flight per
+            // thread.  (cp.async straight into the planes was bound by the ISSUE rate of LDGSTS: ~17 cycles per warp
+            // instruction, 8.8k of the 13k cycles a 128-row tile spent before its first MMA: measured.)  Consecutive lanes =
+            // consecutive chunks of ONE source row: whole sectors per request; the shared-memory side stays conflict-free
+            // through the +16-byte rotation of the k-chunk stride.
             const int cpr = Sd >> 3;                 // chunks per row
             const int items = C::R * cpr;
-            for (int idx = tid; idx < items; idx += C::NT_SIMT) {
-                const int r = idx / cpr, kc = idx - r * cpr;
-                const uint32_t off = (uint32_t)(kc * C::KCS) + ws::row_off<C>(r);
-                const size_t g = (size_t)m.src_s[r] * Sd + 8 * kc;
-                cp_async16(m.A[0] + off, a.s_hi + g);
-                if (C::NS == 2) cp_async16(m.A[1] + off, a.s_lo + g);
+            constexpr int GB = 4;
+            for (int base = 0; base < items; base += GB * C::NT_SIMT) {
+                uint4 vh[GB];
+                [[maybe_unused]] uint4 vl[GB];
+                uint32_t off[GB];
+#pragma unroll
+                for (int k = 0; k < GB; ++k) {
+                    const int idx = base + k * C::NT_SIMT + tid;
+                    off[k] = 0xffffffffu;
+                    if (idx < items) {
+                        const int r = idx / cpr, kc = idx - r * cpr;
+                        off[k] = (uint32_t)(kc * C::KCS) + ws::row_off<C>(r);
+                        const size_t g = (size_t)m.src_s[r] * Sd + 8 * kc;
+                        vh[k] = __ldg(reinterpret_cast<const uint4*>(a.s_hi + g));
+                        if (C::NS == 2) vl[k] = __ldg(reinterpret_cast<const uint4*>(a.s_lo + g));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < GB; ++k) {
+                    if (off[k] != 0xffffffffu) {
+                        *reinterpret_cast<uint4*>(m.A[0] + off[k]) = vh[k];
+                        if (C::NS == 2) *reinterpret_cast<uint4*>(m.A[1] + off[k]) = vl[k];
+                    }
+                }
             }
-            cp_async_commit();
         }
         TC_T(ga1);
         // geometry + v_src -> registers (gvp.py:474-480), in flight together with the gather
@@ -1298,7 +1320,6 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         }
         if (ASYNC) tmem = ws::simt_join<C>(m);
         TC_T(gc);
-        cp_async_wait<0>();
         ws::publish_mma<C>(m, m.feats_ready);
         TC_T(e2);
         WS_ACC(12, e1, ga); WS_ACC(14, ga, gb); WS_ACC(15, gb, gc);
