@@ -49,6 +49,9 @@ constexpr int VS_LD = 52;                                   // fp32 vector stagi
 constexpr int GATE_LD = 20;                                 // gates staged as [R][20]
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t GATE_COL = 256;
+// KS edge kernel: accumulator [0, 256) | gates accumulator [256, 288) | hi plane of feats_out as the next GVP's A operand
+// (bf16 pairs: column 320 + k / 2) [320, 448)
+constexpr uint32_t KS_A_COL = 320;
 
 
 struct Sm {
@@ -211,7 +214,7 @@ __device__ __forceinline__ void teardown(uint32_t tmem) {
 // j = first halves of all column groups, then second halves, then the |Vh| tail.  Otherwise j = i.
 template <class C>
 __device__ __forceinline__ int kstep_at(int i, int ksm, bool chained) {
-    if (!(C::STACK || C::KS) || !chained || i >= ksm) return i;
+    if (!C::STACK || !chained || i >= ksm) return i;
     constexpr int kpg = (256 / C::NCG) / 16, kph = kpg / 2;      // k-steps per column group / per half
     int n0 = (ksm / kpg) * kph + min(ksm % kpg, kph);            // k-steps that lie in first halves
     const bool second = i >= n0;
@@ -395,20 +398,13 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
 // ------------------------------------------------------------------ KS (hi / lo planes, 128-row tiles): producer + issuer
 // Ring order == consumption order (one FIFO of 8 KB slots):
 //   GVP 0:      [W_hi, W_lo] per k-step
-//   GVP g > 0:  gates weight of GVP g-1 | [W_hi | W_lo] of the k-steps over the FIRST halves of the column groups | the
-//               remaining k-steps (second halves, |Vh| tail)
+//   GVP g > 0:  gates weight of GVP g-1 | [W_hi | W_lo] per k-step
 //   at the end: the last GVP's gates weight
-// (epilogue 1 rewrites A in two halves per column group; the k-steps that only need first halves are issued behind
-//  half_ready while the second halves are still being produced, into the OTHER accumulator.)
+// (A chained order -- the next GVP's k-steps over the first halves of the column groups issued behind half_ready into a
+//  second accumulator -- was measured SLOWER, 21.4k vs 19.4k cycles per GVP: the tensor pipe executes in issue order, so
+//  the gates GEMM, which the SIMT warps wait for, queues behind the early k-steps.)
 // The gates weight image is packed with its first-half k-steps first (pack.pack_gates_ks); a gates accumulator lives
 // in columns [0, 16) of the accumulator its GVP has just drained.
-// KPD_KS_CHAIN=1: the next GVP's k-steps over the first halves of the column groups start behind half_ready (into the
-// other accumulator), the whole gates GEMM runs when epilogue 1 completes.  Measured SLOWER than the plain order below
-// (21.4k vs 16-19k cycles per GVP): the tensor pipe executes in issue order, so the gates GEMM -- which the SIMT warps
-// wait for -- queues behind the early k-steps, and the main GEMM is bound by the rate of the weight ring either way.
-#ifndef KPD_KS_CHAIN
-#define KPD_KS_CHAIN 0
-#endif
 template <class C>
 __device__ __forceinline__ bool gates_first_half(int j) { return ((16 * j) % (256 / C::NCG)) < (256 / C::NCG) / 2; }
 
@@ -447,7 +443,7 @@ __device__ __forceinline__ void produce_ks(const GvpW* gv, int n_gvps, Sm& m) {
         // until epilogue 1 of GVP g-1 completes and runs the gates GEMM at once then, before the queued k-steps
         if (g > 0) push(gv[g - 1].WgP2c, gates_bytes(gv[g - 1], 0) + gates_bytes(gv[g - 1], 1));
         for (int i = 0; i < ksf; ++i) {
-            const int j = kstep_at<C>(i, ksm, KPD_KS_CHAIN && g > 0);
+            const int j = i;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(gv[g].WfP2) + (size_t)j * 2 * plane;
             push(src, 2 * plane);
         }
@@ -463,30 +459,32 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
         tc::fence_after_sync();
         return st;
     };
-    auto release = [&](uint32_t st) { tc::mma_commit(&m.empty[st]); ++it; };
-    (void)release;
-    // gates GEMM of GVP gp over the slot `st` that holds its weight: feats_out (hi, lo planes) x Wg (hi, lo) into columns
-    // [0, 32) of the accumulator GVP gp has drained.  The weight image lists the k-steps over the first halves of the
-    // column groups first (pack.pack_gates_ks).
-    auto gates = [&](int gp, uint32_t st, int which) {          // which: 0 / 1 = the k-steps of that half only, 2 = all
+    // The hi plane of every GVP's feats_out but the last's lives in TENSOR MEMORY (epilogue 1 writes it there with
+    // tcgen05.st): an SS-mode MMA fetches its operands from shared memory at ~64 B/clk, so a 128 x 256 x 16 MMA spends
+    // ~190 cycles on 12 KB of operands for 128 cycles of math (measured: ~215 cycles per MMA whatever the weight ring
+    // does); with A from TMEM only the 8 KB of B remain.  Two of the three MMAs of a k-step, and one of the two of a
+    // gates k-step, read A_hi.
+    // gates GEMM of GVP gp over the slot `st` that holds its weight, the k-steps of one half of every column group
+    // (which = 0 / 1): feats_out (hi, lo planes) x [Wg_hi ; Wg_lo] into TMEM columns [GATE_COL, GATE_COL + 32)
+    auto gates = [&](int gp, uint32_t st, int which) {
         const GvpW& w = gv[gp];
         const int ksg = ((w.fout + 15) & ~15) >> 4;
+        const bool a_tmem = gp < n_gvps - 1;
         const uint32_t wg = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
         const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16), idg32 = tc::make_idesc_bf16(C::MMA_M, 32);
-        const uint32_t gcol = tmem + ((gp & 1) ? 256u : 0u);
+        const uint32_t gcol = tmem + GATE_COL;
         int k = 0;
         for (int half = 0; half < 2; ++half)
             for (int j = 0; j < ksg; ++j) {
                 if (gates_first_half<C>(j) != (half == 0)) continue;
-                if (which != 2 && which != half) { ++k; continue; }
-                const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                if (which != half) { ++k; continue; }
                 const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
                 // B = [Wg_hi ; Wg_lo] stacked along N (32 rows, pack.pack_gates_ks): A_hi x B gives hi x hi in columns
-                // [0, 16) and hi x lo in [16, 32) with ONE read of A_hi; A_lo x Wg_hi (the first 16 rows of the same image)
-                // adds to [0, 16).  Epilogue 2 sums the two column groups.  (These small MMAs are bound by the read of
-                // their A operand, ~70 cycles each: two per k-step instead of three.)
+                // [0, 16) and hi x lo in [16, 32) with ONE pass over A_hi; A_lo x Wg_hi (the first 16 rows of the same
+                // image) adds to [0, 16).  Epilogue 2 sums the two column groups.
                 const uint64_t b32 = tc::make_smem_desc(wg + k * 1024, 512, 128);
-                tc::mma_bf16_ss(gcol, a0, b32, idg32, k == 0 ? 0u : 1u);
+                if (a_tmem) tc::mma_bf16_ts(gcol, tmem + KS_A_COL + 8 * j, b32, idg32, k == 0 ? 0u : 1u);
+                else tc::mma_bf16_ss(gcol, tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128), b32, idg32, k == 0 ? 0u : 1u);
                 tc::mma_bf16_ss(gcol, a1, b32, idg, 1u);    // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
                 ++k;
             }
@@ -502,13 +500,10 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
         const int NBf = (w.fout + 15) & ~15, ksf = (w.fin + w.hd + 15) >> 4, ksm = w.fin >> 4;
         const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NBf);
         const uint32_t b_k = (NBf / 8) * 128;
-        const uint32_t acc = tmem + ((g & 1) ? 256u : 0u);
-        const bool chained = KPD_KS_CHAIN && g > 0;
-        const int n_first = chained ? first_half_ksteps<C>(ksm) : 0;
-        uint32_t gst = 0;
-        if (!KPD_KS_CHAIN && g > 0) {
-            // plain order: the gates GEMM of GVP g-1 progressively behind the two halves of its epilogue 1, then this GVP
-            gst = take();
+        if (g > 0) {
+            // the gates GEMM of GVP g-1 progressively behind the two halves of its epilogue 1, then this GVP (by then the
+            // accumulator has been drained and all of feats_out is in place)
+            const uint32_t gst = take();
             ++it;
             tc::mbar_wait(m.half_ready, (g - 1) & 1);
             tc::fence_after_sync();
@@ -517,46 +512,32 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
             tc::fence_after_sync();
             gates(g - 1, gst, 1);
         }
-        if (chained) {
-            gst = take();                       // the gates weight of GVP g-1: held until its epilogue 1 completes
-            ++it;
-            // first halves of epilogue 1 of GVP g-1 are in A, and out of its accumulator
-            tc::mbar_wait(m.half_ready, (g - 1) & 1);
-            tc::fence_after_sync();
-        }
-        bool g1 = !chained;                     // the previous GVP's gates GEMM issued
         for (int i = 0; i < ksf; ++i) {
-            const int j = kstep_at<C>(i, ksm, chained);
-            // epilogue 1 of GVP g-1 done (all of its feats_out is in A): its remaining gates k-steps go first -- the SIMT
-            // warps wait for them --, then the k-steps of this GVP over the second halves
-            // (while the gates weight is held, the ring is one slot short and the producer may be waiting for THAT slot: so
-            // never block on the next slab before the gates are out -- watch both barriers)
-            while (!g1) {
-                if (i == n_first || tc::mbar_try_wait(m.feats_ready, g & 1)) {
-                    if (i == n_first) tc::mbar_wait(m.feats_ready, g & 1);
-                    tc::fence_after_sync();
-                    gates(g - 1, gst, 2);
-                    g1 = true;
-                } else if (tc::mbar_try_wait(&m.full[it % GST<C>], (it / GST<C>) & 1)) {
-                    break;
-                }
-            }
-            if (i == ksm) {         // (n_first <= ksm: the wait above has happened by now)
+            if (i == ksm) {
                 WS_TRACE(2);
                 tc::mbar_wait(m.tail_ready, g & 1);
                 tc::fence_after_sync();
                 WS_TRACE(3);
             }
-            const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
-            const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
+            const bool a_tmem = g > 0 && i < ksm;       // (the |Vh| tail columns are written to shared memory)
+            const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * i * C::KCS), C::KCS, 128);
+            const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * i * C::KCS), C::KCS, 128);
             const uint32_t st = take();         // [W_hi | W_lo] of this k-step
             WS_TRACE(200 + it);
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + 2 * b_k, b_k, 128);
-            tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);      // A_hi W_hi
-            tc::mma_bf16_ss(acc, a1, b0, idesc, 1u);                    // + A_lo W_hi
-            tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);                    // + A_hi W_lo (lo x lo is below the fp32 rounding of the sum)
-            release(st);
+            if (a_tmem) {
+                const uint32_t at = tmem + KS_A_COL + 8 * i;
+                tc::mma_bf16_ts(tmem, at, b0, idesc, i > 0 ? 1u : 0u);  // A_hi W_hi
+                tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);               // + A_lo W_hi
+                tc::mma_bf16_ts(tmem, at, b1, idesc, 1u);               // + A_hi W_lo (lo x lo is below the fp32 rounding of the sum)
+            } else {
+                tc::mma_bf16_ss(tmem, a0, b0, idesc, i > 0 ? 1u : 0u);
+                tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);
+                tc::mma_bf16_ss(tmem, a0, b1, idesc, 1u);
+            }
+            tc::mma_commit(&m.empty[st]);
+            ++it;
         }
         tc::mma_commit(m.acc_done);
         WS_TRACE(4);
@@ -836,6 +817,29 @@ __device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], int c0, int 
     }
 }
 
+// same for the KS edge kernel when another GVP follows: the hi plane goes to TENSOR memory -- hw[] receives the 16 packed
+// bf16 pairs of the 32 columns, for one tcgen05.st by the caller --, the lo plane to shared memory
+template <class C>
+__device__ __forceinline__ void epi1_chunk_ks(const uint32_t (&v)[32], int c0, int fout, int NBf, const float* bf_s,
+                                              const Sm& m, int row, uint32_t (&hw)[16]) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
+        if (c0 + 8 * kc < fout) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bf_s + c0 + 8 * kc);
+            const float4 b1 = *reinterpret_cast<const float4*>(bf_s + c0 + 8 * kc + 4);
+            float f[8];
+            f[0] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 0]) + b0.x); f[1] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 1]) + b0.y);
+            f[2] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 2]) + b0.z); f[3] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 3]) + b0.w);
+            f[4] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 4]) + b1.x); f[5] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 5]) + b1.y);
+            f[6] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 6]) + b1.z); f[7] = act_silu<C::NS>(__uint_as_float(v[8 * kc + 7]) + b1.w);
+            split8(f, hi, lo);
+        }
+        hw[4 * kc + 0] = hi.x; hw[4 * kc + 1] = hi.y; hw[4 * kc + 2] = hi.z; hw[4 * kc + 3] = hi.w;
+        if (c0 + 8 * kc < NBf) *reinterpret_cast<uint4*>(m.A[1] + (uint32_t)(((c0 >> 3) + kc) * C::KCS) + row_off<C>(row)) = lo;
+    }
+}
+
 // M = 64 accumulators: 64 columns loaded with the 16x256b shape (all 32 lanes hold data: rows t/4 and t/4 + 8 of the
 // warp's 16-lane TMEM quarter, column pairs 2(t%4) + 8i).  bias + SiLU -> bf16x2 -> A plane(s), 4-byte stores.
 // fr (NS = 2 only): the packed bf16 pairs just written, [hi row a, hi row b, lo row a, lo row b][block] -- as they are,
@@ -912,7 +916,7 @@ __device__ __forceinline__ void gates_mma(const uint32_t (&fr)[4][NBLK], int c0,
 // published through feats_ready.
 template <class C>
 __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uint32_t tmem, VF& v, const Lane& L,
-                                         int rows_valid, int tb) {
+                                         int rows_valid, int tb, bool last = true) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* Wh_s = m.wsm;
     const float* Wu_s = Wh_s + (C::KS ? 24 * WH_LD_KS : C::NS * WH_SZ);
@@ -963,7 +967,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     const int q = warp & 3, cg = warp >> 2;
     const int row_e = C::R == 128 ? 32 * q + lane : 16 * q + (lane & 15);   // M = 64: lanes 0-15 of each TMEM quarter
     const bool valid_e = C::R == 128 ? true : lane < 16;
-    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (((C::STACK || C::KS) && (gi & 1)) ? 256u : 0u);
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + ((C::STACK && (gi & 1)) ? 256u : 0u);
     TC_T(t2);
     WS_TRACE(12);
     tc::mbar_wait(m.acc_done, gi & 1);
@@ -989,7 +993,14 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     uint32_t v0[32];
                     tc::tmem_ld_x32(taddr + cb, v0);
                     tc::tmem_ld_wait();
-                    epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
+                    if (C::KS && !last) {
+                        // hi plane -> tensor memory (the next GVP's A operand, issue_ks()), lo plane -> shared memory
+                        uint32_t hw[16];
+                        epi1_chunk_ks<C>(v0, cb, g.fout, NBf, bf_s, m, row_e, hw);
+                        tc::tmem_st_x16(tmem + ((uint32_t)(32 * q) << 16) + KS_A_COL + (cb >> 1), hw);
+                    } else {
+                        epi1_chunk<C>(v0, cb, g.fout, NBf, bf_s, m, row_e);
+                    }
                 } else if constexpr (C::NS == 1 && hb == 64) {           // hb = 64 columns, M = 64 accumulator
                     uint32_t v0[32];
                     tc::tmem_ld_16x256b_x8(taddr + cb, v0);
@@ -1021,6 +1032,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                     gates_mma<4>(fr4, cb, NBf, wgf, wg_lo, lane, gD);
                 }
             }
+            if (C::KS && !last) { tc::tmem_st_wait(); tc::fence_before_sync(); }
             if (half == 0) publish_mma<C>(m, m.half_ready);
         }
     }
@@ -1052,10 +1064,17 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         {
             const int sub = warp >> 2;                       // which 8 rows of the warp's TMEM lane quarter
             uint32_t gv[16];
-            // (the gates accumulator: columns [0, 32) of this GVP's own, drained, accumulator -- issue_ks(): hi x (hi + ...)
-            // products in [0, 16), the hi x lo products in [16, 32))
-            tc::tmem_ld_16x256b_x4(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + ((gi & 1) ? 256u : 0u), gv);
-            tc::tmem_ld_wait();
+            // (the gates accumulator, issue_ks(): the hi x hi + lo x hi products in its columns [0, 16), the hi x lo products
+            // in [16, 32))
+            {
+                const uint32_t ga = tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + GATE_COL;
+                uint32_t g0[8], g1[8];
+                tc::tmem_ld_16x256b_x2(ga, g0);
+                tc::tmem_ld_16x256b_x2(ga + 16, g1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { gv[i] = g0[i]; gv[8 + i] = g1[i]; }
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int u = 8 * j + 2 * L.t;
@@ -1323,7 +1342,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         ws::publish_mma<C>(m, m.feats_ready);
         TC_T(e2);
         WS_ACC(12, e1, ga); WS_ACC(14, ga, gb); WS_ACC(15, gb, gc);
-        for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R, 0);
+        for (int i = 0; i < L.n_msg; ++i) ws::gvp_simt<C>(a.msg[i], i, m, tmem, v, Ln, C::R, 0, i == L.n_msg - 1);
         TC_T(e3);
         // ---- deterministic segmented reduction by destination (all MMAs and bulk copies have completed)
         float* VS = reinterpret_cast<float*>(m.ring);
