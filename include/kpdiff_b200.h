@@ -137,7 +137,8 @@ typedef struct kpd_egnn_model kpd_egnn_model;
 
 /* Packed-weight blob layout is produced by the Python host (keypoint_diffusion_b200/pack.py)
  * from the reference state_dict; `blob` is a device pointer that must outlive the model, and
- * `offsets` is a HOST array of float offsets in the order documented in csrc/egnn.cuh. */
+ * `offsets` is a HOST array of float offsets in the order kpd_egnn_create reads them (csrc/egnn.cu; written by
+ * keypoint_diffusion_b200/pack.py: pack_egnn). */
 int kpd_egnn_create(const kpd_egnn_config* cfg, const float* blob, const int64_t* offsets,
                     int32_t n_offsets, kpd_egnn_model** out);
 void kpd_egnn_destroy(kpd_egnn_model* m);
@@ -194,12 +195,16 @@ int kpd_gvp_create(const kpd_gvp_config* cfg, const float* blob, const int64_t* 
 void kpd_gvp_destroy(kpd_gvp_model* m);
 int kpd_gvp_dims(const kpd_gvp_model* m, int* n_kp_scalars, int* vector_size);
 /* Tensor-core modes: the scalar Linear of every GVP and its gates run as tcgen05.mma with fp32 accumulation in
- * TMEM (csrc/gvp_ws.inl, csrc/gvp_tc.inl).  tc_blob holds, for every GVP in creation order, the packed
- * to_feats_out and gates weights (pack.pack_gvp_tc); byte_offsets has two entries per GVP.
+ * TMEM (csrc/gvp_ws.inl).  tc_blob holds, for every GVP in creation order, THREE entries (pack.pack_gvp_tc): the packed
+ * to_feats_out weight (k-step slabs), the gates weight, and the image of its small fp32 weights (Wh, Wu, biases);
+ * byte_offsets has three entries per GVP.
  *   nsplit = 1: bf16 operands                        -> mode 1, the "bf16 GEMM mode" the north star reports
  *               separately (outputs within ~2e-3 of fp32);
- *   nsplit = 2: bf16 (hi, lo) pairs, three MMAs per product (hi*hi + lo*hi + hi*lo) -> mode 2, "bf16x3":
- *               fp32-grade operands, meets the 1e-4 parity bar on the tensor cores.
+ *   nsplit = 2: split bf16 operands, x = hi + lo with hi = bf16(x), lo = bf16(x - hi) -> mode 2, "bf16x3": fp32-grade
+ *               operands, meets the 1e-4 parity bar on the tensor cores.  The edge kernel keeps hi and lo PLANES of a
+ *               128-row tile and issues THREE MMAs per k-step (hi*hi + lo*hi + hi*lo); the node / head kernels stack the
+ *               hi and lo rows of 64 tile rows into one 128-row operand and issue TWO (x W_hi, x W_lo: all four
+ *               products).  KPD_GVP_EDGE=stack at model creation selects the stacked layout for the edge kernel too.
  * mode: 0 = fp32 SIMT (reference arithmetic), 1 = bf16, 2 = bf16x3. */
 int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const int64_t* byte_offsets, int32_t n,
                       int32_t nsplit);

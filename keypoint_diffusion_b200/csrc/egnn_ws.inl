@@ -230,18 +230,29 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             // all 8 rows of the warp in one batch: every load of the batch is in flight together
             constexpr int RPW = R / NW;
             float v[RPW][8], vt[RPW];
+            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+            float wt = 0.f;
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
                 const int r = warp * RPW + j;
                 const float* ps = a.Ps + (size_t)m.src_s[r] * a.ldps + (a.slot_s + br) * Hp;
                 const float* pd = a.Pd + (size_t)m.dst_s[r] * a.ldpd + (a.slot_d + br) * Hp;
+                // the tile is dst-sorted: consecutive rows mostly share their destination (19 ll edges per ligand atom), so
+                // the destination's row of first-layer products is fetched once per RUN inside the warp's rows, not per edge
+                const bool same = j > 0 && m.dst_s[r] == m.dst_s[r - 1];       // (warp-uniform)
+                if (!same) {
+                    if (lane < nfull) {
+                        w0 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane));
+                        w1 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane + 4));
+                    }
+                    wt = lane < ntail ? __ldg(pd + 8 * nfull + lane) : 0.f;
+                }
                 if (lane < nfull) {
                     const float4 u0 = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane)), u1 = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane + 4));
-                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane)), w1 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane + 4));
                     v[j][0] = u0.x + w0.x; v[j][1] = u0.y + w0.y; v[j][2] = u0.z + w0.z; v[j][3] = u0.w + w0.w;
                     v[j][4] = u1.x + w1.x; v[j][5] = u1.y + w1.y; v[j][6] = u1.z + w1.z; v[j][7] = u1.w + w1.w;
                 }
-                vt[j] = lane < ntail ? __ldg(ps + 8 * nfull + lane) + __ldg(pd + 8 * nfull + lane) : 0.f;
+                vt[j] = lane < ntail ? __ldg(ps + 8 * nfull + lane) + wt : 0.f;
             }
             const float* w1c = m.w1c[br];
             const float* w2lo = m.w2lo[br];
