@@ -483,15 +483,20 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
                 // [0, 16) and hi x lo in [16, 32) with ONE pass over A_hi; A_lo x Wg_hi (the first 16 rows of the same
                 // image) adds to [0, 16).  Epilogue 2 sums the two column groups.
                 const uint64_t b32 = tc::make_smem_desc(wg + k * 1024, 512, 128);
-                if (a_tmem) tc::mma_bf16_ts(gcol, tmem + KS_A_COL + 8 * j, b32, idg32, k == 0 ? 0u : 1u);
-                else tc::mma_bf16_ss(gcol, tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128), b32, idg32, k == 0 ? 0u : 1u);
-                tc::mma_bf16_ss(gcol, a1, b32, idg, 1u);    // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
+                if (tc::elect_one()) {
+                    if (a_tmem) tc::mma_bf16_ts(gcol, tmem + KS_A_COL + 8 * j, b32, idg32, k == 0 ? 0u : 1u);
+                    else tc::mma_bf16_ss(gcol, a0, b32, idg32, k == 0 ? 0u : 1u);
+                    tc::mma_bf16_ss(gcol, a1, b32, idg, 1u);    // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                }
                 ++k;
             }
         WS_TRACE(6 + which);
         if (which == 0) return;
-        tc::mma_commit(m.gates_done);
-        tc::mma_commit(&m.empty[st]);
+        if (tc::elect_one()) {
+            tc::mma_commit(m.gates_done);
+            tc::mma_commit(&m.empty[st]);
+        }
     };
     tc::mbar_wait(m.feats_ready, 0);
     tc::fence_after_sync();
@@ -526,20 +531,22 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
             WS_TRACE(200 + it);
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + 2 * b_k, b_k, 128);
-            if (a_tmem) {
-                const uint32_t at = tmem + KS_A_COL + 8 * i;
-                tc::mma_bf16_ts(tmem, at, b0, idesc, i > 0 ? 1u : 0u);  // A_hi W_hi
-                tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);               // + A_lo W_hi
-                tc::mma_bf16_ts(tmem, at, b1, idesc, 1u);               // + A_hi W_lo (lo x lo is below the fp32 rounding of the sum)
-            } else {
-                tc::mma_bf16_ss(tmem, a0, b0, idesc, i > 0 ? 1u : 0u);
-                tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);
-                tc::mma_bf16_ss(tmem, a0, b1, idesc, 1u);
+            if (tc::elect_one()) {
+                if (a_tmem) {
+                    const uint32_t at = tmem + KS_A_COL + 8 * i;
+                    tc::mma_bf16_ts(tmem, at, b0, idesc, i > 0 ? 1u : 0u);  // A_hi W_hi
+                    tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);               // + A_lo W_hi
+                    tc::mma_bf16_ts(tmem, at, b1, idesc, 1u);               // + A_hi W_lo (lo x lo is below the fp32 rounding of the sum)
+                } else {
+                    tc::mma_bf16_ss(tmem, a0, b0, idesc, i > 0 ? 1u : 0u);
+                    tc::mma_bf16_ss(tmem, a1, b0, idesc, 1u);
+                    tc::mma_bf16_ss(tmem, a0, b1, idesc, 1u);
+                }
+                tc::mma_commit(&m.empty[st]);
             }
-            tc::mma_commit(&m.empty[st]);
             ++it;
         }
-        tc::mma_commit(m.acc_done);
+        if (tc::elect_one()) tc::mma_commit(m.acc_done);
         WS_TRACE(4);
     }
     // the last GVP's gates
@@ -1236,9 +1243,10 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
     if (warp >= C::NW) {
         if (ASYNC) { ws::control_setup<C>(m); tmem = *m.tmem_slot; }
         if (warp == C::NW) {
-            if (lane == 0) {
+            if constexpr (C::KS) {
+                ws::issue_ks<C>(a.msg, L.n_msg, m, tmem);       // the whole (converged) warp: see tc::elect_one()
+            } else if (lane == 0) {
                 if (C::CL == 2 && m.rank != 0) ws::relay<C>(a.msg, L.n_msg, m);
-                else if constexpr (C::KS) ws::issue_ks<C>(a.msg, L.n_msg, m, tmem);
                 else ws::issue<C>(a.msg, L.n_msg, m, tmem);
             } else if (lane == 1 && C::CL == 2 && m.rank != 0 && !dead) {
                 ws::forward_ready<C>(L.n_msg, m);

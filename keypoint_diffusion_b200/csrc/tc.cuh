@@ -102,6 +102,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of a CONVERGED warp.  The MMA-issuing warp runs its whole loop with all 32 lanes (barrier waits, descriptor
+// arithmetic: warp-uniform values that ptxas keeps in uniform registers) and lets one elected lane execute the tcgen05
+// instructions: issued from inside `if (lane == 0)` instead, every UTCHMMA is wrapped in a waterfall loop with
+// R2UR moves, and the instruction stream of that single lane bounds the k-step rate
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
+}
+
 // ------------------------------------------------------------------ descriptors
 // shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
