@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                 }
         }
     } else if (warp == NW) {
-        // ---- MMA issuer
-        if (lane == 0) {
+        // ---- MMA issuer: the whole (converged) warp runs the loop, one elected lane executes the tcgen05 instructions
+        //      (tc::elect_one(): descriptors stay in uniform registers, no waterfall loop around every UTCHMMA)
+        {
             const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NB);
             const uint32_t b_k = (NB / 8) * 128, slab1 = 2 * b_k;
             uint32_t it = 0;
@@ -168,11 +169,14 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                     tc::fence_after_sync();
                     const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * C::SLAB);
                     const uint64_t ad = tc::make_smem_desc(tc::smem_u32(m.A[br] + (size_t)2 * j * C::KCS), C::KCS, 128);
-                    tc::mma_bf16_ss(tmem + 256 * br, ad, tc::make_smem_desc(bs, b_k, 128), idesc, j > 0 ? 1u : 0u);
-                    tc::mma_bf16_ss(tmem + 256 * br, ad, tc::make_smem_desc(bs + slab1, b_k, 128), idesc, 1u);
-                    tc::mma_commit(&m.empty[st]);
+                    const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
+                    if (tc::elect_one()) {
+                        tc::mma_bf16_ss(tmem + 256 * br, ad, b0, idesc, j > 0 ? 1u : 0u);
+                        tc::mma_bf16_ss(tmem + 256 * br, ad, b1, idesc, 1u);
+                        tc::mma_commit(&m.empty[st]);
+                    }
                 }
-                tc::mma_commit(&m.acc_done[br]);
+                if (tc::elect_one()) tc::mma_commit(&m.acc_done[br]);
             }
         }
     } else {

@@ -296,6 +296,10 @@ __device__ __forceinline__ void wait_ready(uint64_t* bar, uint32_t parity) {    
 #endif
     tc::mbar_wait(bar, parity);
 }
+// Called by the WHOLE issuing warp when C::CL == 1 (one elected lane executes the tcgen05 instructions, tc::elect_one())
+// and by lane 0 only in the CTA-pair configuration.
+template <class C>
+__device__ __forceinline__ bool issuing_lane() { if constexpr (C::CL == 1) return tc::elect_one(); else return true; }
 template <class C>
 __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_t tmem) {
     uint32_t it = 0;
@@ -337,18 +341,22 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
             const uint32_t bs = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
             const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
             const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128);
-            if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
-            else tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
-            if (C::STACK) {         // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
-                const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
-                if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b1, idesc, 1u);
-                else tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
+            const uint64_t b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
+            if (issuing_lane<C>()) {
+                if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
+                else tc::mma_bf16_ss(acc, a0, b0, idesc, i > 0 ? 1u : 0u);
+                if (C::STACK) {     // [A_hi; A_lo] x W_lo: with the MMA above all four hi/lo products in two instructions
+                    if (PAIR) tc::mma_bf16_ss_pair(acc, a0, b1, idesc, 1u);
+                    else tc::mma_bf16_ss(acc, a0, b1, idesc, 1u);
+                }
+                if (PAIR) tc::mma_commit_pair(&m.empty[st], 3);       // frees the slot in both CTAs
+                else tc::mma_commit(&m.empty[st]);
             }
-            if (PAIR) tc::mma_commit_pair(&m.empty[st], 3);       // frees the slot in both CTAs
-            else tc::mma_commit(&m.empty[st]);
         }
-        if (PAIR) tc::mma_commit_pair(m.acc_done, 3);
-        else tc::mma_commit(m.acc_done);
+        if (issuing_lane<C>()) {
+            if (PAIR) tc::mma_commit_pair(m.acc_done, 3);
+            else tc::mma_commit(m.acc_done);
+        }
         WS_TRACE(4);
         if constexpr (C::STACK) {
             // stacked bf16x3: the gates GEMM runs on the warp-level tensor cores straight from the epilogue registers
@@ -376,12 +384,14 @@ __device__ __forceinline__ void issue(const GvpW* gv, int n_gvps, Sm& m, uint32_
                 if ((((16 * j) % cpw) >= hb) != (half == 1)) continue;
                 const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
                 const uint64_t b0 = tc::make_smem_desc(wg + j * (C::NS * 512), 256, 128);
-                tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, gacc);
+                if (issuing_lane<C>()) tc::mma_bf16_ss(tmem + GATE_COL, a0, b0, idg, gacc);
                 gacc = 1u;
             }
         }
-        tc::mma_commit(m.gates_done);
-        tc::mma_commit(&m.wg_empty[g % (C::WGB > 0 ? C::WGB : 1)]);
+        if (issuing_lane<C>()) {
+            tc::mma_commit(m.gates_done);
+            tc::mma_commit(&m.wg_empty[g % (C::WGB > 0 ? C::WGB : 1)]);
+        }
         WS_TRACE(6);
     }
 #ifdef KPD_WS_TRACE
@@ -1245,6 +1255,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_edge_ws_kernel(const __grid_cons
         if (warp == C::NW) {
             if constexpr (C::KS) {
                 ws::issue_ks<C>(a.msg, L.n_msg, m, tmem);       // the whole (converged) warp: see tc::elect_one()
+            } else if (C::CL == 1) {
+                ws::issue<C>(a.msg, L.n_msg, m, tmem);          // whole warp
             } else if (lane == 0) {
                 if (C::CL == 2 && m.rank != 0) ws::relay<C>(a.msg, L.n_msg, m);
                 else ws::issue<C>(a.msg, L.n_msg, m, tmem);
@@ -1612,7 +1624,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) ws::issue<C>(a.upd, a.n_upd, m, tmem);
+        if (C::CL == 1 || lane == 0) ws::issue<C>(a.upd, a.n_upd, m, tmem);      // (CL == 1: the whole warp, see issue())
     } else if (warp == C::NW + 1) {
         if (lane == 0) ws::produce<C>(a.upd, a.n_upd, m, dead);
     } else if (!dead) {
@@ -1836,7 +1848,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sd = a.Sdim, Vd = a.Vdim;
     if (warp == C::NW) {
-        if (lane == 0) ws::issue<C>(a.g, a.n_gvps, m, tmem);
+        if (C::CL == 1 || lane == 0) ws::issue<C>(a.g, a.n_gvps, m, tmem);
     } else if (warp == C::NW + 1) {
         if (lane == 0) ws::produce<C>(a.g, a.n_gvps, m, dead);
     } else if (!dead) {

@@ -78,8 +78,9 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
             }
         }
     } else if (warp == TCG_EW) {
-        // ---- MMA issuer: accumulator bi % 2, so that the epilogue of one block overlaps the MMAs of the next
-        if (lane == 0) {
+        // ---- MMA issuer: accumulator bi % 2, so that the epilogue of one block overlaps the MMAs of the next.  The whole
+        //      (converged) warp runs the loop, one elected lane executes the tcgen05 instructions (tc::elect_one())
+        {
             tc::mbar_wait(a_ready, 0);
             tc::fence_after_sync();
             uint32_t it = 0;
@@ -94,11 +95,14 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                     tc::fence_after_sync();
                     const uint64_t adesc = tc::make_smem_desc(tc::smem_u32(a_s + (size_t)2 * j * C::KCS), C::KCS, 128);
                     const uint32_t bs = tc::smem_u32(b_s + (size_t)st * slab_stride);
-                    tc::mma_bf16_ss(tmem_base + 256 * buf, adesc, tc::make_smem_desc(bs, b_k, 128), idesc, j > 0 ? 1u : 0u);
-                    if (NS == 2) tc::mma_bf16_ss(tmem_base + 256 * buf, adesc, tc::make_smem_desc(bs + slab1, b_k, 128), idesc, 1u);
-                    tc::mma_commit(&empty[st]);
+                    const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
+                    if (tc::elect_one()) {
+                        tc::mma_bf16_ss(tmem_base + 256 * buf, adesc, b0, idesc, j > 0 ? 1u : 0u);
+                        if (NS == 2) tc::mma_bf16_ss(tmem_base + 256 * buf, adesc, b1, idesc, 1u);
+                        tc::mma_commit(&empty[st]);
+                    }
                 }
-                tc::mma_commit(&acc_done[buf]);
+                if (tc::elect_one()) tc::mma_commit(&acc_done[buf]);
             }
         }
     } else {
