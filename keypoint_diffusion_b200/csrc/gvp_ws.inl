@@ -246,10 +246,18 @@ __device__ __forceinline__ void produce(const GvpW* gv, int n_gvps, Sm& m, bool 
             // shared-memory image of this GVP's small fp32 weights: Wh | Wu into the single buffer once the vector warps
             // are through the previous GVP's Vu GEMM, bf | bg into the buffer of this GVP's parity
             if (g > 0) tc::mbar_wait(m.wsm_empty, (g - 1) & 1);
-            const float* img = C::NS == 2 ? w.wsmP2 : w.wsmP;
-            tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)(C::WSM * sizeof(float)));
-            tc::bulk_g2s(m.wsm, img, C::WSM_W * sizeof(float), m.wsm_full);
-            tc::bulk_g2s(m.bias + (g & 1) * C::WSM_B, img + C::WSM_W, C::WSM_B * sizeof(float), m.wsm_full);
+            if constexpr (C::NS == 2) {
+                // bf16x3: the plain fp32 image for the FP32-pipe vector GEMMs (vec_fma); it follows the fragment image
+                const float* img = w.wsmP2 + C::WSM;
+                tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)((WSM_KS_W + C::WSM_B) * sizeof(float)));
+                tc::bulk_g2s(m.wsm, img, WSM_KS_W * sizeof(float), m.wsm_full);
+                tc::bulk_g2s(m.bias + (g & 1) * C::WSM_B, img + WSM_KS_W, C::WSM_B * sizeof(float), m.wsm_full);
+            } else {
+                const float* img = w.wsmP;
+                tc::mbar_arrive_expect_tx(m.wsm_full, (uint32_t)(C::WSM * sizeof(float)));
+                tc::bulk_g2s(m.wsm, img, C::WSM_W * sizeof(float), m.wsm_full);
+                tc::bulk_g2s(m.bias + (g & 1) * C::WSM_B, img + C::WSM_W, C::WSM_B * sizeof(float), m.wsm_full);
+            }
         }
         for (int i = 0; i < ksf; ++i, ++it) {
             const int j = kstep_at<C>(i, w.fin >> 4, g > 0);
@@ -936,7 +944,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
                                          int rows_valid, int tb, bool last = true) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* Wh_s = m.wsm;
-    const float* Wu_s = Wh_s + (C::KS ? 24 * WH_LD_KS : C::NS * WH_SZ);
+    const float* Wu_s = Wh_s + (C::NS == 2 ? 24 * WH_LD_KS : C::NS * WH_SZ);
     const float* bf_s = m.bias + (gi & 1) * C::WSM_B;
     const float* bg_s = bf_s + 256;
     const int NBf = (g.fout + 15) & ~15;
@@ -951,7 +959,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     [[maybe_unused]] float gD[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};     // bf16x3: this warp's partial gates
     const bool vecw = warp < C::NWV;          // (warp-uniform) this warp owns vector rows
     if (vecw) {
-    if constexpr (C::KS) vec_fma<WH_LD_KS, 3>(v.x, vh, Wh_s, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
+    if constexpr (C::NS == 2) vec_fma<WH_LD_KS, 3>(v.x, vh, Wh_s, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
     else vec_gemm<C::NS, WH_LD, 3>(v.x, vh, Wh_s, WH_SZ, g.vin > 16 ? 3 : 2, g.hd > 16, lane);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -975,7 +983,7 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
     WS_TRACE(11);
     // b. Vu = Vh^T Wu (gvp.py:97), while the tensor core finishes the feats GEMM
     if (vecw) {
-        if constexpr (C::KS) vec_fma<WU_LD_KS, 2>(vh, vu, Wu_s, g.hd > 16 ? 3 : 2, true, lane);
+        if constexpr (C::NS == 2) vec_fma<WU_LD_KS, 2>(vh, vu, Wu_s, g.hd > 16 ? 3 : 2, true, lane);
         else vec_gemm<C::NS, WU_LD, 2>(vh, vu, Wu_s, WU_SZ, g.hd > 16 ? 3 : 2, true, lane);
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(m.wsm_empty);     // Wh | Wu may be overwritten with the next GVP's
