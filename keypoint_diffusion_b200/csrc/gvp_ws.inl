@@ -49,7 +49,7 @@ constexpr int VS_LD = 52;                                   // fp32 vector stagi
 constexpr int GATE_LD = 20;                                 // gates staged as [R][20]
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t GATE_COL = 256;
-// KS edge kernel: accumulator [0, 256) | gates accumulator [256, 288) | hi plane of feats_out as the next GVP's A operand
+// KS edge kernel: accumulator [0, 256) | gates accumulator [256, 272) | hi plane of feats_out as the next GVP's A operand
 // (bf16 pairs: column 320 + k / 2) [320, 448)
 constexpr uint32_t KS_A_COL = 320;
 
@@ -483,13 +483,13 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
     // does); with A from TMEM only the 8 KB of B remain.  Two of the three MMAs of a k-step, and one of the two of a
     // gates k-step, read A_hi.
     // gates GEMM of GVP gp over the slot `st` that holds its weight, the k-steps of one half of every column group
-    // (which = 0 / 1): feats_out (hi, lo planes) x [Wg_hi ; Wg_lo] into TMEM columns [GATE_COL, GATE_COL + 32)
+    // (which = 0 / 1): feats_out (hi, lo planes) x Wg (hi, lo) into TMEM columns [GATE_COL, GATE_COL + 16)
     auto gates = [&](int gp, uint32_t st, int which) {
         const GvpW& w = gv[gp];
         const int ksg = ((w.fout + 15) & ~15) >> 4;
         const bool a_tmem = gp < n_gvps - 1;
         const uint32_t wg = tc::smem_u32(m.ring + (size_t)st * SLOT<C>);
-        const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16), idg32 = tc::make_idesc_bf16(C::MMA_M, 32);
+        const uint32_t idg = tc::make_idesc_bf16(C::MMA_M, 16);
         const uint32_t gcol = tmem + GATE_COL;
         int k = 0;
         for (int half = 0; half < 2; ++half)
@@ -497,15 +497,21 @@ __device__ __forceinline__ void issue_ks(const GvpW* gv, int n_gvps, Sm& m, uint
                 if (gates_first_half<C>(j) != (half == 0)) continue;
                 if (which != half) { ++k; continue; }
                 const uint64_t a1 = tc::make_smem_desc(tc::smem_u32(m.A[1] + (size_t)2 * j * C::KCS), C::KCS, 128);
-                // B = [Wg_hi ; Wg_lo] stacked along N (32 rows, pack.pack_gates_ks): A_hi x B gives hi x hi in columns
-                // [0, 16) and hi x lo in [16, 32) with ONE pass over A_hi; A_lo x Wg_hi (the first 16 rows of the same
-                // image) adds to [0, 16).  Epilogue 2 sums the two column groups.
-                const uint64_t b32 = tc::make_smem_desc(wg + k * 1024, 512, 128);
+                // three small MMAs per k-step: A_hi Wg_hi + A_hi Wg_lo (A_hi from tensor memory when another GVP follows) +
+                // A_lo Wg_hi.  (Stacking [Wg_hi ; Wg_lo] along N -- two MMAs per k-step, the epilogue summing two column
+                // groups -- left the gates GEMM no faster and made the epilogue's TMEM load of the gates ~1.7k cycles
+                // slower: measured, reverted.)
+                const uint64_t b0 = tc::make_smem_desc(wg + k * 1024, 256, 128), b1 = tc::make_smem_desc(wg + k * 1024 + 512, 256, 128);
                 const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(m.A[0] + (size_t)2 * j * C::KCS), C::KCS, 128);
                 if (tc::elect_one()) {
-                    if (a_tmem) tc::mma_bf16_ts(gcol, tmem + KS_A_COL + 8 * j, b32, idg32, k == 0 ? 0u : 1u);
-                    else tc::mma_bf16_ss(gcol, a0, b32, idg32, k == 0 ? 0u : 1u);
-                    tc::mma_bf16_ss(gcol, a1, b32, idg, 1u);    // (dropping the W_lo term of the gates misses the 1e-4 bar: measured)
+                    if (a_tmem) {
+                        tc::mma_bf16_ts(gcol, tmem + KS_A_COL + 8 * j, b0, idg, k == 0 ? 0u : 1u);
+                        tc::mma_bf16_ts(gcol, tmem + KS_A_COL + 8 * j, b1, idg, 1u);    // (dropping the W_lo term misses the 1e-4 bar: measured)
+                    } else {
+                        tc::mma_bf16_ss(gcol, a0, b0, idg, k == 0 ? 0u : 1u);
+                        tc::mma_bf16_ss(gcol, a0, b1, idg, 1u);
+                    }
+                    tc::mma_bf16_ss(gcol, a1, b0, idg, 1u);
                 }
                 ++k;
             }
@@ -1088,24 +1094,15 @@ __device__ __forceinline__ void gvp_simt(const GvpW& g, int gi, const Sm& m, uin
         TC_T(t5);
         {
             const int sub = warp >> 2;                       // which 8 rows of the warp's TMEM lane quarter
-            uint32_t gv[16];
-            // (the gates accumulator, issue_ks(): the hi x hi + lo x hi products in its columns [0, 16), the hi x lo products
-            // in [16, 32))
-            {
-                const uint32_t ga = tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + GATE_COL;
-                uint32_t g0[8], g1[8];
-                tc::tmem_ld_16x256b_x2(ga, g0);
-                tc::tmem_ld_16x256b_x2(ga + 16, g1);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { gv[i] = g0[i]; gv[8 + i] = g1[i]; }
-            }
+            uint32_t gv[8];
+            tc::tmem_ld_16x256b_x2(tmem + ((uint32_t)(32 * q + 16 * (sub >> 1)) << 16) + GATE_COL, gv);
+            tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int u = 8 * j + 2 * L.t;
                 const int o = (sub & 1) ? 2 : 0;
-                float a0 = __uint_as_float(gv[4 * j + o]) + __uint_as_float(gv[4 * (j + 2) + o]) + bg_s[u];
-                float a1 = __uint_as_float(gv[4 * j + o + 1]) + __uint_as_float(gv[4 * (j + 2) + o + 1]) + bg_s[u + 1];
+                float a0 = __uint_as_float(gv[4 * j + o]) + bg_s[u];
+                float a1 = __uint_as_float(gv[4 * j + o + 1]) + bg_s[u + 1];
                 if (g.sigmoid_gate) { a0 = sigmoid_acc(a0); a1 = sigmoid_acc(a1); }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { v.x[c][j][0] = vu[c][j][0] * a0; v.x[c][j][1] = vu[c][j][1] * a1; }

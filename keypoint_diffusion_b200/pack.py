@@ -327,16 +327,11 @@ def pack_gvp_tc(sd: Dict[str, torch.Tensor], *, n_convs, update_kp, n_message_gv
 
 
 def pack_gates_ks(wg: torch.Tensor, n_col_groups: int = 4) -> torch.Tensor:
-    """scalar_to_vector_gates.weight [vout <= 16, fout] for the KS edge kernel (csrc/gvp_ws.inl issue_ks): hi = bf16(W) and
-    lo = bf16(W - hi) STACKED along N into one 32-row B operand ([hi rows 0-15 ; lo rows 0-15]), as tcgen05 k-step slabs
-    (1 KB per k-step), with the k-steps over the FIRST halves of the epilogue's column groups (256 / n_col_groups columns
-    each) first: the issuer runs those as soon as epilogue 1 is half way."""
-    w = wg.detach().float().cpu()
-    vout, fout = w.shape
-    full = torch.zeros(16, fout)
-    full[:vout] = w
-    hi = full.to(torch.bfloat16).float()
-    slabs = pack_tc_weight(torch.cat([hi, full - hi]), False).view(-1, 512)     # [ks][512 bf16 = 1 KB], both planes exact in bf16
+    """scalar_to_vector_gates.weight for the KS edge kernel (csrc/gvp_ws.inl issue_ks): the (hi, lo) tcgen05 k-step slabs
+    of pack_tc_weight(split=True) -- 512 B hi + 512 B lo per k-step -- reordered so that the k-steps over the FIRST halves of
+    the epilogue's column groups (256 / n_col_groups columns each) come first: the issuer runs those as soon as epilogue 1
+    is half way."""
+    slabs = pack_tc_weight(wg, True).view(-1, 512)          # [ks][512 bf16 = 1 KB]
     cpw = 256 // n_col_groups
     first = [j for j in range(slabs.shape[0]) if (16 * j) % cpw < cpw // 2]
     rest = [j for j in range(slabs.shape[0]) if j not in first]
