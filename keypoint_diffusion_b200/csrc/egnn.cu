@@ -429,7 +429,8 @@ extern "C" int kpd_egnn_attach_tc(kpd_egnn_model* m, const void* tc_blob, const 
             for (int br = 0; br < 2; ++br) L.W2P[e][br] = static_cast<const uint4*>(P());
         for (int nt = 0; nt < m->n_upd; ++nt) { L.Wn1P[nt] = P(); L.Wn2P[nt] = P(); }
     }
-    cudaError_t e = cudaFuncSetAttribute(egnn_edge_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->edge_smem_ws);
+    cudaError_t e = cudaFuncSetAttribute(egnn_edge_ws_kernel<257>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->edge_smem_ws);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(egnn_edge_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->edge_smem_ws);
     KPD_REQUIRE(e == cudaSuccess, "kpd_egnn_attach_tc: cannot set %zu B shared memory: %s", m->edge_smem_ws, cudaGetErrorString(e));
     m->tc2_ready = true;
     return 0;
@@ -563,7 +564,9 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             for (int e = 0; e < m->n_et; ++e)
                 for (int br = 0; br < 2; ++br) WL.t[e].W2P[br] = W.W2P[e][br];
             for (int e = 0; e < 4; ++e) WL.tile_off[e + 1] = WL.tile_off[e] + (e < m->n_et ? cdiv(caps[e] > 0 ? caps[e] : 1, egws::R) : 0);
-            egnn_edge_ws_kernel<<<dim3(WL.tile_off[4]), egws::NT, m->edge_smem_ws, st>>>(WL);
+            // (the constants the kernel derives from HS = 257 are exactly what this function passes for H = 257)
+            if (H == 257) egnn_edge_ws_kernel<257><<<dim3(WL.tile_off[4]), egws::NT, m->edge_smem_ws, st>>>(WL);
+            else egnn_edge_ws_kernel<0><<<dim3(WL.tile_off[4]), egws::NT, m->edge_smem_ws, st>>>(WL);
             KPD_TRY(check_launch("egnn_edge_ws_kernel"));
         } else {
             egnn_edge_kernel<<<dim3(max_tiles, m->n_et), NT, m->edge_smem, st>>>(L);

@@ -91,6 +91,41 @@ struct EgnnWsLaunch {
     int tile_off[5];            // 1-D grid: CTAs [tile_off[e], tile_off[e+1]) are the tiles of edge type e (at capacity)
 };
 
+namespace egws {
+// A pair of tile rows of first-layer products in flight (registers): the P_src chunks of both rows and the P_dst chunks --
+// the second row's only when its destination differs from the first's (the tile is dst-sorted: 19 ll edges per atom)
+struct RowPair { float4 u[2][2], w[2][2]; float ut[2], wt[2]; };
+// issue the loads of rows 2 P and 2 P + 1 of this warp for branch br (lane = 8-feature chunk; ntail leftover features)
+template <int P>
+__device__ __forceinline__ void load_pair(const EgnnEtypeArgs& a, int Hp, int br, const int (&rs)[R / NW], const int (&rd)[R / NW],
+                                          int lane, int nfull, int ntail, RowPair& q) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * P + jj;
+        const float* ps = a.Ps + (size_t)rs[j] * a.ldps + (a.slot_s + br) * Hp;
+        const float* pd = a.Pd + (size_t)rd[j] * a.ldpd + (a.slot_d + br) * Hp;
+        const bool need_d = jj == 0 || rd[j] != rd[jj == 0 ? j : j - 1];       // (warp-uniform)
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        q.u[jj][0] = q.u[jj][1] = q.w[jj][0] = q.w[jj][1] = z;
+        if (lane < nfull) {
+            q.u[jj][0] = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane));
+            q.u[jj][1] = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane + 4));
+            if (need_d) {
+                q.w[jj][0] = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane));
+                q.w[jj][1] = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane + 4));
+            }
+        }
+        q.ut[jj] = lane < ntail ? __ldg(ps + 8 * nfull + lane) : 0.f;
+        q.wt[jj] = (need_d && lane < ntail) ? __ldg(pd + 8 * nfull + lane) : 0.f;
+    }
+}
+}  // namespace egws
+
+// HS: the hidden width H = hidden_nf + 1 as a compile-time constant (257 for every shipped model: 32 full chunks, one
+// leftover feature, one leftover output column), or 0 for run-time widths.  With run-time widths every row of build A
+// carried the dot products, shuffle reductions and predicates of three possible leftover columns: 260 instructions per
+// row and lane for 8 features.
+template <int HS>
 __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_constant__ EgnnWsLaunch W) {
     using namespace egws;
     const EgnnEdgeLaunch& L = W.L;
@@ -108,15 +143,28 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         const int e = min(tile_begin + (int)threadIdx.x, max(a.cap, 1) - 1);
         my_s = __ldg(a.src + e); my_d = __ldg(a.dst + e);
     }
+    // ... and the (source, destination) of the RPW rows every SIMT warp builds: warp-uniform addresses, one broadcast
+    // transaction each, so that the gathers of the first-layer products can be issued before anything else
+    constexpr int RPW = R / NW;
+    int rs[RPW], rd[RPW];
+    if ((int)(threadIdx.x >> 5) < NW) {
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const int e = min(tile_begin + (int)(threadIdx.x >> 5) * RPW + j, max(a.cap, 1) - 1);
+            rs[j] = __ldg(a.src + e); rd[j] = __ldg(a.dst + e);
+        }
+    }
     const int E = a.rowptr[a.n_dst];
     if (tile_begin >= E) return;
     const int n = min(R, E - tile_begin);
     extern __shared__ __align__(128) unsigned char smem_eg[];
     TC_T(g0);
-    Sm m = carve(smem_eg, W.kch);
+    const int kch = HS ? 2 * ((HS + 15) / 16) : W.kch;
+    Sm m = carve(smem_eg, kch);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int H = L.H, Hp = L.Hp, nmain = L.nmain, nlo = L.nlo;
-    const int ksteps = W.kch >> 1;
+    const int H = HS ? HS : L.H, Hp = HS ? ((HS + 3) & ~3) : L.Hp, nmain = HS ? (HS < 256 ? HS : 256) & ~3 : L.nmain;
+    const int nlo = HS ? HS - ((HS < 256 ? HS : 256) & ~3) : L.nlo;
+    const int ksteps = kch >> 1;
     const int NB = (nmain + 15) & ~15;
 
     // asynchronous set-up: the control warps initialise the barriers and TMEM and start streaming weights at once; the
@@ -145,6 +193,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         if (lane == 0) {
             const uint32_t slab = C::NS * 2 * (NB / 8) * 128;
             uint32_t it = 0;
+#pragma unroll
             for (int br = 0; br < 2; ++br)
                 for (int j = 0; j < ksteps; ++j, ++it) {
                     const uint32_t st = it % C::STAGES;
@@ -160,6 +209,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
             const uint32_t idesc = tc::make_idesc_bf16(C::MMA_M, NB);
             const uint32_t b_k = (NB / 8) * 128, slab1 = 2 * b_k;
             uint32_t it = 0;
+#pragma unroll
             for (int br = 0; br < 2; ++br) {
                 tc::mbar_wait(&m.a_ready[br], 0);
                 tc::fence_after_sync();
@@ -183,27 +233,73 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         // ---- SIMT warps
         TC_T(g1);
         long long gt[8];
-        // per-etype vectors -> shared memory; indices + geometry (models/dynamics.py:160, :211, :169)
-        for (int i = tid; i < 2 * Hp; i += NT_SIMT) {
-            const int br = i / Hp, k = i - br * Hp;
-            m.w1c[br][k] = a.w1c[br][k];
-            m.b2[br][k] = a.b2[br][k];
-            m.wv[br][k] = br == 0 ? a.watt[k] : a.w3c[k];
-            for (int c = 0; c < 3; ++c) m.w2lo[br][c * VEC_LD + k] = c < nlo ? a.W2lo[br][c * Hp + k] : 0.f;
+        // Row pairs of first-layer products in flight (registers): P_src chunks of both rows, P_dst chunks (the second row's
+        // only when its destination differs: the tile is dst-sorted, 19 ll edges per ligand atom).  The kernel is bound by
+        // the latency of these L2 gathers (225 KB of shared memory leave no L1), so they are issued as early as their
+        // addresses exist -- branch 0 before the tile set-up below, branch 1 behind the rows of branch 0 as those are
+        // consumed -- and added only where they are used.
+        const int nfull = H >> 3, ntail = H & 7;       // full 8-feature chunks (one per lane: H <= 263) and leftover features
+        if (n < R) {        // last tile of the edge type: rows >= n replicate the last valid edge
+            const int sl = __ldg(a.src + tile_begin + n - 1), dl = __ldg(a.dst + tile_begin + n - 1);
+#pragma unroll
+            for (int j = 0; j < RPW; ++j)
+                if (warp * RPW + j >= n) { rs[j] = sl; rd[j] = dl; }
+            if (tid >= n && tid < R) { my_s = sl; my_d = dl; }
+        }
+        // Set-up loads first (they only need this thread's own edge, fetched at the top): the per-etype vectors and the
+        // geometry (models/dynamics.py:160, :211, :169) -- then the gathers, whose row indices have arrived meanwhile -- and
+        // only then the stores that wait for the set-up loads: one exposed L2 round trip instead of three.
+        // (2 Hp <= 528 items over 512 threads: both rounds' loads are issued together.)
+        static_assert(2 * VEC_LD <= 2 * NT_SIMT, "vector staging: two items per thread");
+        float sv[2][6];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = tid + u * NT_SIMT;
+            if (i < 2 * Hp) {
+                const int br = i / Hp, k = i - br * Hp;
+                sv[u][0] = a.w1c[br][k];
+                sv[u][1] = a.b2[br][k];
+                sv[u][2] = br == 0 ? a.watt[k] : a.w3c[k];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sv[u][3 + c] = c < nlo ? a.W2lo[br][c * Hp + k] : 0.f;
+            }
+        }
+        int rp0 = 0, rp1 = 0;
+        float gx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (tid < R) {              // (rows >= n replicate the last valid edge, see above)
+            rp0 = a.rowptr[my_d]; rp1 = a.rowptr[my_d + 1];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { gx[c] = a.xs[3 * my_s + c]; gx[3 + c] = a.xd[3 * my_d + c]; }
+        }
+        egws::RowPair q0, q1;
+        egws::load_pair<0>(a, Hp, 0, rs, rd, lane, nfull, ntail, q0);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = tid + u * NT_SIMT;
+            if (i < 2 * Hp) {
+                const int br = i / Hp, k = i - br * Hp;
+                // (carve(): w1c | b2 | wv of branch 0, then of branch 1, VEC_LD floats each; w2lo[br] = [3][VEC_LD].  No dynamic
+                // index into the Sm arrays: that would put the whole struct into local memory, an L2 round trip per use)
+                float* vb = m.w1c[0] + br * 3 * VEC_LD + k;
+                vb[0] = sv[u][0];
+                vb[VEC_LD] = sv[u][1];
+                vb[2 * VEC_LD] = sv[u][2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) m.w2lo[0][(br * 3 + c) * VEC_LD + k] = sv[u][3 + c];
+            }
         }
         if (tid < R) {
-            int s = my_s, d = my_d;
-            if (tid >= n) { s = a.src[tile_begin + n - 1]; d = a.dst[tile_begin + n - 1]; }     // rows >= n replicate the last valid edge
-            m.src_s[tid] = s;
-            m.dst_s[tid] = d;
-            m.rp[2 * tid] = a.rowptr[d];
-            m.rp[2 * tid + 1] = a.rowptr[d + 1];
-            const float dx = a.xs[3 * s] - a.xd[3 * d], dy = a.xs[3 * s + 1] - a.xd[3 * d + 1], dz = a.xs[3 * s + 2] - a.xd[3 * d + 2];
+            m.src_s[tid] = my_s;
+            m.dst_s[tid] = my_d;
+            m.rp[2 * tid] = rp0;
+            m.rp[2 * tid + 1] = rp1;
+            const float dx = gx[0] - gx[3], dy = gx[1] - gx[4], dz = gx[2] - gx[5];
             const float dij = sqrtf(dx * dx + dy * dy + dz * dz);
             m.dij[tid] = dij;
             const float inv = 1.0f / (dij + 1.0f);
             m.xsc[3 * tid] = dx * inv; m.xsc[3 * tid + 1] = dy * inv; m.xsc[3 * tid + 2] = dz * inv;
         }
+        egws::load_pair<1>(a, Hp, 0, rs, rd, lane, nfull, ntail, q1);       // (behind the stores: their registers are free now)
         simt_bar();
         // segment table of the dst-sorted tile (as ws::build_segments)
         {
@@ -229,107 +325,104 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         }
         // ---- 1. both branches: first Linear (factorised) + SiLU -> A[br]; leftover output columns as fp32 dots
         TC_T(g2);
-        const int nfull = H >> 3, ntail = H & 7;       // full 8-feature chunks (one per lane: H <= 263) and leftover features
-        for (int br = 0; br < 2; ++br) {
-            // all 8 rows of the warp in one batch: every load of the batch is in flight together
-            constexpr int RPW = R / NW;
-            float v[RPW][8], vt[RPW];
-            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-            float wt = 0.f;
-#pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int r = warp * RPW + j;
-                const float* ps = a.Ps + (size_t)m.src_s[r] * a.ldps + (a.slot_s + br) * Hp;
-                const float* pd = a.Pd + (size_t)m.dst_s[r] * a.ldpd + (a.slot_d + br) * Hp;
-                // the tile is dst-sorted: consecutive rows mostly share their destination (19 ll edges per ligand atom), so
-                // the destination's row of first-layer products is fetched once per RUN inside the warp's rows, not per edge
-                const bool same = j > 0 && m.dst_s[r] == m.dst_s[r - 1];       // (warp-uniform)
-                if (!same) {
-                    if (lane < nfull) {
-                        w0 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane));
-                        w1 = __ldg(reinterpret_cast<const float4*>(pd + 8 * lane + 4));
-                    }
-                    wt = lane < ntail ? __ldg(pd + 8 * nfull + lane) : 0.f;
-                }
-                if (lane < nfull) {
-                    const float4 u0 = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane)), u1 = __ldg(reinterpret_cast<const float4*>(ps + 8 * lane + 4));
-                    v[j][0] = u0.x + w0.x; v[j][1] = u0.y + w0.y; v[j][2] = u0.z + w0.z; v[j][3] = u0.w + w0.w;
-                    v[j][4] = u1.x + w1.x; v[j][5] = u1.y + w1.y; v[j][6] = u1.z + w1.z; v[j][7] = u1.w + w1.w;
-                }
-                vt[j] = lane < ntail ? __ldg(ps + 8 * nfull + lane) + wt : 0.f;
-            }
+        static_assert(RPW == 4, "build A: two row pairs per warp");
+        // one row: v = P_src + P_dst chunk of this lane (8 features), vt = its leftover feature
+        auto build_row = [&](int br, int r, float (&v)[8], float vt) __attribute__((always_inline)) {
             const float* w1c = m.w1c[br];
             const float* w2lo = m.w2lo[br];
             unsigned char* Ab = m.A[br];
-#pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int r = warp * RPW + j;
-                const float d = m.dij[r];
-                const uint32_t rof = ws::row_off<C>(r);
-                float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
-                if (lane < nfull) {
-                    const float4 wa = *reinterpret_cast<const float4*>(w1c + 8 * lane), wb = *reinterpret_cast<const float4*>(w1c + 8 * lane + 4);
-                    float f[8];
-                    f[0] = ws::silu_acc(fmaf(wa.x, d, v[j][0])); f[1] = ws::silu_acc(fmaf(wa.y, d, v[j][1]));
-                    f[2] = ws::silu_acc(fmaf(wa.z, d, v[j][2])); f[3] = ws::silu_acc(fmaf(wa.w, d, v[j][3]));
-                    f[4] = ws::silu_acc(fmaf(wb.x, d, v[j][4])); f[5] = ws::silu_acc(fmaf(wb.y, d, v[j][5]));
-                    f[6] = ws::silu_acc(fmaf(wb.z, d, v[j][6])); f[7] = ws::silu_acc(fmaf(wb.w, d, v[j][7]));
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        if (cc < nlo) {
-                            const float4 la = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane);
-                            const float4 lb = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane + 4);
-                            const float t = f[0] * la.x + f[1] * la.y + f[2] * la.z + f[3] * la.w + f[4] * lb.x + f[5] * lb.y + f[6] * lb.z + f[7] * lb.w;
-                            if (cc == 0) dot0 = t; else if (cc == 1) dot1 = t; else dot2 = t;
-                        }
-                    }
-                    uint4 hi, lo;
-                    ws::split8(f, hi, lo);
-                    const uint32_t off = (uint32_t)(lane * C::KCS) + rof;
-                    *reinterpret_cast<uint4*>(Ab + off) = hi;
-                    *reinterpret_cast<uint4*>(Ab + off + 256) = lo;
-                }
-                // leftover features (H = 257: feature 256) and the K padding: zero the chunks, then 2-byte stores
-                if (lane < W.kch - nfull) {
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    const uint32_t off = (uint32_t)((nfull + lane) * C::KCS) + rof;
-                    *reinterpret_cast<uint4*>(Ab + off) = z;
-                    *reinterpret_cast<uint4*>(Ab + off + 256) = z;
-                }
-                __syncwarp();
-                if (lane < ntail) {
-                    const int k = 8 * nfull + lane;
-                    const float f = ws::silu_acc(fmaf(w1c[k], d, vt[j]));
-                    const uint32_t off = (uint32_t)((k >> 3) * C::KCS + (k & 7) * 2) + rof;
-                    const __nv_bfloat16 hi = __float2bfloat16(f);
-                    *reinterpret_cast<__nv_bfloat16*>(Ab + off) = hi;
-                    *reinterpret_cast<__nv_bfloat16*>(Ab + off + 256) = __float2bfloat16(f - __bfloat162float(hi));
-                    if (nlo > 0) dot0 = fmaf(f, w2lo[k], dot0);
-                    if (nlo > 1) dot1 = fmaf(f, w2lo[VEC_LD + k], dot1);
-                    if (nlo > 2) dot2 = fmaf(f, w2lo[2 * VEC_LD + k], dot2);
-                }
+            const float d = m.dij[r];
+            const uint32_t rof = ws::row_off<C>(r);
+            float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
+            if (lane < nfull) {
+                const float4 wa = *reinterpret_cast<const float4*>(w1c + 8 * lane), wb = *reinterpret_cast<const float4*>(w1c + 8 * lane + 4);
+                float f[8];
+                f[0] = ws::silu_acc(fmaf(wa.x, d, v[0])); f[1] = ws::silu_acc(fmaf(wa.y, d, v[1]));
+                f[2] = ws::silu_acc(fmaf(wa.z, d, v[2])); f[3] = ws::silu_acc(fmaf(wa.w, d, v[3]));
+                f[4] = ws::silu_acc(fmaf(wb.x, d, v[4])); f[5] = ws::silu_acc(fmaf(wb.y, d, v[5]));
+                f[6] = ws::silu_acc(fmaf(wb.z, d, v[6])); f[7] = ws::silu_acc(fmaf(wb.w, d, v[7]));
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) {
                     if (cc < nlo) {
-                        float sdot = cc == 0 ? dot0 : cc == 1 ? dot1 : dot2;
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
-                        if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(sdot + m.b2[br][nmain + cc]);
+                        const float4 la = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane);
+                        const float4 lb = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane + 4);
+                        const float t = f[0] * la.x + f[1] * la.y + f[2] * la.z + f[3] * la.w + f[4] * lb.x + f[5] * lb.y + f[6] * lb.z + f[7] * lb.w;
+                        if (cc == 0) dot0 = t; else if (cc == 1) dot1 = t; else dot2 = t;
                     }
                 }
+                uint4 hi, lo;
+                ws::split8(f, hi, lo);
+                const uint32_t off = (uint32_t)(lane * C::KCS) + rof;
+                *reinterpret_cast<uint4*>(Ab + off) = hi;
+                *reinterpret_cast<uint4*>(Ab + off + 256) = lo;
             }
-            if (br == 0) {          // first use of an mbarrier / of TMEM: join the control warps' set-up
-                asm volatile("bar.sync 3, %0;" ::"n"(egws::NT) : "memory");
-                tc::fence_after_sync();
-                tmem = *m.tmem_slot;
+            // leftover features (H = 257: feature 256) and the K padding: zero the chunks, then 2-byte stores
+            if (lane < kch - nfull) {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t off = (uint32_t)((nfull + lane) * C::KCS) + rof;
+                *reinterpret_cast<uint4*>(Ab + off) = z;
+                *reinterpret_cast<uint4*>(Ab + off + 256) = z;
             }
-            publish(&m.a_ready[br]);
-            gt[br] = clock64();
-        }
+            __syncwarp();
+            if (lane < ntail) {
+                const int k = 8 * nfull + lane;
+                const float f = ws::silu_acc(fmaf(w1c[k], d, vt));
+                const uint32_t off = (uint32_t)((k >> 3) * C::KCS + (k & 7) * 2) + rof;
+                const __nv_bfloat16 hi = __float2bfloat16(f);
+                *reinterpret_cast<__nv_bfloat16*>(Ab + off) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(Ab + off + 256) = __float2bfloat16(f - __bfloat162float(hi));
+                if (nlo > 0) dot0 = fmaf(f, w2lo[k], dot0);
+                if (nlo > 1) dot1 = fmaf(f, w2lo[VEC_LD + k], dot1);
+                if (nlo > 2) dot2 = fmaf(f, w2lo[2 * VEC_LD + k], dot2);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                if (cc < nlo) {
+                    float sdot = cc == 0 ? dot0 : cc == 1 ? dot1 : dot2;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+                    if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(sdot + m.b2[br][nmain + cc]);
+                }
+            }
+        };
+        auto build_pair = [&](int br, int j0, const egws::RowPair& q) __attribute__((always_inline)) {
+            // (j0 = first row of the pair inside the warp's rows: a literal at every call)
+            {
+                float v[8];
+                v[0] = q.u[0][0].x + q.w[0][0].x; v[1] = q.u[0][0].y + q.w[0][0].y; v[2] = q.u[0][0].z + q.w[0][0].z; v[3] = q.u[0][0].w + q.w[0][0].w;
+                v[4] = q.u[0][1].x + q.w[0][1].x; v[5] = q.u[0][1].y + q.w[0][1].y; v[6] = q.u[0][1].z + q.w[0][1].z; v[7] = q.u[0][1].w + q.w[0][1].w;
+                build_row(br, warp * RPW + j0, v, q.ut[0] + q.wt[0]);
+            }
+            {
+                const bool own_d = rd[j0 + 1] != rd[j0];
+                const float4 w0 = own_d ? q.w[1][0] : q.w[0][0], w1 = own_d ? q.w[1][1] : q.w[0][1];
+                const float wt = own_d ? q.wt[1] : q.wt[0];
+                float v[8];
+                v[0] = q.u[1][0].x + w0.x; v[1] = q.u[1][0].y + w0.y; v[2] = q.u[1][0].z + w0.z; v[3] = q.u[1][0].w + w0.w;
+                v[4] = q.u[1][1].x + w1.x; v[5] = q.u[1][1].y + w1.y; v[6] = q.u[1][1].z + w1.z; v[7] = q.u[1][1].w + w1.w;
+                build_row(br, warp * RPW + j0 + 1, v, q.ut[1] + wt);
+            }
+        };
+        // branch 0, the rows of branch 1 fetched behind it
+        build_pair(0, 0, q0);
+        egws::load_pair<0>(a, Hp, 1, rs, rd, lane, nfull, ntail, q0);
+        build_pair(0, 2, q1);
+        egws::load_pair<1>(a, Hp, 1, rs, rd, lane, nfull, ntail, q1);
+        // first use of an mbarrier / of TMEM: join the control warps' set-up
+        asm volatile("bar.sync 3, %0;" ::"n"(egws::NT) : "memory");
+        tc::fence_after_sync();
+        tmem = *m.tmem_slot;
+        publish(&m.a_ready[0]);
+        gt[0] = clock64();
+        build_pair(1, 0, q0);
+        build_pair(1, 2, q1);
+        publish(&m.a_ready[1]);
+        gt[1] = clock64();
         // ---- 2. per branch: epilogue straight out of TMEM, then the deterministic segmented reduction
         const int q4 = warp & 3, cg = warp >> 2;
         const int ra = 16 * q4 + (lane >> 2), cp = 2 * (lane & 3);
         const uint32_t ro = ws::row_off<C>(ra) + cp * 2;
+#pragma unroll
         for (int br = 0; br < 2; ++br) {
             tc::mbar_wait(&m.acc_done[br], 0);
             tc::fence_after_sync();

@@ -13,7 +13,10 @@
 
 namespace kpd {
 
-constexpr int TCG_STAGES = 4;
+// Weight ring: as many 16 KB (bf16x3) stages as fit beside the A tile, at most TCG_MAX_STAGES.  The ring is latency-bound --
+// a slab is re-requested when its MMAs have completed and lands ~1500 cycles later --, so with four stages a k-step took
+// (256 + 1500) / 4 = 440 cycles against 256 of tensor-core time.
+constexpr int TCG_MAX_STAGES = 8;
 #ifndef KPD_TCG_EW
 #define KPD_TCG_EW 8
 #endif
@@ -36,17 +39,18 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
     unsigned char* a_s = smem_raw;                     // [2 * ksteps] k-chunks of C::KCS bytes
     unsigned char* b_s = a_s + (((size_t)2 * ((B.kmax + 15) / 16) * C::KCS + 127) & ~(size_t)127);   // [STAGES] ring
     const int slab_stride = NS * 2 * (B.NBmax / 8) * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)TCG_STAGES * slab_stride);
+    const uint32_t stages = (uint32_t)B.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)stages * slab_stride);
     uint64_t* full = bars;
-    uint64_t* empty = bars + TCG_STAGES;
-    uint64_t* a_ready = bars + 2 * TCG_STAGES;
+    uint64_t* empty = bars + TCG_MAX_STAGES;
+    uint64_t* a_ready = bars + 2 * TCG_MAX_STAGES;
     uint64_t* acc_done = a_ready + 1;                  // [2]
     uint64_t* acc_free = acc_done + 2;                 // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < TCG_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < TCG_MAX_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(a_ready, TCG_EW);
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], TCG_EW); }
         tc::fence_barrier_init();
@@ -70,8 +74,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                 const uint32_t slab_bytes = NS * 2 * (NB / 8) * 128;
                 const uint4* Wb = block_W(blk0 + bi);
                 for (int j = 0; j < ksteps; ++j, ++it) {
-                    const uint32_t st = it % TCG_STAGES;
-                    if (it >= (uint32_t)TCG_STAGES) tc::mbar_wait(&empty[st], ((it / TCG_STAGES) - 1) & 1);
+                    const uint32_t st = it % stages;
+                    if (it >= stages) tc::mbar_wait(&empty[st], ((it / stages) - 1) & 1);
                     tc::mbar_arrive_expect_tx(&full[st], slab_bytes);
                     tc::bulk_g2s(b_s + (size_t)st * slab_stride, Wb + (size_t)j * (slab_bytes / 16), slab_bytes, &full[st]);
                 }
@@ -90,8 +94,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                 const uint32_t b_k = (NB / 8) * 128, slab1 = 2 * b_k;
                 if (bi >= 2) { tc::mbar_wait(&acc_free[buf], ((bi >> 1) - 1) & 1); tc::fence_after_sync(); }
                 for (int j = 0; j < ksteps; ++j, ++it) {
-                    const uint32_t st = it % TCG_STAGES;
-                    tc::mbar_wait(&full[st], (it / TCG_STAGES) & 1);
+                    const uint32_t st = it % stages;
+                    tc::mbar_wait(&full[st], (it / stages) & 1);
                     tc::fence_after_sync();
                     const uint64_t adesc = tc::make_smem_desc(tc::smem_u32(a_s + (size_t)2 * j * C::KCS), C::KCS, 128);
                     const uint32_t bs = tc::smem_u32(b_s + (size_t)st * slab_stride);
@@ -238,10 +242,10 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
 }
 
 template <int NS>
-static size_t tc_linear_smem(int K, int NB) {
+static size_t tc_linear_smem(int K, int NB, int stages) {
     using C = ws::Cfg<128 / NS, NS, 1>;
     const int ksteps = (K + 15) / 16;
-    return (((size_t)2 * ksteps * C::KCS + 127) & ~(size_t)127) + (size_t)TCG_STAGES * NS * 2 * (NB / 8) * 128 + (2 * TCG_STAGES + 5) * 8 + 16;
+    return (((size_t)2 * ksteps * C::KCS + 127) & ~(size_t)127) + (size_t)stages * NS * 2 * (NB / 8) * 128 + (2 * TCG_MAX_STAGES + 5) * 8 + 16;
 }
 
 // Wp: packed by pack_tc_weight(W[N,K], split = (nsplit == 2)) -> for each 256-row block nb: [ksteps][hi(, lo)][2][NB/8][8][8]
@@ -261,7 +265,9 @@ static int launch_tc_batch_ns(TcLinBatch& B, int nprob, cudaStream_t st) {
         if (cdiv(p.N, 256) > maxBlocks) maxBlocks = cdiv(p.N, 256);
     }
     if (maxM <= 0) return 0;
-    const size_t smem = tc_linear_smem<NS>(B.kmax, B.NBmax);
+    B.stages = TCG_MAX_STAGES;
+    while (B.stages > 2 && tc_linear_smem<NS>(B.kmax, B.NBmax, B.stages) > 227 * 1024) --B.stages;
+    const size_t smem = tc_linear_smem<NS>(B.kmax, B.NBmax, B.stages);
     KPD_REQUIRE(smem <= 227 * 1024, "tc_linear: K=%d needs %zu B of shared memory", B.kmax, smem);
     static size_t configured = 0;
     if (smem > configured) {

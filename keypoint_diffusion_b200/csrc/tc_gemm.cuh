@@ -14,6 +14,7 @@ struct TcLinBatch {
     int NBmax;              // widest column block of the launch (ring stage size)
     int kmax;               // largest K of the launch (A tile size)
     int bpc;                // 256-column blocks per CTA (blockIdx.y strides over groups of bpc blocks)
+    int stages;             // weight-ring stages (set by the launcher: as many as fit beside the A tile)
 };
 
 TcLinProblem tc_problem(const float* X, int ldx, const void* Wp, const float* bias, const float* R, int ldr, float* Y, int ldy,
