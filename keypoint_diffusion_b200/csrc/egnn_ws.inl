@@ -326,14 +326,16 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         // ---- 1. both branches: first Linear (factorised) + SiLU -> A[br]; leftover output columns as fp32 dots
         TC_T(g2);
         static_assert(RPW == 4, "build A: two row pairs per warp");
-        // one row: v = P_src + P_dst chunk of this lane (8 features), vt = its leftover feature
-        auto build_row = [&](int br, int r, float (&v)[8], float vt) __attribute__((always_inline)) {
+        // one row: v = P_src + P_dst chunk of this lane (8 features); dot = this lane's share of the leftover output columns.
+        // The row's leftover FEATURE and the cross-lane sums of the leftover columns wait for finish_rows(): four rows at a
+        // time, so that their serial chains (one lane's SiLU, five dependent shuffles) overlap instead of adding up
+        auto build_row = [&](int br, int r, float (&v)[8], float (&dot)[3]) __attribute__((always_inline)) {
             const float* w1c = m.w1c[br];
             const float* w2lo = m.w2lo[br];
             unsigned char* Ab = m.A[br];
             const float d = m.dij[r];
             const uint32_t rof = ws::row_off<C>(r);
-            float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
+            dot[0] = dot[1] = dot[2] = 0.f;
             if (lane < nfull) {
                 const float4 wa = *reinterpret_cast<const float4*>(w1c + 8 * lane), wb = *reinterpret_cast<const float4*>(w1c + 8 * lane + 4);
                 float f[8];
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                         const float4 la = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane);
                         const float4 lb = *reinterpret_cast<const float4*>(w2lo + cc * VEC_LD + 8 * lane + 4);
                         const float t = f[0] * la.x + f[1] * la.y + f[2] * la.z + f[3] * la.w + f[4] * lb.x + f[5] * lb.y + f[6] * lb.z + f[7] * lb.w;
-                        if (cc == 0) dot0 = t; else if (cc == 1) dot1 = t; else dot2 = t;
+                        dot[cc] = t;
                     }
                 }
                 uint4 hi, lo;
@@ -363,35 +365,51 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                 *reinterpret_cast<uint4*>(Ab + off) = z;
                 *reinterpret_cast<uint4*>(Ab + off + 256) = z;
             }
-            __syncwarp();
+        };
+        auto finish_rows = [&](int br, float (&dot)[RPW][3], const float (&vt)[RPW]) __attribute__((always_inline)) {
+            const float* w1c = m.w1c[br];
+            const float* w2lo = m.w2lo[br];
+            unsigned char* Ab = m.A[br];
+            __syncwarp();           // (the zero fill of the leftover chunk, by other lanes, precedes the 2-byte stores)
             if (lane < ntail) {
                 const int k = 8 * nfull + lane;
-                const float f = ws::silu_acc(fmaf(w1c[k], d, vt));
-                const uint32_t off = (uint32_t)((k >> 3) * C::KCS + (k & 7) * 2) + rof;
-                const __nv_bfloat16 hi = __float2bfloat16(f);
-                *reinterpret_cast<__nv_bfloat16*>(Ab + off) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(Ab + off + 256) = __float2bfloat16(f - __bfloat162float(hi));
-                if (nlo > 0) dot0 = fmaf(f, w2lo[k], dot0);
-                if (nlo > 1) dot1 = fmaf(f, w2lo[VEC_LD + k], dot1);
-                if (nlo > 2) dot2 = fmaf(f, w2lo[2 * VEC_LD + k], dot2);
+#pragma unroll
+                for (int j = 0; j < RPW; ++j) {
+                    const int r = warp * RPW + j;
+                    const float f = ws::silu_acc(fmaf(w1c[k], m.dij[r], vt[j]));
+                    const uint32_t off = (uint32_t)((k >> 3) * C::KCS + (k & 7) * 2) + ws::row_off<C>(r);
+                    const __nv_bfloat16 hi = __float2bfloat16(f);
+                    *reinterpret_cast<__nv_bfloat16*>(Ab + off) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(Ab + off + 256) = __float2bfloat16(f - __bfloat162float(hi));
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        if (cc < nlo) dot[j][cc] = fmaf(f, w2lo[cc * VEC_LD + k], dot[j][cc]);
+                }
             }
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
                 if (cc < nlo) {
-                    float sdot = cc == 0 ? dot0 : cc == 1 ? dot1 : dot2;
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
-                    if (lane == 0) m.lo[(br * R + r) * 4 + cc] = ws::silu_acc(sdot + m.b2[br][nmain + cc]);
+                    for (int o = 16; o; o >>= 1)
+#pragma unroll
+                        for (int j = 0; j < RPW; ++j) dot[j][cc] += __shfl_xor_sync(0xffffffffu, dot[j][cc], o);
+                    // every lane holds the four sums: lane j finishes row j
+                    float sj = dot[0][cc];
+#pragma unroll
+                    for (int j = 1; j < RPW; ++j) sj = lane == j ? dot[j][cc] : sj;
+                    if (lane < RPW) m.lo[(br * R + warp * RPW + lane) * 4 + cc] = ws::silu_acc(sj + m.b2[br][nmain + cc]);
                 }
             }
         };
+        float dots[RPW][3], vts[RPW];
         auto build_pair = [&](int br, int j0, const egws::RowPair& q) __attribute__((always_inline)) {
             // (j0 = first row of the pair inside the warp's rows: a literal at every call)
             {
                 float v[8];
                 v[0] = q.u[0][0].x + q.w[0][0].x; v[1] = q.u[0][0].y + q.w[0][0].y; v[2] = q.u[0][0].z + q.w[0][0].z; v[3] = q.u[0][0].w + q.w[0][0].w;
                 v[4] = q.u[0][1].x + q.w[0][1].x; v[5] = q.u[0][1].y + q.w[0][1].y; v[6] = q.u[0][1].z + q.w[0][1].z; v[7] = q.u[0][1].w + q.w[0][1].w;
-                build_row(br, warp * RPW + j0, v, q.ut[0] + q.wt[0]);
+                vts[j0] = q.ut[0] + q.wt[0];
+                build_row(br, warp * RPW + j0, v, dots[j0]);
             }
             {
                 const bool own_d = rd[j0 + 1] != rd[j0];
@@ -400,7 +418,8 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
                 float v[8];
                 v[0] = q.u[1][0].x + w0.x; v[1] = q.u[1][0].y + w0.y; v[2] = q.u[1][0].z + w0.z; v[3] = q.u[1][0].w + w0.w;
                 v[4] = q.u[1][1].x + w1.x; v[5] = q.u[1][1].y + w1.y; v[6] = q.u[1][1].z + w1.z; v[7] = q.u[1][1].w + w1.w;
-                build_row(br, warp * RPW + j0 + 1, v, q.ut[1] + wt);
+                vts[j0 + 1] = q.ut[1] + wt;
+                build_row(br, warp * RPW + j0 + 1, v, dots[j0 + 1]);
             }
         };
         // branch 0, the rows of branch 1 fetched behind it
@@ -408,6 +427,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         egws::load_pair<0>(a, Hp, 1, rs, rd, lane, nfull, ntail, q0);
         build_pair(0, 2, q1);
         egws::load_pair<1>(a, Hp, 1, rs, rd, lane, nfull, ntail, q1);
+        finish_rows(0, dots, vts);
         // first use of an mbarrier / of TMEM: join the control warps' set-up
         asm volatile("bar.sync 3, %0;" ::"n"(egws::NT) : "memory");
         tc::fence_after_sync();
@@ -416,6 +436,7 @@ __global__ void __launch_bounds__(egws::NT, 1) egnn_edge_ws_kernel(const __grid_
         gt[0] = clock64();
         build_pair(1, 0, q0);
         build_pair(1, 2, q1);
+        finish_rows(1, dots, vts);
         publish(&m.a_ready[1]);
         gt[1] = clock64();
         // ---- 2. per branch: epilogue straight out of TMEM, then the deterministic segmented reduction
