@@ -16,13 +16,28 @@ namespace kpd {
 // Weight ring: as many 16 KB (bf16x3) stages as fit beside the A tile, at most TCG_MAX_STAGES.  The ring is latency-bound --
 // a slab is re-requested when its MMAs have completed and lands ~1500 cycles later --, so with four stages a k-step took
 // (256 + 1500) / 4 = 440 cycles against 256 of tensor-core time.
-constexpr int TCG_MAX_STAGES = 8;
+#ifndef KPD_TCG_MAX_STAGES
+#define KPD_TCG_MAX_STAGES 8
+#endif
+constexpr int TCG_MAX_STAGES = KPD_TCG_MAX_STAGES;
 #ifndef KPD_TCG_EW
 #define KPD_TCG_EW 8
 #endif
 constexpr int TCG_EW = KPD_TCG_EW;    // SIMT warps: stage A + epilogues (TCG_EW / 4 per TMEM lane quarter)
 constexpr int TCG_CS = TCG_EW / 4;    // ... which take every TCG_CS-th column chunk of a block
 constexpr int TCG_THREADS = 32 * TCG_EW + 64;      // + warp TCG_EW: MMA issuer | warp TCG_EW + 1: weight producer
+
+// phase timers of tools/tc_linear_bench.py (variant builds with -DKPD_TCG_TIMERS only): cycles summed over CTAs, thread 0 of
+// the SIMT warps [0] set-up, [1] A staged, [2] first accumulator waited for, [3] remaining blocks, [4] teardown, [5] CTAs;
+// MMA warp [8] waiting for A, [9] first slab, [10] issue loop
+#ifdef KPD_TCG_TIMERS
+__device__ unsigned long long g_tcg_times[16];
+#define TCG_T(var) const long long var = clock64()
+#define TCG_ACC(slot, a, b) atomicAdd(&g_tcg_times[slot], (unsigned long long)((b) - (a)))
+#else
+#define TCG_T(var)
+#define TCG_ACC(slot, a, b)
+#endif
 
 template <int NS>
 __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinBatch B) {
@@ -48,6 +63,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
     uint64_t* acc_free = acc_done + 2;                 // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TCG_T(t_begin);
 
     if (tid == 0) {
         for (int i = 0; i < TCG_MAX_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
@@ -60,6 +76,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    TCG_T(t_setup);
 
     auto block_NB = [&](int blk) { const int r = N - 256 * blk; return r > 256 ? 256 : (r + 15) & ~15; };
     // all blocks before the last one are full (256 rows): their slabs are NS * 2 * 32 * 128 B per k-step
@@ -87,6 +104,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
         {
             tc::mbar_wait(a_ready, 0);
             tc::fence_after_sync();
+            TCG_T(m_a);
+            [[maybe_unused]] long long m_first = 0;
             uint32_t it = 0;
             for (int bi = 0; bi < nb_cta; ++bi) {
                 const int buf = bi & 1, NB = block_NB(blk0 + bi);
@@ -97,6 +116,9 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                     const uint32_t st = it % stages;
                     tc::mbar_wait(&full[st], (it / stages) & 1);
                     tc::fence_after_sync();
+#ifdef KPD_TCG_TIMERS
+                    if (it == 0) m_first = clock64();
+#endif
                     const uint64_t adesc = tc::make_smem_desc(tc::smem_u32(a_s + (size_t)2 * j * C::KCS), C::KCS, 128);
                     const uint32_t bs = tc::smem_u32(b_s + (size_t)st * slab_stride);
                     const uint64_t b0 = tc::make_smem_desc(bs, b_k, 128), b1 = tc::make_smem_desc(bs + slab1, b_k, 128);
@@ -108,49 +130,64 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                 }
                 if (tc::elect_one()) tc::mma_commit(&acc_done[buf]);
             }
+#ifdef KPD_TCG_TIMERS
+            if (lane == 0) { const long long m_end = clock64(); TCG_ACC(8, t_setup, m_a); TCG_ACC(9, m_a, m_first); TCG_ACC(10, m_first, m_end); }
+#endif
         }
     } else {
         // ---- stage the A tile once: each warp owns R/4 consecutive rows; (row, 8-element k-chunk) items are dealt to
         //      the lanes in order (coalesced 32-byte reads), four items per lane in flight
         {
+            // NI items per lane and round: the 8 rows x 34 chunks of a K = 257 tile (272 items per warp) are ONE round trip to
+            // L2, K = 517 two.  A chunk is read as two 16-byte loads wherever the row (ldx floats, a multiple of 4) has them --
+            // the columns beyond K are masked afterwards: they may hold anything -- so there is no scalar path.
             const int nch = 2 * ksteps;
             constexpr int RPW = C::R / TCG_EW;
+            constexpr int NI = 9;
             const int items = RPW * nch;
-            for (int base = 0; base < items; base += 128) {
-                float v[4][8];
+            for (int base = 0; base < items; base += 32 * NI) {
+                float4 va[NI], vb[NI];
+                int ri = (base + lane) / nch, c = (base + lane) - ri * nch;
+                int ri0 = ri, c0 = c;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NI; ++u) {
                     const int i = base + 32 * u + lane;
-                    const int ri = i / nch, c = i - ri * nch;
                     const int gm = m0 + warp * RPW + ri;
-                    if (i < items && gm < M && 8 * c + 8 <= K) {
+                    va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < items && gm < M) {
                         const float* xr = P.X + (size_t)gm * P.ldx + 8 * c;
-                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(xr)), u1 = __ldg(reinterpret_cast<const float4*>(xr + 4));
-                        v[u][0] = u0.x; v[u][1] = u0.y; v[u][2] = u0.z; v[u][3] = u0.w;
-                        v[u][4] = u1.x; v[u][5] = u1.y; v[u][6] = u1.z; v[u][7] = u1.w;
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            v[u][q] = (i < items && gm < M && 8 * c + q < K) ? __ldg(P.X + (size_t)gm * P.ldx + 8 * c + q) : 0.0f;
+                        if (8 * c + 4 <= P.ldx && 8 * c < K) va[u] = __ldg(reinterpret_cast<const float4*>(xr));
+                        if (8 * c + 8 <= P.ldx && 8 * c + 4 < K) vb[u] = __ldg(reinterpret_cast<const float4*>(xr + 4));
                     }
+                    c += 32;
+                    while (c >= nch) { c -= nch; ++ri; }
                 }
+                ri = ri0; c = c0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NI; ++u) {
                     const int i = base + 32 * u + lane;
                     if (i < items) {
-                        const int ri = i / nch, c = i - ri * nch;
+                        float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                        if (8 * c + 8 > K) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = 8 * c + q < K ? v[q] : 0.0f;
+                        }
                         uint4 hi, lo;
-                        ws::split8(v[u], hi, lo);
+                        ws::split8(v, hi, lo);
                         const uint32_t off = (uint32_t)(c * C::KCS) + ws::row_off<C>(warp * RPW + ri);
                         *reinterpret_cast<uint4*>(a_s + off) = hi;
                         if (NS == 2) *reinterpret_cast<uint4*>(a_s + off + 256) = lo;
                     }
+                    c += 32;
+                    while (c >= nch) { c -= nch; ++ri; }
                 }
             }
             tc::fence_proxy_async();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(a_ready);
         }
+        TCG_T(t_staged);
+        [[maybe_unused]] long long t_first = 0;
         // ---- epilogues
         const int q = warp & 3, chalf = warp >> 2;       // TMEM lane quarter; which 64-column chunks (c0 / 64 parity)
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -158,6 +195,9 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
             const int buf = bi & 1, blk = blk0 + bi, NB = block_NB(blk);
             tc::mbar_wait(&acc_done[buf], (bi >> 1) & 1);
             tc::fence_after_sync();
+#ifdef KPD_TCG_TIMERS
+            if (bi == 0) t_first = clock64();
+#endif
             if (NS == 1) {          // thread r reads its accumulator row from TMEM
                 const int gm = m0 + 32 * q + lane;
                 for (int c0 = 32 * chalf; c0 < NB; c0 += 32 * TCG_CS) {
@@ -184,6 +224,44 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
                     uint32_t v0[32], v1[32];
                     tc::tmem_ld_16x256b_x8(lane_addr + 256 * buf + c0, v0);
                     tc::tmem_ld_16x256b_x8(lane_addr + (16u << 16) + 256 * buf + c0, v1);
+                    // interior chunk (all 64 columns exist, 8-byte accesses possible): every global load of the chunk -- bias
+                    // and both rows' residuals -- is issued before the TMEM wait, nothing is predicated per element.  (The
+                    // general path below is ~1400 instructions per chunk and warp, three dependent L2 round trips.)
+                    if (vec2 && blk * 256 + c0 + 64 <= N && (!P.bias || (reinterpret_cast<uintptr_t>(P.bias) & 7) == 0)) {
+                        const int gn0 = blk * 256 + c0 + cp;
+                        const int gma = m0 + ra, gmb = gma + 8;
+                        float2 bz[8], rza[8], rzb[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            bz[i] = P.bias ? __ldg(reinterpret_cast<const float2*>(P.bias + gn0 + 8 * i)) : make_float2(0.f, 0.f);
+                            rza[i] = rzb[i] = make_float2(0.f, 0.f);
+                        }
+                        if (P.R) {
+                            const float* rpa = P.R + (size_t)gma * P.ldr + gn0;
+                            const float* rpb = P.R + (size_t)gmb * P.ldr + gn0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (gma < M) rza[i] = *reinterpret_cast<const float2*>(rpa + 8 * i);
+                                if (gmb < M) rzb[i] = *reinterpret_cast<const float2*>(rpb + 8 * i);
+                            }
+                        }
+                        tc::tmem_ld_wait();
+                        float* ypa = P.Y + (size_t)gma * P.ldy + gn0;
+                        float* ypb = P.Y + (size_t)gmb * P.ldy + gn0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float2 fa, fb;
+                            fa.x = __uint_as_float(v0[4 * i + 0]) + __uint_as_float(v1[4 * i + 0]) + bz[i].x;
+                            fa.y = __uint_as_float(v0[4 * i + 1]) + __uint_as_float(v1[4 * i + 1]) + bz[i].y;
+                            fb.x = __uint_as_float(v0[4 * i + 2]) + __uint_as_float(v1[4 * i + 2]) + bz[i].x;
+                            fb.y = __uint_as_float(v0[4 * i + 3]) + __uint_as_float(v1[4 * i + 3]) + bz[i].y;
+                            if (P.act == 1) { fa.x = ws::silu_acc(fa.x); fa.y = ws::silu_acc(fa.y); fb.x = ws::silu_acc(fb.x); fb.y = ws::silu_acc(fb.y); }
+                            fa.x += rza[i].x; fa.y += rza[i].y; fb.x += rzb[i].x; fb.y += rzb[i].y;
+                            if (gma < M) *reinterpret_cast<float2*>(ypa + 8 * i) = fa;
+                            if (gmb < M) *reinterpret_cast<float2*>(ypb + 8 * i) = fb;
+                        }
+                        continue;
+                    }
                     // bias of this lane's column pairs: independent loads, in flight with the TMEM reads
                     float2 bz[8];
 #pragma unroll
@@ -235,6 +313,12 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tc_linear_kernel(const __grid_
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&acc_free[buf]);
         }
+#ifdef KPD_TCG_TIMERS
+        if (tid == 0) {
+            const long long t_end = clock64();
+            TCG_ACC(0, t_begin, t_setup); TCG_ACC(1, t_setup, t_staged); TCG_ACC(2, t_staged, t_first); TCG_ACC(3, t_first, t_end); TCG_ACC(5, 0, 1);
+        }
+#endif
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -309,6 +393,16 @@ int launch_tc_linear(const float* X, int ldx, const void* Wp, const float* bias,
 }
 
 }  // namespace kpd
+
+#ifdef KPD_TCG_TIMERS
+extern "C" int kpd_debug_tcg_times(unsigned long long* out16) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, kpd::g_tcg_times, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(kpd::g_tcg_times, z, sizeof(z));
+    return e == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int kpd_tc_linear(const float* X, int32_t ldx, const void* Wp, const float* bias, const float* R, int32_t ldr,
                              float* Y, int32_t ldy, int32_t M, int32_t K, int32_t N, int32_t act, int32_t nsplit, void* stream) {
