@@ -215,6 +215,8 @@ __device__ __forceinline__ float seg_gather(const float* __restrict__ out, int l
 // ------------------------------------------------------------------ row ops (row_ops.cu)
 int launch_linear(const float* X, int ldx, const float* WT, int ldw, const float* bias, const float* R,
                   int ldr, float* Y, int ldy, int M, int K, int N, int act, cudaStream_t st);
+int launch_layernorm_pair(const float* in0, float* out0, int M0, const float* w0, const float* b0, const float* in1, float* out1,
+                          int M1, const float* w1, const float* b1, int ldi, int ldo, int H, cudaStream_t st);
 int launch_layernorm(const float* in, int ldi, float* out, int ldo, int M, int H, const float* w,
                      const float* b, cudaStream_t st);
 int launch_set_time_col(float* out, int ld, int col, int n, const float* t_ptr, const int* batch,

@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(128) egnn_node_prep_kernel(const EgnnNodePrep 
 // the same node stage for the tensor-core mode: one warp per node, a lane per 8-feature chunk (float4 traffic, all
 // loads of a node in flight together); h_neigh starts at column off_neigh of the cat row (a multiple of 4: the packed
 // node_mlp.0 weight has matching zero columns, pack.pack_egnn_tc)
-__global__ void __launch_bounds__(256) egnn_node_prep_warp_kernel(const EgnnNodePrep a, int off_neigh) {
-    const int nd = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void node_prep_warp_body(const EgnnNodePrep& a, int off_neigh, int blk) {
+    const int nd = blk * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (nd >= a.n) return;
     float z = 1.0f;
     if (a.z_mode == 1) z = a.z_const;
@@ -293,6 +293,16 @@ __global__ void __launch_bounds__(256) egnn_node_prep_warp_kernel(const EgnnNode
         }
     }
     for (int c = a.H + lane; c < off_neigh; c += 32) crow[c] = 0.f;
+}
+__global__ void __launch_bounds__(256) egnn_node_prep_warp_kernel(const EgnnNodePrep a, int off_neigh) {
+    node_prep_warp_body(a, off_neigh, blockIdx.x);
+}
+// both updated node types in one launch (blocks [0, blocks0) = ligand atoms, the rest = keypoints): each of these kernels is
+// ~7 us of latency, not of work
+struct EgnnNodePrepPair { EgnnNodePrep a[2]; };
+__global__ void __launch_bounds__(256) egnn_node_prep_pair_kernel(const __grid_constant__ EgnnNodePrepPair p, int off_neigh, int blocks0) {
+    if ((int)blockIdx.x < blocks0) node_prep_warp_body(p.a[0], off_neigh, blockIdx.x);
+    else node_prep_warp_body(p.a[1], off_neigh, (int)blockIdx.x - blocks0);
 }
 
 }  // namespace kpd
@@ -578,9 +588,10 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
         // tensor-core mode: h_neigh starts at the 4-aligned column Hp of the cat row (zero gap [H, Hp))
         const int off_neigh = m->mode == 2 ? Hp : H;
         const int ldcat = (off_neigh + H + 3) & ~3;
+        EgnnNodePrepPair NP;
+        memset(&NP, 0, sizeof(NP));
         for (int nt = 0; nt < m->n_upd; ++nt) {
-            EgnnNodePrep a;
-            memset(&a, 0, sizeof(a));
+            EgnnNodePrep& a = NP.a[nt];
             a.n = N[nt]; a.H = H; a.Hp = Hp; a.pw = m->pw;
             a.ldcat = ldcat;
             a.h = w.h[nt]; a.cat = w.cat[nt]; a.x = w.xc[nt];
@@ -593,12 +604,16 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
             a.z_const = m->cfg.message_norm;
             a.node_batch = nt == 0 ? b->lig_batch : b->kp_batch;
             a.ptr = nt == 0 ? b->lig_ptr : b->kp_ptr;
-            if (a.n > 0 && m->mode == 2) {
-                egnn_node_prep_warp_kernel<<<cdiv(a.n, 8), 256, 0, st>>>(a, off_neigh);
-                KPD_TRY(check_launch("egnn_node_prep_warp_kernel"));
-            } else if (a.n > 0) {
+            if (a.n > 0 && m->mode != 2) {
                 egnn_node_prep_kernel<<<a.n, 128, 0, st>>>(a);
                 KPD_TRY(check_launch("egnn_node_prep_kernel"));
+            }
+        }
+        if (m->mode == 2) {
+            const int blocks0 = cdiv(NP.a[0].n > 0 ? NP.a[0].n : 0, 8), blocks1 = m->n_upd > 1 ? cdiv(NP.a[1].n > 0 ? NP.a[1].n : 0, 8) : 0;
+            if (blocks0 + blocks1 > 0) {
+                egnn_node_prep_pair_kernel<<<blocks0 + blocks1, 256, 0, st>>>(NP, off_neigh, blocks0);
+                KPD_TRY(check_launch("egnn_node_prep_pair_kernel"));
             }
         }
         // node_mlp = Linear(2H,H), SiLU, Linear(H,H); residual; LayerNorm  (:202-205)
@@ -618,8 +633,14 @@ extern "C" int kpd_egnn_forward(const kpd_egnn_model* m, const kpd_batch* b, con
                 KPD_TRY(launch_linear(w.cat[nt], ldcat, W.Wn1T[nt], Hp, W.bn1[nt], nullptr, 0, w.tmp1[nt], Hp, N[nt], 2 * H, H, 1, st));
                 KPD_TRY(launch_linear(w.tmp1[nt], Hp, W.Wn2T[nt], Hp, W.bn2[nt], w.h[nt], Hp, w.y[nt], Hp, N[nt], H, H, 0, st));
             }
+            if (m->cfg.norm && m->mode == 2) continue;      // (one launch for all node types below)
             if (m->cfg.norm) KPD_TRY(launch_layernorm(w.y[nt], Hp, w.h[nt], Hp, N[nt], H, W.lnw[nt], W.lnb[nt], st));
             else KPD_TRY(launch_copy_rows(w.y[nt], Hp, w.h[nt], Hp, N[nt], H, st));
+        }
+        if (m->cfg.norm && m->mode == 2) {
+            const bool two = m->n_upd > 1;
+            KPD_TRY(launch_layernorm_pair(w.y[0], w.h[0], N[0], W.lnw[0], W.lnb[0], two ? w.y[1] : nullptr, two ? w.h[1] : nullptr,
+                                          two ? N[1] : 0, two ? W.lnw[1] : nullptr, two ? W.lnb[1] : nullptr, Hp, Hp, H, st));
         }
         prof_end(PROF_EGNN_NODE, st);
     }
