@@ -1,6 +1,14 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02g_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02g_pytest.log
-for sb in 1 2 3 4; do
-timeout 400 python bench.py --workload egnn_20kp --steps 2 --warmup 3 --sub-batches $sb --no-cpu-baseline --no-ragged --no-shipped-ll-block --no-mode-blocks --no-roofline > gpurun_out/r02g_bench_egnn_sb$sb.json 2> gpurun_out/r02g_bench_egnn.err; echo "bench rc=$?"
-python -c "import json; d=json.load(open('gpurun_out/r02g_bench_egnn_sb$sb.json')); print('egnn sub-batches $sb', d['value'], d['e2e']['value'])"
+timeout 900 python bench.py --workload egnn_20kp > gpurun_out/r02_final_bench_egnn_20kp.json 2> gpurun_out/err1.txt; echo "rc=$?"
+timeout 900 python bench.py --workload egnn_20kp_c1 > gpurun_out/r02_final_bench_egnn_20kp_c1.json 2> gpurun_out/err2.txt; echo "rc=$?"
+timeout 1500 python bench.py --workload egnn_all_atom --steps 1 --warmup 1 --no-mode-blocks --no-ragged --no-shipped-ll-block > gpurun_out/r02_final_bench_egnn_all_atom.json 2> gpurun_out/err3.txt; echo "rc=$?"
+for n in 1 16 256 1024 4096; do
+timeout 900 python bench.py --workload gvp_ca --ligands $n --steps 1 --warmup 1 --no-mode-blocks --no-cpu-baseline --no-roofline --no-ragged --no-shipped-ll-block > gpurun_out/r02_final_bench_gvp_ca_$n.json 2> gpurun_out/err4.txt; echo "rc=$?"
 done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r02_final_bench_*.json')):
+    try:
+        d=json.load(open(f)); print(f, round(d['value'],2), round(d['e2e']['value'],2), (d.get('roofline') or {}).get('frac'), (d.get('cpu_baseline') or {}).get('value'))
+    except Exception as e: print(f, 'ERR', e)
+PY
