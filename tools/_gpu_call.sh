@@ -1,14 +1,7 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python bench.py --workload egnn_20kp > gpurun_out/r02_final_bench_egnn_20kp.json 2> gpurun_out/err1.txt; echo "rc=$?"
-timeout 900 python bench.py --workload egnn_20kp_c1 > gpurun_out/r02_final_bench_egnn_20kp_c1.json 2> gpurun_out/err2.txt; echo "rc=$?"
-timeout 1500 python bench.py --workload egnn_all_atom --steps 1 --warmup 1 --no-mode-blocks --no-ragged --no-shipped-ll-block > gpurun_out/r02_final_bench_egnn_all_atom.json 2> gpurun_out/err3.txt; echo "rc=$?"
-for n in 1 16 256 1024 4096; do
-timeout 900 python bench.py --workload gvp_ca --ligands $n --steps 1 --warmup 1 --no-mode-blocks --no-cpu-baseline --no-roofline --no-ragged --no-shipped-ll-block > gpurun_out/r02_final_bench_gvp_ca_$n.json 2> gpurun_out/err4.txt; echo "rc=$?"
-done
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r02_final_bench_*.json')):
-    try:
-        d=json.load(open(f)); print(f, round(d['value'],2), round(d['e2e']['value'],2), (d.get('roofline') or {}).get('frac'), (d.get('cpu_baseline') or {}).get('value'))
-    except Exception as e: print(f, 'ERR', e)
-PY
+timeout 300 python tools/profile_step.py egnn_20kp 8 100 bf16x3 > gpurun_out/r02_final_prof_plain.log 2>&1; echo "plain rc=$?"; tail -1 gpurun_out/r02_final_prof_plain.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 3000 -c 400 --csv --log-file gpurun_out/r02_final_egnn20kp_launches.csv python tools/profile_step.py egnn_20kp 60 100 bf16x3 > gpurun_out/r02_final_ncu_list_egnn.log 2>&1; echo "rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 2000 -c 400 --csv --log-file gpurun_out/r02_final_gvp20kp_launches.csv python tools/profile_step.py gvp_20kp 110 100 bf16x3 > gpurun_out/r02_final_ncu_list_gvp.log 2>&1; echo "rc=$?"
+timeout 400 ncu --set full --clock-control none --cache-control none --import-source on -k regex:egnn_edge_ws -s 12 -c 1 -o gpurun_out/r02_final_egnn_edge_warm python tools/profile_step.py egnn_20kp 8 100 bf16x3 > gpurun_out/r02_final_ncu_egnn.log 2>&1; echo "rc=$?"
+timeout 400 ncu --set full --clock-control none --cache-control none --import-source on -k regex:tc_linear -s 40 -c 3 -o gpurun_out/r02_final_tc_linear_warm python tools/profile_step.py egnn_20kp 8 100 bf16x3 > gpurun_out/r02_final_ncu_tcl.log 2>&1; echo "rc=$?"
+ls -la gpurun_out/*.ncu-rep
