@@ -223,7 +223,8 @@ class _Model:
         self._ws: Dict[Tuple, torch.Tensor] = {}
 
     def _workspace(self, batch: DeviceBatch, caps: Tuple[int, int, int]) -> torch.Tensor:
-        key = (id(batch), caps)
+        # keyed on what the workspace size depends on (values, not id(batch): ids are reused after garbage collection)
+        key = (batch.c.B, batch.c.n_lig, batch.c.n_kp, batch.c.max_lig, batch.c.max_kp, tuple(caps), str(batch.device))
         ws = self._ws.get(key)
         if ws is None:
             fn = lib.kpd_egnn_workspace_bytes if self.arch == 0 else lib.kpd_gvp_workspace_bytes
