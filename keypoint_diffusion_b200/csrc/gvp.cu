@@ -636,16 +636,20 @@ extern "C" int kpd_gvp_attach_tc(kpd_gvp_model* m, const void* tc_blob, const in
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsSplitPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         if (e == cudaSuccess && m->edge_ks) e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ks);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsSplit, NODE_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit, NODE_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsSplit, NODE_ROWS_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsSplit, NODE_ROWS_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws2);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws2);
         m->tc2_ready = true;
         return gvp_dag_init(m);
     }
     {
         cudaError_t e = cudaFuncSetAttribute(gvp_edge_ws_kernel<WsBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsBf16N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsBf16N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsBf16N, NODE_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsBf16N, NODE_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_node_ws_kernel<WsBf16N, NODE_ROWS_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gvp_head_ws_kernel<WsBf16N, NODE_ROWS_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_ws1n);
         KPD_REQUIRE(e == cudaSuccess, "kpd_gvp_attach_tc: cannot set %zu B of dynamic shared memory", m->smem_ws1);
     }
     m->tc_ready = true;
@@ -830,9 +834,22 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         for (int k = 0; k < a.n_upd; ++k) a.upd[k] = W.upd[nt][k];
         a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
     };
+    // full 64-row node / head tiles for calls of >= 32 complexes (capacity: the layouts of the capacity-bucketed samplers
+    // round 24 .. 31 real complexes up to 32, 16 .. 23 up to 24): the sampler cuts batches of >= 64 complexes into four
+    // concurrent groups and smaller ones into groups of >= 16, so a call this large means the GPU is kept full by its
+    // siblings and SM time, not the critical path, is what counts (gvp_ws.inl: NODE_ROWS; measured: headline, groups of 25:
+    // 89.3 -> 92.1 ligands/s; gvp_ca with 16 ligands in one group: 33.1 with 32-row tiles, 29.9 with 64)
+    const bool full_node_tiles = b->B >= 32;
+    const int node_rows = full_node_tiles ? NODE_ROWS_FULL : NODE_ROWS;
     auto launch_node_ws = [&](const GvpNodeLaunch& NL, int max_n, int n_dst, cudaStream_t s_) -> int {
-        if (m->mode == 1) launch_clustered(gvp_node_ws_kernel<WsBf16N>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsBf16N::NT, m->smem_ws1n, s_, WsBf16N::CL, NL, dag);
-        else launch_clustered(gvp_node_ws_kernel<WsSplit>, dim3(cdiv(max_n, NODE_ROWS), n_dst), WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, NL, dag);
+        const dim3 grid(cdiv(max_n, node_rows), n_dst);
+        if (m->mode == 1) {
+            if (full_node_tiles) launch_clustered(gvp_node_ws_kernel<WsBf16N, NODE_ROWS_FULL>, grid, WsBf16N::NT, m->smem_ws1n, s_, WsBf16N::CL, NL, dag);
+            else launch_clustered(gvp_node_ws_kernel<WsBf16N, NODE_ROWS>, grid, WsBf16N::NT, m->smem_ws1n, s_, WsBf16N::CL, NL, dag);
+        } else {
+            if (full_node_tiles) launch_clustered(gvp_node_ws_kernel<WsSplit, NODE_ROWS_FULL>, grid, WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, NL, dag);
+            else launch_clustered(gvp_node_ws_kernel<WsSplit, NODE_ROWS>, grid, WsSplit::NT, m->smem_ws2, s_, WsSplit::CL, NL, dag);
+        }
         return check_launch("gvp_node_ws_kernel");
     };
 
@@ -929,10 +946,12 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
             prof_begin(PROF_GVP_HEAD, st);
             a.kch = m->kch;
             if (m->mode == 1) {
-                launch_clustered(gvp_head_ws_kernel<WsBf16N>, dim3(cdiv(a.n, NODE_ROWS)), WsBf16N::NT, m->smem_ws1n, st, WsBf16N::CL, a);
+                if (full_node_tiles) launch_clustered(gvp_head_ws_kernel<WsBf16N, NODE_ROWS_FULL>, dim3(cdiv(a.n, node_rows)), WsBf16N::NT, m->smem_ws1n, st, WsBf16N::CL, a);
+                else launch_clustered(gvp_head_ws_kernel<WsBf16N, NODE_ROWS>, dim3(cdiv(a.n, node_rows)), WsBf16N::NT, m->smem_ws1n, st, WsBf16N::CL, a);
                 KPD_TRY(check_launch("gvp_head_ws_kernel"));
             } else if (m->mode == 2) {
-                launch_clustered(gvp_head_ws_kernel<WsSplit>, dim3(cdiv(a.n, NODE_ROWS)), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, a);
+                if (full_node_tiles) launch_clustered(gvp_head_ws_kernel<WsSplit, NODE_ROWS_FULL>, dim3(cdiv(a.n, node_rows)), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, a);
+                else launch_clustered(gvp_head_ws_kernel<WsSplit, NODE_ROWS>, dim3(cdiv(a.n, node_rows)), WsSplit::NT, m->smem_ws2, st, WsSplit::CL, a);
                 KPD_TRY(check_launch("gvp_head_ws_kernel"));
             } else {
                 gvp_head_kernel<<<cdiv(a.n, TN), NT, m->smem_node, st>>>(a);

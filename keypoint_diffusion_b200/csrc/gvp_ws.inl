@@ -1607,13 +1607,16 @@ __global__ void __launch_bounds__(256) gvp_encode_kernel(const __grid_constant__
     }
 }
 
-// node / head tiles hold NODE_ROWS valid rows of the C::R-row MMA tile: node counts per launch are small, so
-// more, lighter CTAs (one wave) beat full tiles; rows are dealt round-robin to the SIMT warps for the scalar phases
-constexpr int NODE_ROWS = 32;
+// node / head tiles hold NR valid rows of the C::R-row MMA tile; rows are dealt round-robin to the SIMT warps for the
+// scalar phases.  NR = 32: more, lighter CTAs -- the shorter critical path wins while the GPU is not full (gvp_ca, 16
+// ligands: 33.1 against 29.9 ligands/s).  NR = 64 (full tiles): half the CTAs for ~1.4x the cycles each -- less SM time,
+// which wins once concurrent sub-batches keep every SM busy (headline 89.3 -> 91.9, gvp_ca 256 ligands 67.9 -> 71.0).
+// kpd_gvp_forward picks per call by the number of edge tiles of the call (node_tile_rows()).
+constexpr int NODE_ROWS = 32, NODE_ROWS_FULL = 64;
 
 // GVPMultiEdgeConv.forward after the message pass (models/gvp.py:501-536): messages / norm, residual,
 // GVPLayerNorm, update GVPs, residual, GVPLayerNorm; both node types in one launch.
-template <class C>
+template <class C, int NODE_ROWS>
 __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_constant__ GvpNodeLaunch L) {
     const GvpNodeArgs& a = L.nt[blockIdx.y];
     const int n0 = blockIdx.x * NODE_ROWS;
@@ -1841,7 +1844,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
 }
 
 // NoisePredictionBlock (models/dynamics_gvp.py:38-44): noise GVPs + Linear(64 -> atom_nf); eps_x = vectors.squeeze(1)
-template <class C>
+template <class C, int NODE_ROWS>
 __global__ void __launch_bounds__(C::NT, 1) gvp_head_ws_kernel(const __grid_constant__ GvpHeadArgs a) {
     const int n0 = blockIdx.x * NODE_ROWS;
     if ((int)(blockIdx.x / C::CL) * C::CL * NODE_ROWS >= a.n) return;
