@@ -92,36 +92,8 @@ __device__ __forceinline__ float sigmoid_acc(float x) {
 }
 __device__ __forceinline__ float silu_acc(float x) { return x * sigmoid_acc(x); }
 
-// fp32-grade SiLU of FOUR values on five MUFU ops instead of eight: the epilogues are bound by the MUFU pipe (16 lanes
-// per clock and SM; ex2 + rcp per element), and one reciprocal can serve four denominators -- 1/a = (b c d) / (a b c d).
-// The exponent arguments are clamped to 30 so that the product of four denominators (<= 2^120) stays finite: for
-// x < -20.8 the logistic is held at 9.3e-10, an absolute error of the SiLU below 5e-8.  ~5 ulp.
-#ifndef KPD_SILU_PLAIN
-__device__ __forceinline__ void silu_acc4(float& x0, float& x1, float& x2, float& x3) {
-    float e0, e1, e2, e3, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0 * -1.4426950408889634f, 30.f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1 * -1.4426950408889634f, 30.f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fminf(x2 * -1.4426950408889634f, 30.f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fminf(x3 * -1.4426950408889634f, 30.f)));
-    const float a = 1.0f + e0, b = 1.0f + e1, c = 1.0f + e2, d = 1.0f + e3;
-    const float ab = a * b, cd = c * d;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ab * cd));
-    const float rab = r * cd, rcd = r * ab;         // 1 / (a b), 1 / (c d)
-    x0 *= rab * b; x1 *= rab * a; x2 *= rcd * d; x3 *= rcd * c;
-}
-#else
-__device__ __forceinline__ void silu_acc4(float& x0, float& x1, float& x2, float& x3) {
-    x0 = silu_acc(x0); x1 = silu_acc(x1); x2 = silu_acc(x2); x3 = silu_acc(x3);
-}
-#endif
-
 template <int NS>
 __device__ __forceinline__ float act_silu(float x) { return NS == 1 ? silu_fast(x) : silu_acc(x); }
-template <int NS>
-__device__ __forceinline__ void act_silu4(float& x0, float& x1, float& x2, float& x3) {
-    if (NS == 1) { x0 = silu_fast(x0); x1 = silu_fast(x1); x2 = silu_fast(x2); x3 = silu_fast(x3); }
-    else silu_acc4(x0, x1, x2, x3);
-}
 template <int NS>
 __device__ __forceinline__ float act_sigmoid(float x) { return NS == 1 ? sigmoid_fast(x) : sigmoid_acc(x); }
 
