@@ -1666,11 +1666,16 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
             const int lg = a.edge_tile == 128 ? 7 : 6;
             float lw[8], lb[8];
             ws::ln_params8(a.mln_w, a.mln_b, act, lane, lw, lb);
-            float x[RPW][8];
-            float4 ga[RPW][2][2], sa[RPW][2];
+            // (batches of RB = 2 rows: their 12 16-byte loads per lane are in flight together; all four rows of a 64-row tile
+            // at once would need 128 registers for the loads alone -- 300 B of spills per thread, each an L2 round trip)
+            constexpr int RB = RPW < 2 ? RPW : 2;
+#pragma unroll 1
+            for (int jb = 0; jb < RPW; jb += RB) {
+            float x[RB][8];
+            float4 ga[RB][2][2], sa[RB][2];
 #pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int r = warp + C::NW * j;
+            for (int j = 0; j < RB; ++j) {
+                const int r = warp + C::NW * (jb + j);
                 const int nd = n0 + min(r, n - 1);
                 const int col = act ? 8 * lane : 0;
 #pragma unroll
@@ -1686,8 +1691,8 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                 sa[j][1] = __ldg(reinterpret_cast<const float4*>(a.s + (size_t)nd * Sd + col + 4));
             }
 #pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int r = warp + C::NW * j;
+            for (int j = 0; j < RB; ++j) {
+                const int r = warp + C::NW * (jb + j);
                 float msg[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) msg[i] = 0.f;
@@ -1723,6 +1728,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                     }
                     ws::put_chunk<C>(m, r, lane, x[j]);
                 }
+            }
             }
         }
         // ---- phase 1b: vectors of lane (row, c) -> registers; residual stash in global
@@ -1786,21 +1792,24 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
         // ---- phase 3: residual + GVPLayerNorm -> global (fp32 + the bf16 planes the next edge kernel gathers)
         TC_T(n4t);
         {
-            float x[RPW][8];
-            float4 sa[RPW][2];
             float lw[8], lb[8];
             ws::ln_params8(a.uln_w, a.uln_b, act, lane, lw, lb);
+            constexpr int RB = RPW < 2 ? RPW : 2;           // (row pairs, as in phase 1a: the vectors stay live underneath)
+#pragma unroll 1
+            for (int jb = 0; jb < RPW; jb += RB) {
+            float x[RB][8];
+            float4 sa[RB][2];
 #pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int r = warp + C::NW * j;
+            for (int j = 0; j < RB; ++j) {
+                const int r = warp + C::NW * (jb + j);
                 const int nd = n0 + min(r, n - 1);
                 const int col = act ? 8 * lane : 0;
                 sa[j][0] = *reinterpret_cast<const float4*>(a.s_out + (size_t)nd * Sd + col);
                 sa[j][1] = *reinterpret_cast<const float4*>(a.s_out + (size_t)nd * Sd + col + 4);
             }
 #pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int r = warp + C::NW * j;
+            for (int j = 0; j < RB; ++j) {
+                const int r = warp + C::NW * (jb + j);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[j][i] = 0.f;
                 if (act) {
@@ -1815,6 +1824,7 @@ __global__ void __launch_bounds__(C::NT, 1) gvp_node_ws_kernel(const __grid_cons
                     *reinterpret_cast<float4*>(a.s_out + o + 4) = make_float4(x[j][4], x[j][5], x[j][6], x[j][7]);
                     ws::store_planes8(a.s_hi_out, a.s_lo_out, o, x[j]);
                 }
+            }
             }
         }
         if (vecw) {
