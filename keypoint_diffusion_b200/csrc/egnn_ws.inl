@@ -4,7 +4,10 @@
 // tiles of 64 dst-sorted edges.  Per branch (edge_mlp, coord_mlp):
 //   SIMT:   A = SiLU(P_src[src] + P_dst[dst] + w1c * dij)  -> bf16 (hi, lo) rows stacked into ONE 128-row UMMA
 //           operand (ws_common.cuh); the few output columns beyond a multiple of 8 (H = 257 -> column 256) as
-//           fp32 dot products on the way;
+//           fp32 dot products on the way.  The kernel is bound by the latency of the P gathers (L2: 225 KB of shared
+//           memory leave no L1) and by SIMT instruction count, so every warp fetches the (src, dst) of its four rows
+//           itself at the top of the kernel, issues the gathers of branch 0 BEFORE the tile set-up, keeps them in flight
+//           as row pairs in registers and fetches branch 1 behind the rows of branch 0 as those are consumed;
 //   MMA:    acc[64 x 256] (+)= A W2^T, two tcgen05.mma per k-step (W_hi, W_lo) = all four hi/lo products, fp32 in
 //           TMEM; weights streamed as packed k-step slabs through a cp.async.bulk ring;
 //   SIMT:   m2 = SiLU(acc + b2) straight out of TMEM; the row dot products with the attention / coordinate vector;

@@ -1,7 +1,9 @@
 // tcgen05 GEMM for node-level rows, and the unit under test for the tensor-core primitives of tc.cuh:
 //     Y[m, 0:N] = act( X[m, 0:K] @ W^T + bias ) (+R)
 //   X fp32 row-major, staged into shared memory as the bf16 UMMA A operand; W pre-packed bf16 "k-step slabs"
-//   (keypoint_diffusion_b200/pack.py: pack_tc_weight), streamed through a cp.async.bulk ring; fp32 accumulation in
+//   (keypoint_diffusion_b200/pack.py: pack_tc_weight), streamed through a cp.async.bulk ring (as deep as shared memory
+//   allows beside the A tile); the A tile is staged in ONE round trip to L2 (9 16-byte-pair items per lane in flight);
+//   interior 64-column epilogue chunks take a lean path (every global load before the TMEM wait); fp32 accumulation in
 //   TMEM, fp32 output.  NS = 1: plain bf16 operands, 128 rows per CTA.  NS = 2 ("bf16x3"): 64 rows per CTA, the
 //   (hi, lo) bf16 rows stacked into one 128-row operand and two MMAs per k-step (W_hi, W_lo), which together give
 //   all four hi/lo products -- fp32-grade results on the tensor cores (ws_common.cuh).
