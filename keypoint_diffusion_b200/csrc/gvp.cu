@@ -835,7 +835,7 @@ extern "C" int kpd_gvp_forward(const kpd_gvp_model* m, const kpd_batch* b, const
         a.mln_w = W.mln_w[nt]; a.mln_b = W.mln_b[nt]; a.uln_w = W.uln_w[nt]; a.uln_b = W.uln_b[nt];
     };
     // full 64-row node / head tiles for calls of >= 32 complexes (capacity: the layouts of the capacity-bucketed samplers
-    // round 24 .. 31 real complexes up to 32, 16 .. 23 up to 24): the sampler cuts batches of >= 64 complexes into four
+    // round 23 .. 31 real complexes up to 32, 16 .. 22 up to 24; tests/test_modules_cpu.py pins that): the sampler cuts batches of >= 64 complexes into four
     // concurrent groups and smaller ones into groups of >= 16, so a call this large means the GPU is kept full by its
     // siblings and SM time, not the critical path, is what counts (gvp_ws.inl: NODE_ROWS; measured: headline, groups of 25:
     // 89.3 -> 92.1 ligands/s; gvp_ca with 16 ligands in one group: 33.1 with 32-row tiles, 29.9 with 64)

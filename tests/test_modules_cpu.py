@@ -206,6 +206,22 @@ def test_capacity_plan_properties():
     assert sum(waste) / len(waste) < 0.10
 
 
+def test_capacity_plan_batch_rounding_feeds_the_node_tile_rule():
+    """kpd_gvp_forward runs the GVP node / head kernels on full 64-row tiles for calls of >= 32 complexes (csrc/gvp.cu:
+    the GPU is kept full by the call's sibling sub-batches then) and on 32-row tiles below.  It sees the CAPACITY of the
+    bucket, so the rule rests on how plan_capacity rounds the batch: up to 22 real complexes (a single group, the GPU
+    not full) stay below 32, groups of 25 of the 100-ligand headline reach it."""
+    from keypoint_diffusion_b200 import ops
+    from keypoint_diffusion_b200.utils import split_bounds
+    gp = ops.GraphParams(ll_r=6.0, kl_k=7)
+    for B in range(1, 23):
+        assert ops.plan_capacity([20] * B, [20] * B, 322 * B, gp).key[0] < 32, B
+    for B in range(23, 70):
+        assert ops.plan_capacity([20] * B, [20] * B, 322 * B, gp).key[0] >= 32, B
+    bd = split_bounds(100, 4)
+    assert all(ops.plan_capacity([20] * (b - a), [20] * (b - a), 322 * (b - a), gp).key[0] >= 32 for a, b in zip(bd[:-1], bd[1:]))
+
+
 def test_reference_arm_weights_equal_product_arm():
     """bench.py --impl reference rebuilds the seeded weights without importing the product package (no .so in that
     process); they must be the weights the product arm's model_from_config draws."""
